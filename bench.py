@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the SdP-Net forward path (BASELINE.json metric: XL 224^2 bf16 forward images/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config XL|M|S] [--batch B]
+    python bench.py --impl reference ...      # the CPU arm (oracle port of the reference forward)
+
+One JSON line on stdout (rank 0).  A "step" is one forward over one batch of B synthetic images per
+GPU.  `value` = images/s with the batch already resident in HBM (device-timed with CUDA events,
+max over ranks); `e2e` = the same through the public module API with HOST inputs (pinned fp32
+images copied H2D and logits read back D2H inside the timed region); `roofline` = the dominant
+kernel family (the tcgen05 GEMM), timed live with CUDA events in an instrumented pass of the same
+forward; `cpu_baseline` = the oracle (a port of the reference's PyTorch forward) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+YAML = dict(n_head=8, activation="gelu", embedding_activation="none", conv_kernel_size=7, output_classes=1000,
+            conv_block_num=2, ff_multiplication_factor=4, max_image_size=[16, 16], max_num_registers=5,
+            conv_first=False, head_output_from_register=True, simple_mlp_output=False, output_head_bias=False,
+            normalize_qv=True, mixer_deptwise_bias=False, mixer_ffn_bias=False, conv_embedding=False)
+CONFIGS = {   # BASELINE.json configs[1..3]
+    "S": (dict(YAML, embedding_dim=512, num_blocks=12, patch_size=16), 256),
+    "M": (dict(YAML, embedding_dim=768, num_blocks=12, patch_size=16), 512),
+    "XL": (dict(YAML, embedding_dim=768, num_blocks=17, patch_size=14), 1024),
+}
+NUM_REGISTERS = 4   # R = 5
+METRIC = "SdP-Net XL 224^2 bf16 fwd images/sec"
+
+
+def workload_name(size, batch):
+    cfg = CONFIGS[size][0]
+    return (f"SdP-Net {size} ({cfg['num_blocks']} blocks, embed {cfg['embedding_dim']}, patch {cfg['patch_size']}, "
+            f"conv 7, 8 heads, R=5) 224^2 eval forward, batch {batch} per GPU, random-init weights (seed 0)")
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(burst=p["bf16_tflops"], sustained=p["bf16_tflops_sustained"], hbm=p["hbm_gbs"], src="measured")
+    except Exception:
+        return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [s.strip() for s in l.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        # keep the samples taken under load (upper half) for the median
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_forward_rate(cfg, batch, warm_batch=2, threads=None):
+    """images/s of the oracle (reference-forward port) on the host cores, fp32."""
+    import torch
+    import sdpnet_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.set_float32_matmul_precision("highest")
+    sd = O.synth_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    with torch.no_grad():
+        O.forward(sd, cfg, torch.randn(warm_batch, 3, 224, 224, generator=g), NUM_REGISTERS)
+        x = torch.randn(batch, 3, 224, 224, generator=g)
+        t0 = time.perf_counter()
+        O.forward(sd, cfg, x, NUM_REGISTERS)
+        dt = time.perf_counter() - t0
+    return batch / dt, threads, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU forward (oracle port; the reference is pure PyTorch and
+    cannot travel to the GPU box) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    import sdpnet_oracle as O
+    cfg, _ = CONFIGS[args.config]
+    sample = args.cpu_batch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.set_float32_matmul_precision("highest")
+    sd = O.synth_state_dict(cfg, seed=0)
+    x = torch.randn(sample, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.forward(sd, cfg, x[:2], NUM_REGISTERS)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.forward(sd, cfg, x, NUM_REGISTERS)
+        dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    batch = args.batch or CONFIGS[args.config][1]
+    line = {
+        "impl": "reference", "metric": METRIC if args.config == "XL" else f"SdP-Net {args.config} 224^2 fwd images/sec",
+        "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, batch), "num_registers": NUM_REGISTERS},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} images per step (fp32, oracle/sdpnet_oracle.py, torch CPU)"},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def gemm_flops_per_image(cfg, T, R):
+    C, m, nb, cbn, K, p = (cfg["embedding_dim"], cfg["ff_multiplication_factor"], cfg["num_blocks"],
+                           cfg["conv_block_num"], cfg["output_classes"], cfg["patch_size"])
+    S = T + R
+    enc = 6 * S * C * C + 2 * S * C * C + 4 * m * S * C * C
+    mixer = 2 * S * C * C + 16 * S * C * C          # GEMMs run over all S rows (register rows masked)
+    patch = 2 * T * C * 3 * p * p
+    head = 2 * C * K + 2 * K * K
+    return patch + nb * (cbn * mixer + enc) + enc + head
+
+
+def profile_families(eng, x, R, steps):
+    """Per-kernel-family device time of one forward (CUDA events around every op of the op-by-op
+    sequence -- same kernels, same order as sdp_forward)."""
+    import torch
+    import sdpnet_b200 as sdp
+    ops = sdp.ops
+    fam = {}
+    pending = []
+    orig = {}
+
+    def wrap(name, family):
+        fn = getattr(ops, name)
+        orig[name] = fn
+
+        def timed(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            pending.append((family, e0, e1))
+            return r
+        setattr(ops, name, timed)
+
+    for name, family in [("gemm", "gemm_bf16_tc"), ("layernorm_rows", "layernorm_rows"), ("ln_dwconv", "ln_dwconv"),
+                         ("attention", "attention"), ("im2col_patches", "other"), ("fill_registers", "other"),
+                         ("pool_ln", "other")]:
+        wrap(name, family)
+    try:
+        for _ in range(steps):
+            eng.forward(x, R - 1, staged=True)
+        torch.cuda.synchronize()
+    finally:
+        for name, fn in orig.items():
+            setattr(ops, name, fn)
+    counts = {}
+    for family, e0, e1 in pending:
+        fam[family] = fam.get(family, 0.0) + e0.elapsed_time(e1)
+        counts[family] = counts.get(family, 0) + 1
+    return {k: {"ms_per_step": v / steps, "launches_per_step": counts[k] // steps} for k, v in fam.items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--config", default="XL", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: BASELINE batch)")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import sdpnet_oracle as O
+    import sdpnet_b200 as sdp
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, default_batch = CONFIGS[args.config]
+    B = args.batch or default_batch
+    R = NUM_REGISTERS + 1
+    p = cfg["patch_size"]
+    T = (224 // p) ** 2
+
+    # weights: reference-layout state_dict -> nn.Module API (strict load) -> packed engine
+    sd = O.synth_state_dict(cfg, seed=0)
+    model = sdp.MainModel.from_dict(**cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().to(dev)
+    eng = model.engine()
+    del sd
+
+    # this rank's shard of the synthetic batch: host (pinned, fp32 like the reference's loaders) + device bf16
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+    x_dev = x_host.to(dev, non_blocking=True).bfloat16()
+    x_stage = torch.empty_like(x_host, device=dev)
+    logits_host = torch.empty(B, cfg["output_classes"], dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ---------------------------------------------------------
+    for _ in range(args.warmup):
+        eng.forward(x_dev, NUM_REGISTERS)
+    barrier()
+    sdp.ops.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            logits = eng.forward(x_dev, NUM_REGISTERS)
+        e1.record()
+        barrier()
+    launches = sdp.ops.launch_count()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms / args.steps
+    value = B * world * args.steps / (ms / 1e3)
+
+    # ---- end to end through the module API, host buffers in and out -------------------------
+    for _ in range(2):
+        x_stage.copy_(x_host, non_blocking=True)
+        logits_host.copy_(model(x_stage, NUM_REGISTERS), non_blocking=True)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        x_stage.copy_(x_host, non_blocking=True)
+        logits_host.copy_(model(x_stage, NUM_REGISTERS), non_blocking=True)
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    e2e = {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": "images/s",
+           "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": logits_host.numel() * 4 * world,
+           "api": "sdpnet_b200.MainModel.__call__ (one sdp_forward C-ABI call), pinned fp32 host images"}
+
+    # ---- off the timed path: gather logits + 2-scalar reduction (training_utilities.py:33,72-73) ----
+    if world > 1:
+        gathered = [torch.empty_like(logits) for _ in range(world)]
+        dist.all_gather(gathered, logits)
+        stats = torch.tensor([float(logits.argmax(-1).eq(0).sum()), float(B)], device=dev)
+        dist.all_reduce(stats)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    flops_img = O.flops_per_image(cfg, 224, 224, R)
+    line = {
+        "metric": METRIC if args.config == "XL" else f"SdP-Net {args.config} 224^2 bf16 fwd images/sec",
+        "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, B), "global_batch": B * world, "num_registers": NUM_REGISTERS,
+                   "parallelism": f"dp{world} (batch-sharded, no collective on the timed path)",
+                   "l2": "no explicit flush: per-step inputs (%d MB) and activations (%.1f GB) far exceed the 126 MB L2"
+                         % (x_dev.numel() * 2 >> 20, eng.buffers(B, 224 // p, 224 // p, R).nbytes() / 2 ** 30)},
+        "clocks": clk.summary(),
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "model_tflops": value / world * flops_img / 1e12,
+        "model_frac_of_sustained_peak": value / world * flops_img / 1e12 / peaks["sustained"],
+        "algorithmic_gflop_per_image": flops_img / 1e9,
+    }
+
+    if not args.no_profile:
+        fam = profile_families(eng, x_dev, R, 2)
+        gf = gemm_flops_per_image(cfg, T, R) * B
+        gms = fam["gemm_bf16_tc"]["ms_per_step"]
+        nl = fam["gemm_bf16_tc"]["launches_per_step"]
+        achieved = gf / (gms / 1e3) / 1e12
+        line["roofline"] = {
+            "kernel": "gemm_bf16_tc_kernel (tcgen05/TMEM/TMA)", "bound": "tensor", "achieved": achieved,
+            "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["sustained"], "traffic": None,
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
+            "launches_per_step": nl, "avg_launch_ms": gms / nl, "avg_launch_gflop": gf / nl / 1e9,
+            "share_of_step": gms / sum(v["ms_per_step"] for v in fam.values()),
+            "how": "CUDA events around every launch of an instrumented op-by-op pass of the same forward",
+        }
+        line["kernel_families_ms_per_step"] = {k: round(v["ms_per_step"], 3) for k, v in fam.items()}
+        # bandwidth-bound families, for the record (algorithmic bytes: read + write of [B,S,C] bf16)
+        S = T + R
+        if "ln_dwconv" in fam:
+            nbytes = 2 * B * T * cfg["embedding_dim"] * 2 * cfg["num_blocks"] * cfg["conv_block_num"]
+            line["ln_dwconv_gbs"] = nbytes / (fam["ln_dwconv"]["ms_per_step"] / 1e3) / 1e9
+        if "layernorm_rows" in fam:
+            nbytes = 2 * B * S * cfg["embedding_dim"] * 2 * fam["layernorm_rows"]["launches_per_step"]
+            line["layernorm_gbs"] = nbytes / (fam["layernorm_rows"]["ms_per_step"] / 1e3) / 1e9
+        line["hbm_peak_gbs"] = peaks["hbm"]
+
+    if not args.no_cpu_baseline:
+        v, cores, dt = cpu_forward_rate(cfg, args.cpu_batch)
+        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_batch} images, one fp32 forward of the oracle port "
+                                          f"(oracle/sdpnet_oracle.py) in {dt:.1f} s after a 2-image warm-up"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

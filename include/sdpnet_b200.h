@@ -1,0 +1,205 @@
+/*
+ * sdpnet_b200.h -- C-ABI of the B200-native (sm_100a) SdP-Net forward engine.
+ *
+ * The reference (y-akbal/SdP-Net) has no FFI layer: its hot path is `MainModel.forward`
+ * (reference model.py:129-149) calling PyTorch modules (reference layers.py).  The drop-in
+ * boundary is therefore the nn.Module API, mirrored by the Python package `sdp-net_b200/`,
+ * whose `forward` bodies call ONLY the entry points below (via ctypes, registered as
+ * `torch.ops.sdpnet_b200.*`).  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes; every pointer is a DEVICE pointer unless stated otherwise;
+ *     no ownership transfer: the caller allocates inputs, outputs and workspaces.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - return value: 0 = ok, non-zero = error; `sdp_last_error()` gives the message
+ *     (thread-local).  Nothing here ever computes on the CPU.
+ *   - dtypes: SDP_F32 / SDP_BF16.  Activations are token-major `[B, S = R + T, C]`:
+ *     rows 0..R-1 of every image are the register (CLS) tokens, rows R..S-1 the patches in
+ *     row-major (i*Gw + j) order -- the reference's `cat([register, x_flat])`
+ *     (layers.py:271-275) made permanent, so no transpose/cat/split ever runs.
+ *   - parameters (LN affine, biases, depthwise taps, tables) are fp32; GEMM weights are in
+ *     the compute dtype, `[N, K]` row-major (nn.Linear layout; 1x1 convs reshaped).
+ */
+#ifndef SDPNET_B200_H
+#define SDPNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDPNET_B200_ABI_VERSION 1
+
+typedef enum { SDP_F32 = 0, SDP_BF16 = 1 } sdp_dtype;
+
+/* reference model.py:13-24 (`activations` table) + training_utilities.py:91-92 (KeLu) */
+typedef enum {
+  SDP_ACT_NONE = 0,
+  SDP_ACT_RELU = 1,
+  SDP_ACT_GELU = 2,       /* exact erf form, nn.GELU() */
+  SDP_ACT_GELU_TANH = 3,
+  SDP_ACT_TANH = 4,
+  SDP_ACT_SIGMOID = 5,
+  SDP_ACT_LEAKY_RELU = 6, /* slope 0.01 */
+  SDP_ACT_SELU = 7,
+  SDP_ACT_KELU = 8        /* a = 3.5 */
+} sdp_act;
+
+int sdp_abi_version(void);
+const char *sdp_last_error(void);
+/* 1 if the current device is compute capability 10.x (tcgen05/TMEM/TMA path usable). */
+int sdp_device_ok(void);
+
+/* ---------------------------------------------------------------------------------------
+ * GEMM with fused epilogue:  out = epi(A[M,K] . W[N,K]^T)
+ * Replaces every nn.Linear / 1x1 nn.Conv2d / the patch conv on the path:
+ *   layers.py:34-42 (patcher), :79-92 (mixer pointwise + MLP), :282-284,301 (q/k/v/o),
+ *   :308 (FFN), :443-460 (head).
+ * bf16: TMA-fed tcgen05.mma, fp32 accumulators in TMEM, persistent warp-specialised kernel.
+ * fp32: CUDA-core FFMA kernel (verification mode, 1e-4 logits).
+ *
+ * Epilogue, per element (r, c), v = acc:
+ *   v += bias[c]                                   (bias != NULL)
+ *   if res_first:  v = act(v + res[rr, c])         (patch embedding: act(x + pos))
+ *   else:          v = act(v) + res[ro, c]         (residual != NULL)
+ *   out[ro, c] = v
+ * where  ro = seq_in ? (r / seq_in) * seq_out + seq_off + r % seq_in : r   (row remap, used to
+ * scatter the B*T patch rows into the [B, S, C] activation behind the R register rows),
+ * rr = res_mod ? r % res_mod : ro   (res_mod = T: broadcast the [T, C] position table), and
+ * rows with (ro % pass_seq) < pass_rows are left untouched when pass_seq != 0 (the mixers
+ * must not modify register rows; requires out == residual, i.e. in-place).
+ * --------------------------------------------------------------------------------------- */
+typedef struct {
+  const void *A;        int64_t lda;   /* [M, K], row pitch in elements */
+  const void *W;        int64_t ldw;   /* [N, K] */
+  const float *bias;                   /* [N] or NULL */
+  const void *residual; int64_t ldr;   /* or NULL */
+  void *out;            int64_t ldo;
+  int32_t M, N, K;
+  int32_t dtype;        /* of A and W */
+  int32_t out_dtype;
+  int32_t res_dtype;
+  int32_t act;
+  int32_t res_first;
+  int32_t res_mod;
+  int32_t seq_in, seq_out, seq_off;
+  int32_t pass_seq, pass_rows;
+} sdp_gemm_args;
+
+int sdp_gemm(const sdp_gemm_args *args, void *stream);
+
+/* im2col for kernel == stride patches (layers.py:34-42): x NCHW [B,3,H,W] (fp32 or bf16) ->
+ * A [B*T, ldA] with A[b*T + i*Gw + j, c*p*p + dy*p + dx] = x[b, c, i*p+dy, j*p+dx]; columns
+ * 3*p*p .. ldA-1 are zero-filled. */
+int sdp_im2col_patches(const void *x, int x_dtype, void *A, int a_dtype, int64_t ldA,
+                       int B, int H, int W, int p, void *stream);
+
+/* Register rows (layers.py:157,166 / :206-208): act[b, r, :] = table[r, :] for r < R. */
+int sdp_fill_registers(void *act, int dtype, const float *table, int B, int S, int R, int C,
+                       void *stream);
+
+/* Token LayerNorm over the last dim (nn.LayerNorm eps 1e-5: layers.py:280,307; channel-first
+ * LayerNorm eps 1e-6 seen token-major: layers.py:12-24,103). x,out: [M, C]. */
+int sdp_layernorm_rows(const void *x, int64_t ldx, const float *w, const float *b, void *out,
+                       int64_t ldo, int M, int C, float eps, int dtype, void *stream);
+
+/* Mixer front half (layers.py:102 up to the depthwise conv): per image, channel-LayerNorm
+ * (eps 1e-6, gamma/beta) of the patch rows, then depthwise kxk 'same' conv (zero halo applied
+ * AFTER the norm), taps wdw [C, k, k] fp32, optional bias bdw [C].  act,out: [B, S, C];
+ * register rows of `out` are written as zeros. */
+int sdp_ln_dwconv(const void *act, const float *gamma, const float *beta, const float *wdw,
+                  const float *bdw, void *out, int B, int Gh, int Gw, int C, int k, int R,
+                  float eps, int dtype, void *stream);
+
+/* Fused QK-LayerNorm + softmax attention (layers.py:282-300): qkv [B, S, 3C] with column
+ * blocks q | k | v, each [h, d]; q/k get a per-head LayerNorm(d) (eps, affine) when
+ * qn_w != NULL; out[b, s, head*d + :] = softmax(q k^T / sqrt(d)) v.  No mask, no dropout
+ * (eval).  bf16 with d % 16 == 0, d <= 128 runs on tensor cores; otherwise CUDA cores. */
+int sdp_attention(const void *qkv, const float *qn_w, const float *qn_b, const float *kn_w,
+                  const float *kn_b, void *out, int B, int S, int h, int d, float eps, int dtype,
+                  void *stream);
+
+/* Head front (layers.py:464 `registers.mean(-2)` + LN at :445/:449, or AdaptiveAvgPool at
+ * :457): out[b, :] = LN(mean over rows [row0, row0+nrows) of image b), LN skipped when
+ * ln_w == NULL.  act [B, S, C] -> out [B, ldo]. */
+int sdp_pool_ln(const void *act, int dtype, int B, int S, int C, int row0, int nrows,
+                const float *ln_w, const float *ln_b, float eps, void *out, int out_dtype,
+                int64_t ldo, void *stream);
+
+/* Layout bridges for the reference's NCHW module API (layers.py:271,314) and for
+ * `return_raw_outputs` (model.py:147-149).  x NCHW [B,C,Gh,Gw], reg [B,R,C], both fp32. */
+int sdp_tokens_from_nchw(const float *x, const float *reg, void *act, int dtype, int B, int C,
+                         int T, int R, void *stream);
+int sdp_tokens_to_nchw(const void *act, int dtype, float *x, float *reg, int B, int C, int T,
+                       int R, void *stream);
+
+/* Position-embedding add on token-major data (layers.py:162-168 / :205):
+ * act[b, R + t, :] = actfn(act[b, R + t, :] + pos[t, :]); pos is [T, C] fp32.  (MainModel fuses
+ * this into the patch GEMM epilogue; this entry serves the stand-alone EmbeddingLayer module.) */
+int sdp_embed_tokens(void *act, int dtype, const float *pos, int B, int T, int R, int C, int act_id,
+                     void *stream);
+
+/* Elementwise activation (embedding activation on a [n] buffer; test hook for epilogues). */
+int sdp_activation(const void *x, void *y, int64_t n, int act, int dtype, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Whole-model forward (model.py:129-149) sequenced on the device side of the ABI: one call
+ * enqueues every kernel of the forward on `stream`.
+ * --------------------------------------------------------------------------------------- */
+typedef struct {          /* one EncoderLayer, layers.py:216-257 */
+  const float *norm1_w, *norm1_b, *norm2_w, *norm2_b;
+  const float *qn_w, *qn_b, *kn_w, *kn_b;          /* NULL when normalize_qv=False */
+  const void *w_qkv;                               /* [3C, C] = cat(q_proj, k_proj, v_proj) */
+  const void *w_o;                                 /* [C, C] */
+  const void *w_ff1; const float *b_ff1;           /* [mC, C], [mC] */
+  const void *w_ff2; const float *b_ff2;           /* [C, mC], [C] */
+} sdp_encoder_weights;
+
+typedef struct {          /* one ConvMixer, layers.py:63-99 */
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const float *w_dw, *b_dw;                        /* [C,k,k], [C] or NULL */
+  const void *w_pw;  const float *b_pw;            /* [C, C] */
+  const void *w_mlp1; const float *b_mlp1;         /* [4C, C] */
+  const void *w_mlp2; const float *b_mlp2;         /* [C, 4C] */
+} sdp_mixer_weights;
+
+typedef struct {
+  int32_t dtype;                 /* compute dtype of activations and GEMM weights */
+  int32_t C, n_head, num_blocks, conv_block_num, ff_mult, conv_k, patch, classes;
+  int32_t act, embed_act, conv_first;
+  int32_t head_from_register, head_simple;
+  int32_t Kp;                    /* padded 3*p*p (pitch of w_patch and of the im2col buffer) */
+  int32_t Kc;                    /* padded `classes` (pitch of w_head2 and of the hidden buffer) */
+  const void *w_patch;           /* [C, Kp] */
+  const float *pos_table;        /* [T, C] fp32, precomputed for this grid (layers.py:158-163 / :205) */
+  const float *reg_table;        /* [R, C] fp32, the R selected register rows */
+  const sdp_encoder_weights *enc;   /* HOST array, num_blocks + 1 entries (last = final_block) */
+  const sdp_mixer_weights *mix;     /* HOST array, num_blocks * conv_block_num entries */
+  const float *head_ln_w, *head_ln_b;
+  const void *w_head1; const float *b_head1;       /* [classes, C] */
+  const void *w_head2; const float *b_head2;       /* [classes, Kc] or NULL */
+} sdp_model_desc;
+
+typedef struct {                 /* caller-allocated device workspaces */
+  void *act;      /* [B, S, C] */
+  void *norm;     /* [B, S, C] */
+  void *qkv;      /* [B, S, 3C] */
+  void *attn;     /* [B, S, C] */
+  void *hidden;   /* [B, S, max(ff_mult,4)*C] */
+  void *im2col;   /* [B*T, Kp] */
+  void *pooled;   /* [B, C] */
+  void *head_h;   /* [B, Kc] */
+} sdp_workspace;
+
+/* x: NCHW [B,3,H,W] in x_dtype; logits: fp32 [B, classes]. */
+int sdp_forward(const sdp_model_desc *m, const sdp_workspace *ws, const void *x, int x_dtype,
+                int B, int H, int W, int R, float *logits, void *stream);
+
+/* Number of kernels the engine launched since the counter was last reset (all streams). */
+int64_t sdp_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDPNET_B200_H */

@@ -31,7 +31,7 @@ import sdpnet_oracle as O  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
-TINY = dict(embedding_dim=32, n_head=4, num_blocks=2, patch_size=4, output_classes=10,
+TINY = dict(embedding_dim=32, n_head=2, num_blocks=2, patch_size=4, output_classes=10,
             max_image_size=[8, 8])
 YAML_FLAGS = dict(conv_first=False, head_output_from_register=True, simple_mlp_output=False,
                   output_head_bias=False, normalize_qv=True, mixer_deptwise_bias=False,
@@ -43,8 +43,8 @@ CASES = {
     # name: (cfg, H, W, B, num_registers, seed, stress, embed_weights)
     "yaml_r4_refinit": ({**TINY, **YAML_FLAGS, "conv_kernel_size": 3}, 16, 16, 3, 3, 0, False, True),
     "yaml_r5_stress": ({**TINY, **YAML_FLAGS, "conv_kernel_size": 7}, 32, 32, 3, 4, 1, True, False),
-    "yaml_r1_stress": ({**TINY, **YAML_FLAGS, "conv_kernel_size": 5}, 32, 28, 2, 0, 2, True, False),
-    "cifar_path": (dict(patch_size=2, embedding_dim=32, num_blocks=2, n_head=4,
+    "yaml_r1_stress": ({**TINY, **YAML_FLAGS, "conv_kernel_size": 5, "n_head": 4}, 32, 28, 2, 0, 2, True, False),
+    "cifar_path": (dict(patch_size=2, embedding_dim=32, num_blocks=2, n_head=2,
                         conv_kernel_size=5, conv_embedding=True, max_image_size=[8, 8],
                         head_output_from_register=False, output_classes=10,
                         conv_embedding_kernel_size=5, embedding_activation="gelu"),

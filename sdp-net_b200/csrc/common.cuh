@@ -1,0 +1,266 @@
+// Shared device/host helpers for the sdpnet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sdpnet_b200.h"
+
+namespace sdp {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- host-side error plumbing (thread-local message behind sdp_last_error) -------------
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define SDP_CHECK(cond, ...)          \
+  do {                                \
+    if (!(cond)) {                    \
+      sdp::set_error(__VA_ARGS__);    \
+      return 1;                       \
+    }                                 \
+  } while (0)
+
+#define SDP_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      sdp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                     __LINE__);                                                         \
+      return 2;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+#define SDP_LAUNCH_OK()                                                              \
+  do {                                                                               \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess) {                                                         \
+      sdp::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),     \
+                     __FILE__, __LINE__);                                            \
+      return 3;                                                                      \
+    }                                                                                \
+    sdp::count_launch();                                                             \
+  } while (0)
+
+static inline size_t dtype_size(int dt) { return dt == SDP_BF16 ? 2 : 4; }
+
+// ---- element load/store in either dtype --------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&p);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 p = *reinterpret_cast<__nv_bfloat162 *>(&u);
+  return __bfloat1622float2(p);
+}
+
+// ---- activations (reference model.py:13-24, training_utilities.py:91-92) -----------------
+// EXACT selects libdevice erff/tanhf (fp32 verification mode); otherwise the fast forms whose
+// error is far below one bf16 ulp of the result.
+__device__ __forceinline__ float gelu_erf_exact(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 7 FMA.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = fast_ex2(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-p, e, 1.0f);          // erf(|x|/sqrt2)
+  const float half_x = 0.5f * x;
+  return fmaf(fabsf(half_x), erf_abs, half_x);      // 0.5x + 0.5|x|erf(|x|/sqrt2) == 0.5x(1+erf(x/sqrt2))
+}
+
+__device__ __forceinline__ float kelu_f(float x) {
+  const float a = 3.5f;
+  if (x < -a) return 0.0f;
+  if (x > a) return x;
+  return 0.5f * x * (1.0f + x / a + 0.31830988618379067154f * sinf(x * (3.14159265358979323846f / a)));
+}
+
+template <bool EXACT>
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case SDP_ACT_NONE: return x;
+    case SDP_ACT_RELU: return fmaxf(x, 0.0f);
+    case SDP_ACT_GELU: return EXACT ? gelu_erf_exact(x) : gelu_erf_fast(x);
+    case SDP_ACT_GELU_TANH: {
+      const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+      return 0.5f * x * (1.0f + tanhf(u));
+    }
+    case SDP_ACT_TANH: return tanhf(x);
+    case SDP_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
+    case SDP_ACT_LEAKY_RELU: return x > 0.0f ? x : 0.01f * x;
+    case SDP_ACT_SELU: {
+      const float alpha = 1.6732632423543772848170429916717f;
+      const float scale = 1.0507009873554804934193349852946f;
+      return scale * (x > 0.0f ? x : alpha * expm1f(x));
+    }
+    case SDP_ACT_KELU: return kelu_f(x);
+    default: return x;
+  }
+}
+
+// ---- GEMM epilogue description (shared by the tcgen05 and the CUDA-core GEMM) -----------
+struct Epilogue {
+  const float *bias;
+  const void *residual;
+  void *out;
+  long long ldr, ldo;
+  int M, N;
+  int out_dtype, res_dtype;
+  int act, res_first, res_mod;
+  int seq_in, seq_out, seq_off;
+  int pass_seq, pass_rows;
+};
+
+struct RowMap {
+  long long ro, rr;   // output row, residual row
+  bool live;          // row < M and not a pass-through (register) row
+};
+
+__device__ __forceinline__ RowMap map_row(const Epilogue &e, int r) {
+  RowMap m;
+  m.live = r < e.M;
+  const int rc = m.live ? r : 0;
+  m.ro = e.seq_in ? (long long)(rc / e.seq_in) * e.seq_out + e.seq_off + rc % e.seq_in : rc;
+  m.rr = e.res_mod ? rc % e.res_mod : m.ro;
+  if (e.pass_seq && (int)(m.ro % e.pass_seq) < e.pass_rows) m.live = false;
+  return m;
+}
+
+// Finish NV consecutive columns [c0, c0+NV) of one row held in v[] (fp32 accumulators).
+// NV is a multiple of 8.  VEC = the pointers/pitches allow 16-byte accesses.
+template <int NV, bool EXACT, int ACT>   // ACT < 0: runtime e.act
+__device__ __forceinline__ void epilogue_row(const Epilogue &e, const RowMap &m, int c0, float *v,
+                                             bool vec) {
+  if (!m.live) return;
+  const int act = ACT < 0 ? e.act : ACT;
+  const bool full = vec && (c0 + NV <= e.N);
+  if (e.bias) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(e.bias + c0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (c0 + j < e.N) v[j] += __ldg(e.bias + c0 + j);
+    }
+  }
+  if (e.residual == nullptr || !e.res_first) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = apply_act<EXACT>(v[j], act);
+  }
+  if (e.residual) {
+    if (e.res_dtype == SDP_BF16) {
+      const bf16 *rp = reinterpret_cast<const bf16 *>(e.residual) + m.rr * e.ldr + c0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < NV; j += 8) {
+          const uint4 u = *reinterpret_cast<const uint4 *>(rp + j);
+          float2 f;
+          f = unpack_bf16x2(u.x); v[j] += f.x; v[j + 1] += f.y;
+          f = unpack_bf16x2(u.y); v[j + 2] += f.x; v[j + 3] += f.y;
+          f = unpack_bf16x2(u.z); v[j + 4] += f.x; v[j + 5] += f.y;
+          f = unpack_bf16x2(u.w); v[j + 6] += f.x; v[j + 7] += f.y;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+          if (c0 + j < e.N) v[j] += __bfloat162float(rp[j]);
+      }
+    } else {
+      const float *rp = reinterpret_cast<const float *>(e.residual) + m.rr * e.ldr + c0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < NV; j += 4) {
+          const float4 u = *reinterpret_cast<const float4 *>(rp + j);
+          v[j] += u.x; v[j + 1] += u.y; v[j + 2] += u.z; v[j + 3] += u.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+          if (c0 + j < e.N) v[j] += rp[j];
+      }
+    }
+    if (e.res_first) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = apply_act<EXACT>(v[j], act);
+    }
+  }
+  if (e.out_dtype == SDP_BF16) {
+    bf16 *op = reinterpret_cast<bf16 *>(e.out) + m.ro * e.ldo + c0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(v[j], v[j + 1]);
+        u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        u.z = pack_bf16x2(v[j + 4], v[j + 5]);
+        u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4 *>(op + j) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (c0 + j < e.N) op[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else {
+    float *op = reinterpret_cast<float *>(e.out) + m.ro * e.ldo + c0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 4)
+        *reinterpret_cast<float4 *>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (c0 + j < e.N) op[j] = v[j];
+    }
+  }
+}
+
+// Host: can the epilogue use 16-byte accesses for every row?
+static inline bool epilogue_vec_ok(const Epilogue &e) {
+  auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const size_t os = dtype_size(e.out_dtype), rs = dtype_size(e.res_dtype);
+  bool ok = al(e.out) && (e.ldo * os) % 16 == 0;
+  if (e.residual) ok = ok && al(e.residual) && (e.ldr * rs) % 16 == 0;
+  if (e.bias) ok = ok && al(e.bias);
+  return ok;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace sdp

@@ -1,0 +1,205 @@
+// Mixer front half: channel LayerNorm (eps 1e-6) fused with the depthwise k x k 'same' conv.
+// Reference: layers.py:102 `conv2d[0](layer_norm_1(x))` = layers.py:12-24 + :73-78.
+//
+// One CTA per image.  Phase 1: per-token mean / rstd over C (one warp per token, coalesced
+// 128-bit row reads) into shared memory.  Phase 2: for each slab of CH channels, stage the
+// normalised G x G plane with its zero halo in shared memory (the halo is literal 0 -- padding is
+// applied after the norm), then every thread owns one channel and slides an
+// XB-wide output window along image rows (k*(XB+k-1) shared loads per k*k*XB FMAs).
+// HBM traffic: the image's [T, C] slab is read once from HBM (phase 1), re-read from L2 (phase 2)
+// and written once: algorithmic bytes = 2 * T * C * sizeof(T) per image.
+#include "common.cuh"
+
+namespace sdp {
+
+constexpr int DW_THREADS = 256;
+constexpr int DW_XB = 8;
+
+template <typename T>
+__device__ __forceinline__ void token_stats(const T *__restrict__ row, int C, int lane, float eps, float &mean,
+                                            float &rstd) {
+  float s = 0.0f;
+  for (int c = lane; c < C; c += 32) s += to_f(row[c]);
+  mean = warp_sum(s) / (float)C;
+  float q = 0.0f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = to_f(row[c]) - mean;
+    q = fmaf(d, d, q);
+  }
+  rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+}
+template <>
+__device__ __forceinline__ void token_stats<bf16>(const bf16 *__restrict__ row, int C, int lane, float eps,
+                                                  float &mean, float &rstd) {
+  float s = 0.0f, q = 0.0f;
+  if ((C & 7) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    const uint4 *rv = reinterpret_cast<const uint4 *>(row);
+    const int nv = C >> 3;
+    for (int i = lane; i < nv; i += 32) {
+      const uint4 u = rv[i];
+      float2 f;
+      f = unpack_bf16x2(u.x); s += f.x + f.y;
+      f = unpack_bf16x2(u.y); s += f.x + f.y;
+      f = unpack_bf16x2(u.z); s += f.x + f.y;
+      f = unpack_bf16x2(u.w); s += f.x + f.y;
+    }
+    mean = warp_sum(s) / (float)C;
+    for (int i = lane; i < nv; i += 32) {
+      const uint4 u = rv[i];
+      float2 f;
+      float d;
+      f = unpack_bf16x2(u.x); d = f.x - mean; q = fmaf(d, d, q); d = f.y - mean; q = fmaf(d, d, q);
+      f = unpack_bf16x2(u.y); d = f.x - mean; q = fmaf(d, d, q); d = f.y - mean; q = fmaf(d, d, q);
+      f = unpack_bf16x2(u.z); d = f.x - mean; q = fmaf(d, d, q); d = f.y - mean; q = fmaf(d, d, q);
+      f = unpack_bf16x2(u.w); d = f.x - mean; q = fmaf(d, d, q); d = f.y - mean; q = fmaf(d, d, q);
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) s += to_f(row[c]);
+    mean = warp_sum(s) / (float)C;
+    for (int c = lane; c < C; c += 32) {
+      const float d = to_f(row[c]) - mean;
+      q = fmaf(d, d, q);
+    }
+  }
+  rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+}
+
+// KS > 0: compile-time kernel size with the sliding window; KS == 0: runtime k, one output at a time.
+template <typename T, int KS, int CH>
+__global__ void __launch_bounds__(DW_THREADS)
+ln_dwconv_kernel(const T *__restrict__ act, const float *__restrict__ gamma, const float *__restrict__ beta,
+                 const float *__restrict__ wdw, const float *__restrict__ bdw, T *__restrict__ out, int Gh, int Gw,
+                 int C, int krt, int R, float eps, int PW) {
+  extern __shared__ float smem[];
+  const int k = KS > 0 ? KS : krt;
+  const int lo = (k - 1) / 2;                       // 'same': left/top pad (k-1)/2, rest on the right/bottom
+  const int Tn = Gh * Gw, S = R + Tn;
+  const int PH = Gh + k - 1;
+  float *s_mean = smem;
+  float *s_rstd = smem + Tn;
+  float *tile = smem + 2 * Tn;                      // [PH][PW][CH]
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const T *xin = act + (long long)b * S * C;
+  T *xout = out + (long long)b * S * C;
+
+  // register rows of the output: zeros (the following GEMM passes registers through untouched)
+  for (int i = tid; i < R * C; i += DW_THREADS) xout[i] = from_f<T>(0.0f);
+
+  // ---- phase 1: token statistics ----
+  for (int t = warp; t < Tn; t += DW_THREADS / 32) {
+    float mean, rstd;
+    token_stats<T>(xin + (long long)(R + t) * C, C, lane, eps, mean, rstd);
+    if (lane == 0) { s_mean[t] = mean; s_rstd[t] = rstd; }
+  }
+  __syncthreads();
+
+  // ---- phase 2: channel slabs ----
+  constexpr int GROUPS = DW_THREADS / CH;
+  const int cl = tid % CH, grp = tid / CH;
+  for (int c0 = 0; c0 < C; c0 += CH) {
+    const int c = c0 + cl;
+    const bool cok = c < C;
+    const float g = cok ? __ldg(gamma + c) : 0.0f;
+    const float be = cok ? __ldg(beta + c) : 0.0f;
+    // stage the normalised plane with zero halo
+    for (int pix = grp; pix < PH * PW; pix += GROUPS) {
+      const int py = pix / PW, px = pix % PW;
+      const int iy = py - lo, ix = px - lo;
+      float v = 0.0f;
+      if (cok && iy >= 0 && iy < Gh && ix >= 0 && ix < Gw) {
+        const int t = iy * Gw + ix;
+        v = (to_f(xin[(long long)(R + t) * C + c]) - s_mean[t]) * s_rstd[t] * g + be;
+      }
+      tile[pix * CH + cl] = v;
+    }
+    __syncthreads();
+    const float bias = (cok && bdw) ? __ldg(bdw + c) : 0.0f;
+    if (KS > 0) {
+      float w[KS > 0 ? KS * KS : 1];
+#pragma unroll
+      for (int i = 0; i < KS * KS; ++i) w[i] = cok ? __ldg(wdw + (long long)c * KS * KS + i) : 0.0f;
+      const int xchunks = (Gw + DW_XB - 1) / DW_XB;
+      for (int item = grp; item < Gh * xchunks; item += GROUPS) {
+        const int y = item / xchunks, x0 = (item % xchunks) * DW_XB;
+        float acc[DW_XB];
+#pragma unroll
+        for (int i = 0; i < DW_XB; ++i) acc[i] = bias;
+#pragma unroll
+        for (int dy = 0; dy < KS; ++dy) {
+          const float *trow = tile + ((y + dy) * PW + x0) * CH + cl;
+          float win[DW_XB + KS - 1];
+#pragma unroll
+          for (int xx = 0; xx < DW_XB + KS - 1; ++xx) win[xx] = trow[xx * CH];
+#pragma unroll
+          for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+            for (int i = 0; i < DW_XB; ++i) acc[i] = fmaf(win[i + dx], w[dy * KS + dx], acc[i]);
+        }
+        if (cok) {
+#pragma unroll
+          for (int i = 0; i < DW_XB; ++i)
+            if (x0 + i < Gw) xout[(long long)(R + y * Gw + x0 + i) * C + c] = from_f<T>(acc[i]);
+        }
+      }
+    } else {
+      for (int t = grp; t < Tn; t += GROUPS) {
+        const int y = t / Gw, x = t % Gw;
+        float acc = bias;
+        for (int dy = 0; dy < k; ++dy)
+          for (int dx = 0; dx < k; ++dx)
+            acc = fmaf(tile[((y + dy) * PW + x + dx) * CH + cl],
+                       cok ? __ldg(wdw + ((long long)c * k + dy) * k + dx) : 0.0f, acc);
+        if (cok) xout[(long long)(R + t) * C + c] = from_f<T>(acc);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int KS>
+static int launch_dw(const void *act, const float *gamma, const float *beta, const float *wdw, const float *bdw,
+                     void *out, int B, int Gh, int Gw, int C, int k, int R, float eps, cudaStream_t st) {
+  constexpr int CH = 32;
+  const int PW = ((Gw + DW_XB - 1) / DW_XB) * DW_XB + k - 1;
+  const int PH = Gh + k - 1;
+  const size_t smem = (size_t)(2 * Gh * Gw + (size_t)PH * PW * CH) * sizeof(float);
+  SDP_CHECK(smem <= 220 * 1024, "sdp_ln_dwconv: grid %dx%d with k=%d needs %zu B of shared memory", Gh, Gw, k,
+            smem);
+  auto kern = ln_dwconv_kernel<T, KS, CH>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  kern<<<B, DW_THREADS, smem, st>>>((const T *)act, gamma, beta, wdw, bdw, (T *)out, Gh, Gw, C, k, R, eps, PW);
+  SDP_LAUNCH_OK();
+  return 0;
+}
+
+template <typename T>
+static int dispatch_dw(const void *act, const float *gamma, const float *beta, const float *wdw, const float *bdw,
+                       void *out, int B, int Gh, int Gw, int C, int k, int R, float eps, cudaStream_t st) {
+  switch (k) {
+    case 3: return launch_dw<T, 3>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, st);
+    case 5: return launch_dw<T, 5>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, st);
+    case 7: return launch_dw<T, 7>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, st);
+    default: return launch_dw<T, 0>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, st);
+  }
+}
+
+}  // namespace sdp
+
+using namespace sdp;
+
+extern "C" int sdp_ln_dwconv(const void *act, const float *gamma, const float *beta, const float *wdw,
+                             const float *bdw, void *out, int B, int Gh, int Gw, int C, int k, int R, float eps,
+                             int dtype, void *stream) {
+  SDP_CHECK(act && gamma && beta && wdw && out, "sdp_ln_dwconv: null pointer");
+  SDP_CHECK(B > 0 && Gh > 0 && Gw > 0 && C > 0 && k > 0 && R >= 0, "sdp_ln_dwconv: bad sizes");
+  SDP_CHECK(act != out, "sdp_ln_dwconv: must not run in place (spatial neighbours are read)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == SDP_BF16) return dispatch_dw<bf16>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, st);
+  SDP_CHECK(dtype == SDP_F32, "sdp_ln_dwconv: unknown dtype %d", dtype);
+  return dispatch_dw<float>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, st);
+}

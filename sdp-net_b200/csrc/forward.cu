@@ -1,0 +1,152 @@
+// ABI housekeeping + the whole-model forward (reference model.py:129-149) sequenced behind the
+// C-ABI: one call enqueues every kernel of the forward on the caller's stream.  No allocation,
+// no synchronisation, no host<->device copies happen here.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace sdp {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace sdp
+
+using namespace sdp;
+
+extern "C" int sdp_abi_version(void) { return SDPNET_B200_ABI_VERSION; }
+extern "C" const char *sdp_last_error(void) { return g_err; }
+extern "C" int64_t sdp_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+extern "C" int sdp_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+namespace {
+
+struct Ctx {
+  const sdp_model_desc *m;
+  const sdp_workspace *ws;
+  int B, S, T, R, Gh, Gw;
+  void *st;
+};
+
+int gemm(const Ctx &c, const void *A, long long lda, const void *W, long long ldw, const float *bias, int M, int N,
+         int K, int act, const void *res, void *out, long long ldo, int out_dtype, bool mask_regs) {
+  sdp_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.bias = bias;
+  a.residual = res; a.ldr = ldo; a.out = out; a.ldo = ldo;
+  a.M = M; a.N = N; a.K = K;
+  a.dtype = c.m->dtype; a.out_dtype = out_dtype; a.res_dtype = c.m->dtype;
+  a.act = act;
+  if (mask_regs && c.R > 0) { a.pass_seq = c.S; a.pass_rows = c.R; }
+  return sdp_gemm(&a, c.st);
+}
+
+// layers.py:259-316
+int encoder(const Ctx &c, const sdp_encoder_weights &w) {
+  const sdp_model_desc &m = *c.m;
+  const int C = m.C, M = c.B * c.S, dt = m.dtype, F = m.ff_mult * C;
+  if (int rc = sdp_layernorm_rows(c.ws->act, C, w.norm1_w, w.norm1_b, c.ws->norm, C, M, C, 1e-5f, dt, c.st)) return rc;
+  if (int rc = gemm(c, c.ws->norm, C, w.w_qkv, C, nullptr, M, 3 * C, C, SDP_ACT_NONE, nullptr, c.ws->qkv, 3 * C, dt, false)) return rc;
+  if (int rc = sdp_attention(c.ws->qkv, w.qn_w, w.qn_b, w.kn_w, w.kn_b, c.ws->attn, c.B, c.S, m.n_head, C / m.n_head, 1e-5f, dt, c.st)) return rc;
+  if (int rc = gemm(c, c.ws->attn, C, w.w_o, C, nullptr, M, C, C, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, false)) return rc;
+  if (int rc = sdp_layernorm_rows(c.ws->act, C, w.norm2_w, w.norm2_b, c.ws->norm, C, M, C, 1e-5f, dt, c.st)) return rc;
+  if (int rc = gemm(c, c.ws->norm, C, w.w_ff1, C, w.b_ff1, M, F, C, m.act, nullptr, c.ws->hidden, F, dt, false)) return rc;
+  return gemm(c, c.ws->hidden, F, w.w_ff2, F, w.b_ff2, M, C, F, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, false);
+}
+
+// layers.py:101-104
+int mixer(const Ctx &c, const sdp_mixer_weights &w) {
+  const sdp_model_desc &m = *c.m;
+  const int C = m.C, M = c.B * c.S, dt = m.dtype;
+  if (int rc = sdp_ln_dwconv(c.ws->act, w.ln1_g, w.ln1_b, w.w_dw, w.b_dw, c.ws->norm, c.B, c.Gh, c.Gw, C, m.conv_k, c.R, 1e-6f, dt, c.st)) return rc;
+  if (int rc = gemm(c, c.ws->norm, C, w.w_pw, C, w.b_pw, M, C, C, m.act, c.ws->act, c.ws->act, C, dt, true)) return rc;
+  if (int rc = sdp_layernorm_rows(c.ws->act, C, w.ln2_g, w.ln2_b, c.ws->norm, C, M, C, 1e-6f, dt, c.st)) return rc;
+  if (int rc = gemm(c, c.ws->norm, C, w.w_mlp1, C, w.b_mlp1, M, 4 * C, C, m.act, nullptr, c.ws->hidden, 4 * C, dt, false)) return rc;
+  return gemm(c, c.ws->hidden, 4 * C, w.w_mlp2, 4 * C, w.b_mlp2, M, C, 4 * C, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, true);
+}
+
+}  // namespace
+
+extern "C" int sdp_forward(const sdp_model_desc *m, const sdp_workspace *ws, const void *x, int x_dtype, int B,
+                           int H, int W, int R, float *logits, void *stream) {
+  SDP_CHECK(m && ws && x && logits, "sdp_forward: null argument");
+  SDP_CHECK(B > 0 && R >= 1, "sdp_forward: need B > 0 and R >= 1 (got B=%d R=%d)", B, R);
+  SDP_CHECK(m->patch > 0 && H % m->patch == 0 && W % m->patch == 0,
+            "sdp_forward: image %dx%d not divisible by patch %d", H, W, m->patch);
+  SDP_CHECK(m->C % m->n_head == 0, "sdp_forward: embedding_dim %d not divisible by n_head %d", m->C, m->n_head);
+  Ctx c;
+  c.m = m; c.ws = ws; c.B = B; c.R = R; c.st = stream;
+  c.Gh = H / m->patch; c.Gw = W / m->patch;
+  c.T = c.Gh * c.Gw; c.S = c.T + R;
+  const int C = m->C, dt = m->dtype, Kc3 = 3 * m->patch * m->patch;
+
+  // patcher + position table + embedding activation, scattered behind the register rows
+  // (layers.py:34-42, :152-168 / :202-209)
+  if (int rc = sdp_im2col_patches(x, x_dtype, ws->im2col, dt, m->Kp, B, H, W, m->patch, stream)) return rc;
+  {
+    sdp_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.A = ws->im2col; a.lda = m->Kp; a.W = m->w_patch; a.ldw = m->Kp;
+    a.residual = m->pos_table; a.ldr = C; a.res_dtype = SDP_F32; a.res_first = 1; a.res_mod = c.T;
+    a.out = ws->act; a.ldo = C; a.M = B * c.T; a.N = C; a.K = Kc3;
+    a.dtype = dt; a.out_dtype = dt; a.act = m->embed_act;
+    a.seq_in = c.T; a.seq_out = c.S; a.seq_off = R;
+    if (int rc = sdp_gemm(&a, stream)) return rc;
+  }
+  if (int rc = sdp_fill_registers(ws->act, dt, m->reg_table, B, c.S, R, C, stream)) return rc;
+
+  for (int i = 0; i < m->num_blocks; ++i) {            // model.py:139-140, layers.py:377-386
+    if (m->conv_first)
+      for (int j = 0; j < m->conv_block_num; ++j)
+        if (int rc = mixer(c, m->mix[i * m->conv_block_num + j])) return rc;
+    if (int rc = encoder(c, m->enc[i])) return rc;
+    if (!m->conv_first)
+      for (int j = 0; j < m->conv_block_num; ++j)
+        if (int rc = mixer(c, m->mix[i * m->conv_block_num + j])) return rc;
+  }
+  if (int rc = encoder(c, m->enc[m->num_blocks])) return rc;   // model.py:143
+
+  // classification head (layers.py:443-465)
+  const int K = m->classes;
+  if (m->head_from_register) {
+    if (int rc = sdp_pool_ln(ws->act, dt, B, c.S, C, 0, R, m->head_ln_w, m->head_ln_b, 1e-5f, ws->pooled, dt, C, stream)) return rc;
+  } else {
+    if (int rc = sdp_pool_ln(ws->act, dt, B, c.S, C, R, c.T, nullptr, nullptr, 0.0f, ws->pooled, dt, C, stream)) return rc;
+  }
+  const bool two = m->head_from_register && !m->head_simple;
+  {
+    sdp_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.A = ws->pooled; a.lda = C; a.W = m->w_head1; a.ldw = C; a.bias = m->b_head1;
+    a.M = B; a.N = K; a.K = C; a.dtype = dt;
+    if (two) { a.out = ws->head_h; a.ldo = m->Kc; a.out_dtype = dt; a.act = SDP_ACT_TANH; }
+    else { a.out = logits; a.ldo = K; a.out_dtype = SDP_F32; a.act = SDP_ACT_NONE; }
+    if (int rc = sdp_gemm(&a, stream)) return rc;
+  }
+  if (two) {
+    sdp_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.A = ws->head_h; a.lda = m->Kc; a.W = m->w_head2; a.ldw = m->Kc; a.bias = m->b_head2;
+    a.M = B; a.N = K; a.K = K; a.dtype = dt;
+    a.out = logits; a.ldo = K; a.out_dtype = SDP_F32; a.act = SDP_ACT_NONE;
+    if (int rc = sdp_gemm(&a, stream)) return rc;
+  }
+  return 0;
+}

@@ -1,0 +1,393 @@
+// bf16 GEMM on the 5th-gen tensor cores:  out = epi(A[M,K] . W[N,K]^T), fp32 accumulate in TMEM.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, STAGES-deep ring)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128 x BLOCK_N x 16; owns TMEM alloc)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> bias/act/residual -> global), double-buffered
+//                              TMEM accumulators so tile i's epilogue overlaps tile i+1's MMAs.
+// Replaces every nn.Linear / 1x1 conv of the reference forward (see include/sdpnet_b200.h).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace sdp {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;      // 64 bf16 = 128 bytes = one swizzle-128B atom row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {   // ~4 s at 2 GHz
+      printf("sdp gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t *r = reinterpret_cast<uint32_t *>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B)
+//   [46,48) version=1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
+};
+
+template <int BN, int STAGES, int ACT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const Epilogue epi, const int K, const int vec_ok) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  // swizzle-128B tiles need 1024-byte alignment
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + L::BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + L::BAR_OFF + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 2 * BN;   // 128 / 256 / 512: powers of two >= 32
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);        // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t *>(tmem_slot))),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (epi.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (epi.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BLOCK_M;
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
+          tma_load_2d(sa + L::A_BYTES, &tmW, full_bar(stage), kb * BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      if (lane == 0) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);             // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 bytes (16 bf16) inside the 128B swizzle atom: +2 in the >>4 address field
+            tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(empty_bar(stage));                   // smem slot free once these MMAs retire
+          if (kb == num_kb - 1) tc_commit(tfull_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue =================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * BLOCK_M;
+      const int n0 = (tile % n_tiles) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const RowMap rm = map_row(epi, m0 + quad * 32 + lane);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (n0 + c < epi.N) epilogue_row<32, false, ACT>(epi, rm, n0 + c, v, vec_ok != 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Host side: tensor-map cache + launcher
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void *ptr;
+  uint64_t rows, cols, pitch;
+  uint32_t box_rows;
+  bool operator==(const MapKey &o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && pitch == o.pitch && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey &k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1315423911u ^ k.rows;
+    h = h * 1315423911u ^ k.cols;
+    h = h * 1315423911u ^ k.pitch;
+    h = h * 1315423911u ^ k.box_rows;
+    return h;
+  }
+};
+
+// [rows, cols] bf16 row-major with `pitch` elements per row; box = box_rows x 64, 128B swizzle.
+static int get_tensor_map(const void *ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows,
+                          CUtensorMap *out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, rows, cols, pitch, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  SDP_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  SDP_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand not 16-byte aligned");
+  SDP_CHECK((pitch * 2) % 16 == 0, "GEMM operand row pitch (%llu elements) not a multiple of 8",
+            (unsigned long long)pitch);
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {pitch * 2};
+  cuuint32_t box[2] = {BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SDP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+  }
+  *out = m;
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int BN, int STAGES, int ACT>
+static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tw, const Epilogue &e, int K, cudaStream_t st) {
+  using L = SmemLayout<BN, STAGES>;
+  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT>;
+  static bool configured = false;
+  if (!configured) {
+    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int tiles = ((e.M + BLOCK_M - 1) / BLOCK_M) * ((e.N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, L::TOTAL, st>>>(ta, tw, e, K, epilogue_vec_ok(e) ? 1 : 0);
+  SDP_LAUNCH_OK();
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_tc_act(const CUtensorMap &ta, const CUtensorMap &tw, const Epilogue &e, int K,
+                         cudaStream_t st) {
+  if (e.act == SDP_ACT_NONE) return launch_tc<BN, STAGES, SDP_ACT_NONE>(ta, tw, e, K, st);
+  if (e.act == SDP_ACT_GELU) return launch_tc<BN, STAGES, SDP_ACT_GELU>(ta, tw, e, K, st);
+  return launch_tc<BN, STAGES, -1>(ta, tw, e, K, st);
+}
+
+int gemm_bf16_tc(const sdp_gemm_args &a, const Epilogue &e, cudaStream_t st) {
+  // BLOCK_N minimising padded columns; ties -> the larger tile
+  int bn = 256;
+  {
+    long best = -1;
+    const int cand[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      const long padded = (long)((a.N + cand[i] - 1) / cand[i]) * cand[i];
+      if (best < 0 || padded < best) { best = padded; bn = cand[i]; }
+    }
+  }
+  CUtensorMap ta, tw;
+  if (int rc = get_tensor_map(a.A, a.M, a.K, a.lda, BLOCK_M, &ta)) return rc;
+  if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, bn, &tw)) return rc;
+  switch (bn) {
+    case 256: return launch_tc_act<256, 4>(ta, tw, e, a.K, st);
+    case 128: return launch_tc_act<128, 6>(ta, tw, e, a.K, st);
+    default: return launch_tc_act<64, 8>(ta, tw, e, a.K, st);
+  }
+}
+
+}  // namespace sdp

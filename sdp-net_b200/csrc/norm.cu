@@ -1,0 +1,416 @@
+// Bandwidth-bound row kernels: token LayerNorm, register fill, pooled head front, layout bridges,
+// patch im2col, elementwise activation.  One pass over HBM each, 128-bit accesses where the shape
+// allows.  Reference call sites are cited per entry point in include/sdpnet_b200.h.
+#include "common.cuh"
+
+namespace sdp {
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm over the last dim, one warp per row, row cached in registers (single HBM read).
+// ---------------------------------------------------------------------------------------
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float *p, float *v) {
+    const float4 u = *reinterpret_cast<const float4 *>(p);
+    v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+  }
+  __device__ static void store(float *p, const float *v) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  __device__ static void load(const bf16 *p, float *v) {
+    const uint4 u = *reinterpret_cast<const uint4 *>(p);
+    float2 f;
+    f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+    f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+    f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+    f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+  }
+  __device__ static void store(bf16 *p, const float *v) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4 *>(p) = u;
+  }
+};
+
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256)
+ln_rows_vec_kernel(const T *__restrict__ x, long long ldx, const float *__restrict__ w,
+                   const float *__restrict__ b, T *__restrict__ out, long long ldo, int M, int C, float eps) {
+  constexpr int EPV = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nvec = C / EPV;
+  const T *xr = x + (long long)row * ldx;
+  float v[VPL][EPV];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int iv = lane + 32 * i;
+    if (iv < nvec) {
+      Vec<T>::load(xr + iv * EPV, v[i]);
+#pragma unroll
+      for (int j = 0; j < EPV; ++j) s += v[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int j = 0; j < EPV; ++j) {
+        const float d = v[i][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+  T *orow = out + (long long)row * ldo;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int iv = lane + 32 * i;
+    if (iv < nvec) {
+      float y[EPV];
+#pragma unroll
+      for (int j = 0; j < EPV; ++j) {
+        const int c = iv * EPV + j;
+        float t = (v[i][j] - mean) * rstd;
+        if (w) t *= __ldg(w + c);
+        if (b) t += __ldg(b + c);
+        y[j] = t;
+      }
+      Vec<T>::store(orow + iv * EPV, y);
+    }
+  }
+}
+
+// any C / alignment: three passes over the (L1-resident) row
+template <typename T>
+__global__ void __launch_bounds__(256)
+ln_rows_generic_kernel(const T *__restrict__ x, long long ldx, const float *__restrict__ w,
+                       const float *__restrict__ b, T *__restrict__ out, long long ldo, int M, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const T *xr = x + (long long)row * ldx;
+  float s = 0.0f;
+  for (int c = lane; c < C; c += 32) s += to_f(xr[c]);
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.0f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = to_f(xr[c]) - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+  T *orow = out + (long long)row * ldo;
+  for (int c = lane; c < C; c += 32) {
+    float t = (to_f(xr[c]) - mean) * rstd;
+    if (w) t *= __ldg(w + c);
+    if (b) t += __ldg(b + c);
+    orow[c] = from_f<T>(t);
+  }
+}
+
+template <typename T>
+static int launch_ln_rows(const void *x, long long ldx, const float *w, const float *b, void *out, long long ldo,
+                          int M, int C, float eps, cudaStream_t st) {
+  constexpr int EPV = Vec<T>::N;
+  const T *xp = reinterpret_cast<const T *>(x);
+  T *op = reinterpret_cast<T *>(out);
+  const int wpb = 8;
+  const dim3 grid((M + wpb - 1) / wpb), block(32 * wpb);
+  const bool vec = C % EPV == 0 && (ldx * sizeof(T)) % 16 == 0 && (ldo * sizeof(T)) % 16 == 0 &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const int need = vec ? (C / EPV + 31) / 32 : 99;
+#define LN_CASE(V)                                                                             \
+  if (need <= V) {                                                                             \
+    ln_rows_vec_kernel<T, V><<<grid, block, 0, st>>>(xp, ldx, w, b, op, ldo, M, C, eps);       \
+    SDP_LAUNCH_OK();                                                                           \
+    return 0;                                                                                  \
+  }
+  LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(6) LN_CASE(8)
+#undef LN_CASE
+  ln_rows_generic_kernel<T><<<grid, block, 0, st>>>(xp, ldx, w, b, op, ldo, M, C, eps);
+  SDP_LAUNCH_OK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void fill_registers_kernel(T *act, const float *__restrict__ table, int B, int S, int R, int C) {
+  const long long n = (long long)B * R * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int r = (i / C) % R;
+    const long long b = i / ((long long)C * R);
+    act[(b * S + r) * C + c] = from_f<T>(__ldg(table + r * C + c));
+  }
+}
+
+// out[b, :] = LN(mean_{rows}(act[b, row0:row0+nrows, :])); one CTA per image
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256)
+pool_ln_kernel(const T *__restrict__ act, int S, int C, int row0, int nrows, const float *__restrict__ lw,
+               const float *__restrict__ lb, float eps, TO *__restrict__ out, long long ldo) {
+  extern __shared__ float pooled[];   // [C] + 32 scratch
+  float *red = pooled + C;
+  const int b = blockIdx.x;
+  const T *base = act + ((long long)b * S + row0) * C;
+  float s = 0.0f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.0f;
+    for (int r = 0; r < nrows; ++r) a += to_f(base[(long long)r * C + c]);
+    a /= (float)nrows;
+    pooled[c] = a;
+    s += a;
+  }
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.0f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    return t;
+  };
+  float mean = 0.0f, rstd = 1.0f;
+  if (lw) {
+    mean = block_sum(s) / (float)C;
+    float q = 0.0f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float d = pooled[c] - mean;
+      q = fmaf(d, d, q);
+    }
+    rstd = 1.0f / sqrtf(block_sum(q) / (float)C + eps);
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = pooled[c];
+    if (lw) {
+      t = (t - mean) * rstd * __ldg(lw + c);
+      if (lb) t += __ldg(lb + c);
+    }
+    out[(long long)b * ldo + c] = from_f<TO>(t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// NCHW fp32 <-> token-major bridges (32x32 smem transpose per image)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void tokens_from_nchw_kernel(const float *__restrict__ x, T *__restrict__ act, int C, int T_, int R) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T_) ? x[((long long)b * C + c) * T_ + t] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T_ && c < C) act[((long long)b * (R + T_) + R + t) * C + c] = from_f<T>(tile[threadIdx.x][i]);
+  }
+}
+template <typename T>
+__global__ void tokens_to_nchw_kernel(const T *__restrict__ act, float *__restrict__ x, int C, int T_, int R) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < T_ && c < C) ? to_f(act[((long long)b * (R + T_) + R + t) * C + c]) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (c < C && t < T_) x[((long long)b * C + c) * T_ + t] = tile[threadIdx.x][i];
+  }
+}
+template <typename T, bool TO_ACT>
+__global__ void registers_copy_kernel(T *act, float *reg, int B, int S, int R, int C) {
+  const long long n = (long long)B * R * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int r = (i / C) % R;
+    const long long b = i / ((long long)C * R);
+    T *a = act + (b * S + r) * C + c;
+    if (TO_ACT) *a = from_f<T>(reg[i]);
+    else reg[i] = to_f(*a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void im2col_kernel(const TI *__restrict__ x, TO *__restrict__ A, long long ldA, int B, int H, int W,
+                              int p, int Gh, int Gw) {
+  const int Kc = 3 * p * p;
+  const long long n = (long long)B * Gh * Gw * ldA;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int col = i % ldA;
+    const long long row = i / ldA;
+    float v = 0.0f;
+    if (col < Kc) {
+      const int dx = col % p, dy = (col / p) % p, c = col / (p * p);
+      const int j = row % Gw, ii = (row / Gw) % Gh;
+      const long long b = row / ((long long)Gw * Gh);
+      v = to_f(x[((b * 3 + c) * H + (ii * p + dy)) * (long long)W + (j * p + dx)]);
+    }
+    A[i] = from_f<TO>(v);
+  }
+}
+
+template <typename T, bool EXACT>
+__global__ void embed_tokens_kernel(T *__restrict__ act, const float *__restrict__ pos, int B, int T_, int R, int C,
+                                    int act_id) {
+  const long long n = (long long)B * T_ * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int t = (i / C) % T_;
+    const long long b = i / ((long long)C * T_);
+    T *a = act + ((b * (R + T_) + R + t) * C + c);
+    *a = from_f<T>(apply_act<EXACT>(to_f(*a) + __ldg(pos + (long long)t * C + c), act_id));
+  }
+}
+
+template <typename T, bool EXACT>
+__global__ void activation_kernel(const T *__restrict__ x, T *__restrict__ y, long long n, int act) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = from_f<T>(apply_act<EXACT>(to_f(x[i]), act));
+}
+
+static inline int grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  return (int)(g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g));
+}
+
+}  // namespace sdp
+
+using namespace sdp;
+
+extern "C" int sdp_layernorm_rows(const void *x, int64_t ldx, const float *w, const float *b, void *out,
+                                  int64_t ldo, int M, int C, float eps, int dtype, void *stream) {
+  SDP_CHECK(x && out && M > 0 && C > 0, "sdp_layernorm_rows: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == SDP_BF16) return launch_ln_rows<bf16>(x, ldx, w, b, out, ldo, M, C, eps, st);
+  SDP_CHECK(dtype == SDP_F32, "sdp_layernorm_rows: unknown dtype %d", dtype);
+  return launch_ln_rows<float>(x, ldx, w, b, out, ldo, M, C, eps, st);
+}
+
+extern "C" int sdp_fill_registers(void *act, int dtype, const float *table, int B, int S, int R, int C,
+                                  void *stream) {
+  SDP_CHECK(act && table && B > 0 && R > 0 && R <= S && C > 0, "sdp_fill_registers: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int g = grid_for((long long)B * R * C);
+  if (dtype == SDP_BF16) fill_registers_kernel<bf16><<<g, 256, 0, st>>>((bf16 *)act, table, B, S, R, C);
+  else fill_registers_kernel<float><<<g, 256, 0, st>>>((float *)act, table, B, S, R, C);
+  SDP_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sdp_pool_ln(const void *act, int dtype, int B, int S, int C, int row0, int nrows,
+                           const float *ln_w, const float *ln_b, float eps, void *out, int out_dtype,
+                           int64_t ldo, void *stream) {
+  SDP_CHECK(act && out && B > 0 && nrows > 0 && row0 >= 0 && row0 + nrows <= S, "sdp_pool_ln: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t sm = (C + 32) * sizeof(float);
+  SDP_CHECK(sm <= 48 * 1024, "sdp_pool_ln: C=%d too large", C);
+#define POOL(TI, TO) \
+  pool_ln_kernel<TI, TO><<<B, 256, sm, st>>>((const TI *)act, S, C, row0, nrows, ln_w, ln_b, eps, (TO *)out, ldo)
+  if (dtype == SDP_BF16 && out_dtype == SDP_BF16) POOL(bf16, bf16);
+  else if (dtype == SDP_BF16) POOL(bf16, float);
+  else if (out_dtype == SDP_BF16) POOL(float, bf16);
+  else POOL(float, float);
+#undef POOL
+  SDP_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sdp_tokens_from_nchw(const float *x, const float *reg, void *act, int dtype, int B, int C, int T,
+                                    int R, void *stream) {
+  SDP_CHECK(x && act && B > 0 && C > 0 && T > 0 && R >= 0, "sdp_tokens_from_nchw: bad arguments");
+  SDP_CHECK(B <= 65535, "sdp_tokens_from_nchw: B too large");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  if (dtype == SDP_BF16) tokens_from_nchw_kernel<bf16><<<grid, block, 0, st>>>(x, (bf16 *)act, C, T, R);
+  else tokens_from_nchw_kernel<float><<<grid, block, 0, st>>>(x, (float *)act, C, T, R);
+  SDP_LAUNCH_OK();
+  if (R > 0 && reg) {
+    const int g = grid_for((long long)B * R * C);
+    if (dtype == SDP_BF16)
+      registers_copy_kernel<bf16, true><<<g, 256, 0, st>>>((bf16 *)act, const_cast<float *>(reg), B, R + T, R, C);
+    else
+      registers_copy_kernel<float, true><<<g, 256, 0, st>>>((float *)act, const_cast<float *>(reg), B, R + T, R, C);
+    SDP_LAUNCH_OK();
+  }
+  return 0;
+}
+
+extern "C" int sdp_tokens_to_nchw(const void *act, int dtype, float *x, float *reg, int B, int C, int T, int R,
+                                  void *stream) {
+  SDP_CHECK(act && B > 0 && C > 0 && T > 0 && R >= 0, "sdp_tokens_to_nchw: bad arguments");
+  SDP_CHECK(B <= 65535, "sdp_tokens_to_nchw: B too large");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x) {
+    dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    if (dtype == SDP_BF16) tokens_to_nchw_kernel<bf16><<<grid, block, 0, st>>>((const bf16 *)act, x, C, T, R);
+    else tokens_to_nchw_kernel<float><<<grid, block, 0, st>>>((const float *)act, x, C, T, R);
+    SDP_LAUNCH_OK();
+  }
+  if (R > 0 && reg) {
+    const int g = grid_for((long long)B * R * C);
+    if (dtype == SDP_BF16)
+      registers_copy_kernel<bf16, false><<<g, 256, 0, st>>>((bf16 *)const_cast<void *>(act), reg, B, R + T, R, C);
+    else
+      registers_copy_kernel<float, false><<<g, 256, 0, st>>>((float *)const_cast<void *>(act), reg, B, R + T, R, C);
+    SDP_LAUNCH_OK();
+  }
+  return 0;
+}
+
+extern "C" int sdp_im2col_patches(const void *x, int x_dtype, void *A, int a_dtype, int64_t ldA, int B, int H,
+                                  int W, int p, void *stream) {
+  SDP_CHECK(x && A && B > 0 && p > 0, "sdp_im2col_patches: bad arguments");
+  SDP_CHECK(H % p == 0 && W % p == 0, "sdp_im2col_patches: image %dx%d not divisible by patch %d", H, W, p);
+  SDP_CHECK(ldA >= 3 * p * p, "sdp_im2col_patches: ldA=%lld < 3*p*p", (long long)ldA);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int Gh = H / p, Gw = W / p;
+  const int g = grid_for((long long)B * Gh * Gw * ldA);
+#define I2C(TI, TO) im2col_kernel<TI, TO><<<g, 256, 0, st>>>((const TI *)x, (TO *)A, ldA, B, H, W, p, Gh, Gw)
+  if (x_dtype == SDP_F32 && a_dtype == SDP_BF16) I2C(float, bf16);
+  else if (x_dtype == SDP_F32) I2C(float, float);
+  else if (a_dtype == SDP_BF16) I2C(bf16, bf16);
+  else I2C(bf16, float);
+#undef I2C
+  SDP_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sdp_embed_tokens(void *act, int dtype, const float *pos, int B, int T, int R, int C, int act_id,
+                                void *stream) {
+  SDP_CHECK(act && pos && B > 0 && T > 0 && R >= 0 && C > 0, "sdp_embed_tokens: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int g = grid_for((long long)B * T * C);
+  if (dtype == SDP_BF16) embed_tokens_kernel<bf16, false><<<g, 256, 0, st>>>((bf16 *)act, pos, B, T, R, C, act_id);
+  else embed_tokens_kernel<float, true><<<g, 256, 0, st>>>((float *)act, pos, B, T, R, C, act_id);
+  SDP_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sdp_activation(const void *x, void *y, int64_t n, int act, int dtype, void *stream) {
+  SDP_CHECK(x && y && n > 0, "sdp_activation: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool force_fast = (act & 0x100) != 0;   // test hook: fast forms on fp32 I/O
+  act &= 0xff;
+  const int g = grid_for(n);
+  if (dtype == SDP_BF16) activation_kernel<bf16, false><<<g, 256, 0, st>>>((const bf16 *)x, (bf16 *)y, n, act);
+  else if (force_fast) activation_kernel<float, false><<<g, 256, 0, st>>>((const float *)x, (float *)y, n, act);
+  else activation_kernel<float, true><<<g, 256, 0, st>>>((const float *)x, (float *)y, n, act);
+  SDP_LAUNCH_OK();
+  return 0;
+}

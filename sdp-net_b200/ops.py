@@ -1,0 +1,218 @@
+"""Tensor-level wrappers over the C-ABI (include/sdpnet_b200.h).
+
+Each function validates its torch tensors (CUDA, dtype, contiguity), passes raw device pointers
+plus the current CUDA stream to the library and raises on a non-zero status.  These are the
+only compute calls the package makes; they are also registered as `torch.ops.sdpnet_b200.*`.
+PyTorch here is device memory + streams, nothing else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_IDS, SDP_BF16, SDP_F32
+
+_DT = {torch.float32: SDP_F32, torch.bfloat16: SDP_BF16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"sdpnet_b200 supports float32 / bfloat16 tensors, got {t.dtype}") from None
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("sdpnet_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    return t.data_ptr()
+
+
+def _f32(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous float32 tensor")
+    return t
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def act_id(name) -> int:
+    if isinstance(name, int):
+        return name
+    try:
+        return ACT_IDS[str(name).lower()]
+    except KeyError:
+        raise ValueError(f"unknown activation {name!r}; known: {sorted(ACT_IDS)}") from None
+
+
+def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, act="none", res_first: bool = False, res_mod: int = 0,
+         seq_remap=(0, 0, 0), pass_rows=(0, 0), M: Optional[int] = None, N: Optional[int] = None,
+         K: Optional[int] = None) -> torch.Tensor:
+    """out = epi(A[M,K] @ W[N,K]^T); see sdp_gemm in the header for the epilogue definition."""
+    if A.dim() != 2 or W.dim() != 2 or out.dim() != 2:
+        raise ValueError("gemm operands must be 2-D (views with a row pitch are fine)")
+    if A.stride(1) != 1 or W.stride(1) != 1 or out.stride(1) != 1:
+        raise ValueError("gemm operands must be K/N-contiguous")
+    if A.dtype != W.dtype:
+        raise TypeError("A and W must share a dtype")
+    a = L.GemmArgs()
+    a.A, a.lda = _p(A), A.stride(0)
+    a.W, a.ldw = _p(W), W.stride(0)
+    a.bias = _p(_f32(bias, "bias"))
+    a.out, a.ldo = _p(out), out.stride(0)
+    a.M = A.shape[0] if M is None else M
+    a.N = W.shape[0] if N is None else N
+    a.K = A.shape[1] if K is None else K
+    if residual is not None:
+        if residual.stride(-1) != 1:
+            raise ValueError("residual must be contiguous in its last dim")
+        a.residual, a.ldr, a.res_dtype = _p(residual), residual.stride(0), _dt(residual)
+    a.dtype, a.out_dtype = _dt(A), _dt(out)
+    a.act, a.res_first, a.res_mod = act_id(act), int(res_first), int(res_mod)
+    a.seq_in, a.seq_out, a.seq_off = (int(v) for v in seq_remap)
+    a.pass_seq, a.pass_rows = (int(v) for v in pass_rows)
+    L.check(L.lib().sdp_gemm(C.byref(a), _stream()), "sdp_gemm")
+    return out
+
+
+def im2col_patches(x: torch.Tensor, A: torch.Tensor, patch: int) -> torch.Tensor:
+    if x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
+        raise ValueError("x must be a contiguous NCHW tensor with 3 channels")
+    B, _, H, W = x.shape
+    L.check(L.lib().sdp_im2col_patches(_p(x), _dt(x), _p(A), _dt(A), A.stride(0), B, H, W, patch, _stream()),
+            "sdp_im2col_patches")
+    return A
+
+
+def fill_registers(act: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    B, S, Cc = act.shape
+    R = table.shape[0]
+    L.check(L.lib().sdp_fill_registers(_p(act), _dt(act), _p(_f32(table, "table")), B, S, R, Cc, _stream()),
+            "sdp_fill_registers")
+    return act
+
+
+def layernorm_rows(x: torch.Tensor, w: Optional[torch.Tensor], b: Optional[torch.Tensor], out: torch.Tensor,
+                   eps: float) -> torch.Tensor:
+    x2, o2 = x.reshape(-1, x.shape[-1]), out.reshape(-1, out.shape[-1])
+    if x2.dtype != o2.dtype:
+        raise TypeError("layernorm_rows: in/out dtype mismatch")
+    L.check(L.lib().sdp_layernorm_rows(_p(x2), x2.stride(0), _p(_f32(w, "w")), _p(_f32(b, "b")), _p(o2),
+                                       o2.stride(0), x2.shape[0], x2.shape[1], float(eps), _dt(x2), _stream()),
+            "sdp_layernorm_rows")
+    return out
+
+
+def ln_dwconv(act: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, wdw: torch.Tensor,
+              bdw: Optional[torch.Tensor], out: torch.Tensor, Gh: int, Gw: int, R: int, eps: float = 1e-6):
+    B, S, Cc = act.shape
+    if S != R + Gh * Gw or not act.is_contiguous() or not out.is_contiguous():
+        raise ValueError("ln_dwconv: act must be contiguous [B, R + Gh*Gw, C]")
+    k = wdw.shape[-1]
+    L.check(L.lib().sdp_ln_dwconv(_p(act), _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")),
+                                  _p(_f32(wdw, "wdw")), _p(_f32(bdw, "bdw")), _p(out), B, Gh, Gw, Cc, k, R,
+                                  float(eps), _dt(act), _stream()), "sdp_ln_dwconv")
+    return out
+
+
+def attention(qkv: torch.Tensor, out: torch.Tensor, n_head: int, qn_w=None, qn_b=None, kn_w=None, kn_b=None,
+              eps: float = 1e-5) -> torch.Tensor:
+    B, S, C3 = qkv.shape
+    Cc = C3 // 3
+    if not qkv.is_contiguous() or not out.is_contiguous() or out.shape != (B, S, Cc):
+        raise ValueError("attention: qkv [B,S,3C] and out [B,S,C] must be contiguous")
+    L.check(L.lib().sdp_attention(_p(qkv), _p(_f32(qn_w, "qn_w")), _p(_f32(qn_b, "qn_b")), _p(_f32(kn_w, "kn_w")),
+                                  _p(_f32(kn_b, "kn_b")), _p(out), B, S, n_head, Cc // n_head, float(eps),
+                                  _dt(qkv), _stream()), "sdp_attention")
+    return out
+
+
+def pool_ln(act: torch.Tensor, row0: int, nrows: int, ln_w, ln_b, out: torch.Tensor, eps: float = 1e-5):
+    B, S, Cc = act.shape
+    L.check(L.lib().sdp_pool_ln(_p(act), _dt(act), B, S, Cc, row0, nrows, _p(_f32(ln_w, "ln_w")),
+                                _p(_f32(ln_b, "ln_b")), float(eps), _p(out), _dt(out), out.stride(0), _stream()),
+            "sdp_pool_ln")
+    return out
+
+
+def tokens_from_nchw(x: torch.Tensor, reg: Optional[torch.Tensor], act: torch.Tensor) -> torch.Tensor:
+    B, Cc, Gh, Gw = x.shape
+    R = 0 if reg is None else reg.shape[1]
+    x = _f32(x.contiguous(), "x")
+    reg = None if reg is None else _f32(reg.contiguous(), "reg")
+    L.check(L.lib().sdp_tokens_from_nchw(_p(x), _p(reg), _p(act), _dt(act), B, Cc, Gh * Gw, R, _stream()),
+            "sdp_tokens_from_nchw")
+    return act
+
+
+def tokens_to_nchw(act: torch.Tensor, x: Optional[torch.Tensor], reg: Optional[torch.Tensor], T: int, R: int):
+    B, S, Cc = act.shape
+    L.check(L.lib().sdp_tokens_to_nchw(_p(act), _dt(act), _p(_f32(x, "x")), _p(_f32(reg, "reg")), B, Cc, T, R,
+                                       _stream()), "sdp_tokens_to_nchw")
+    return x, reg
+
+
+def embed_tokens(act: torch.Tensor, pos: torch.Tensor, R: int, act_name="none") -> torch.Tensor:
+    B, S, Cc = act.shape
+    L.check(L.lib().sdp_embed_tokens(_p(act), _dt(act), _p(_f32(pos, "pos")), B, S - R, R, Cc, act_id(act_name),
+                                     _stream()), "sdp_embed_tokens")
+    return act
+
+
+def activation(x: torch.Tensor, act, force_fast: bool = False) -> torch.Tensor:
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    L.check(L.lib().sdp_activation(_p(x), _p(y), x.numel(), act_id(act) | (0x100 if force_fast else 0), _dt(x),
+                                   _stream()), "sdp_activation")
+    return y
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(L.lib().sdp_launch_count(1 if reset else 0))
+
+
+def device_ok() -> bool:
+    return bool(L.lib().sdp_device_ok())
+
+
+# ---- torch.ops registration (thin: the op bodies are the ctypes calls above) ------------------
+def _register_torch_ops() -> None:
+    lib = torch.library.Library("sdpnet_b200", "DEF")
+    lib.define("gemm(Tensor A, Tensor W, Tensor(a!) out, Tensor? bias, Tensor? residual, int act) -> ()")
+    lib.define("layernorm_rows(Tensor x, Tensor? w, Tensor? b, Tensor(a!) out, float eps) -> ()")
+    lib.define("ln_dwconv(Tensor act, Tensor gamma, Tensor beta, Tensor wdw, Tensor? bdw, Tensor(a!) out, "
+               "int Gh, int Gw, int R, float eps) -> ()")
+    lib.define("attention(Tensor qkv, Tensor(a!) out, int n_head, Tensor? qn_w, Tensor? qn_b, Tensor? kn_w, "
+               "Tensor? kn_b, float eps) -> ()")
+
+    def _gemm(A, W, out, bias, residual, act):
+        gemm(A, W, out, bias=bias, residual=residual, act=act)
+
+    def _ln(x, w, b, out, eps):
+        layernorm_rows(x, w, b, out, eps)
+
+    def _dw(act, g, be, wdw, bdw, out, Gh, Gw, R, eps):
+        ln_dwconv(act, g, be, wdw, bdw, out, Gh, Gw, R, eps)
+
+    def _attn(qkv, out, nh, a, b, c, d, eps):
+        attention(qkv, out, nh, a, b, c, d, eps)
+
+    lib.impl("gemm", _gemm, "CUDA")
+    lib.impl("layernorm_rows", _ln, "CUDA")
+    lib.impl("ln_dwconv", _dw, "CUDA")
+    lib.impl("attention", _attn, "CUDA")
+    globals()["_torch_lib"] = lib   # keep alive
+
+
+try:
+    _register_torch_ops()
+except Exception:  # pragma: no cover - registration is a convenience, never a dependency
+    pass

@@ -1,0 +1,299 @@
+"""Kernel-level numerics (B200 only): every C-ABI entry point against a plain PyTorch fp32
+reference of the same op on the same seeded inputs.  Model-level parity against the oracle and
+the golden vectors is in test_gpu_parity.py."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import sdpnet_oracle as O  # noqa: E402  (activation table for references)
+
+
+@pytest.fixture(scope="module")
+def sdp():
+    import sdpnet_b200 as m
+    m._lib.lib()
+    assert m.ops.device_ok(), "needs an sm_100 device"
+    return m
+
+
+def _g(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    return (torch.randn(*shape, generator=_g(seed), device="cuda") * scale).to(dtype)
+
+
+def relerr(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
+
+
+# --------------------------------------------------------------------------------------------
+# GEMM: tcgen05 (bf16) and CUDA-core (fp32)
+# --------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    (128, 256, 64), (128, 256, 256), (256, 512, 128), (300, 768, 768), (1000, 3072, 768),
+    (1044, 768, 3072), (77, 96, 32), (64, 1000, 768), (50, 10, 32), (1024, 2304, 768),
+    (130, 384, 128), (257, 128, 512), (19000, 768, 768), (8, 1000, 1000), (200, 64, 592),
+]
+
+
+def gemm_ref(A, W, bias=None, act="none", residual=None, res_first=False):
+    v = A.float() @ W.float().t()
+    if bias is not None:
+        v = v + bias
+    if residual is not None and res_first:
+        return O.ACTIVATIONS[act](v + residual.float())
+    v = O.ACTIVATIONS[act](v)
+    if residual is not None:
+        v = v + residual.float()
+    return v
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_bf16_plain(sdp, M, N, K):
+    A = rnd(M, K, seed=1, dtype=torch.bfloat16)
+    W = rnd(N, K, seed=2, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    sdp.ops.gemm(A, W, out)
+    torch.cuda.synchronize()
+    ref = gemm_ref(A, W)
+    assert torch.isfinite(out.float()).all()
+    assert relerr(out, ref) < 1.2e-2        # bf16 output rounding (2^-8) on O(1) values
+    # fp32 output isolates accumulation from output rounding
+    out32 = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    sdp.ops.gemm(A, W, out32)
+    assert relerr(out32, ref) < 2e-4
+
+
+@pytest.mark.parametrize("act", ["none", "gelu", "relu", "tanh", "sigmoid", "leaky_relu", "selu", "kelu", "gelu_tanh"])
+def test_gemm_bf16_epilogues(sdp, act):
+    M, N, K = 523, 768, 256
+    A = rnd(M, K, seed=3, dtype=torch.bfloat16)
+    W = rnd(N, K, seed=4, scale=2 / math.sqrt(K), dtype=torch.bfloat16)
+    bias = rnd(N, seed=5, scale=0.5)
+    res = rnd(M, N, seed=6, dtype=torch.bfloat16)
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    sdp.ops.gemm(A, W, out, bias=bias, act=act, residual=res)
+    ref = gemm_ref(A, W, bias, act, res)
+    assert (out - ref).abs().max() < 3e-3
+    out_b = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    sdp.ops.gemm(A, W, out_b, bias=bias, act=act, residual=res, res_first=True)
+    assert relerr(out_b, gemm_ref(A, W, bias, act, res, True)) < 1.2e-2
+
+
+def test_gemm_bf16_inplace_residual_and_passthrough(sdp):
+    B, S, R, C, K = 7, 41, 5, 256, 128
+    M = B * S
+    A = rnd(M, K, seed=7, dtype=torch.bfloat16)
+    W = rnd(C, K, seed=8, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    x = rnd(M, C, seed=9, dtype=torch.bfloat16)
+    ref = gemm_ref(A, W, None, "gelu", x)
+    rows = torch.arange(M, device="cuda") % S < R
+    ref[rows] = x.float()[rows]
+    out = x.clone()
+    sdp.ops.gemm(A, W, out, act="gelu", residual=out, pass_rows=(S, R))
+    assert relerr(out, ref) < 1.2e-2
+    assert torch.equal(out[rows], x[rows])          # register rows bit-identical
+
+
+def test_gemm_bf16_patch_embed_epilogue(sdp):
+    """row remap [B*T] -> [B, S, C] behind R register rows + fp32 position table with row modulo."""
+    B, T, R, C, K = 5, 49, 4, 128, 588
+    S = T + R
+    Kp = 592
+    A = torch.zeros(B * T, Kp, device="cuda", dtype=torch.bfloat16)
+    A[:, :K] = rnd(B * T, K, seed=10, dtype=torch.bfloat16)
+    W = torch.zeros(C, Kp, device="cuda", dtype=torch.bfloat16)
+    W[:, :K] = rnd(C, K, seed=11, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    pos = rnd(T, C, seed=12)
+    act = torch.full((B, S, C), 7.0, device="cuda", dtype=torch.bfloat16)
+    sdp.ops.gemm(A, W, act.view(B * S, C), residual=pos, res_first=True, res_mod=T, act="gelu",
+                 seq_remap=(T, S, R), K=K)
+    ref = F.gelu((A[:, :K].float() @ W[:, :K].float().t()).view(B, T, C) + pos)
+    assert relerr(act[:, R:], ref) < 1.2e-2
+    assert (act[:, :R] == 7.0).all()                 # register rows untouched
+
+
+@pytest.mark.parametrize("M,N,K", [(70, 50, 33), (129, 65, 100), (300, 128, 64)])
+def test_gemm_fp32(sdp, M, N, K):
+    A, W = rnd(M, K, seed=13), rnd(N, K, seed=14, scale=1 / math.sqrt(K))
+    bias, res = rnd(N, seed=15), rnd(M, N, seed=16)
+    out = torch.empty(M, N, device="cuda")
+    sdp.ops.gemm(A, W, out, bias=bias, act="gelu", residual=res)
+    ref = F.gelu(A.double() @ W.double().t() + bias.double()) + res.double()
+    assert (out.double() - ref).abs().max() < 2e-5
+
+
+def test_gemm_rejects_misaligned_pitch(sdp):
+    A = rnd(16, 36, dtype=torch.bfloat16)     # 72-byte rows: not a legal TMA pitch
+    W = rnd(16, 36, dtype=torch.bfloat16)
+    with pytest.raises(sdp._lib.SdpNetLibraryError):
+        sdp.ops.gemm(A, W, torch.empty(16, 16, device="cuda", dtype=torch.bfloat16))
+
+
+# --------------------------------------------------------------------------------------------
+# activations (epilogue functions), incl. the fast erf-GELU used by the bf16 epilogue
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("act", ["relu", "gelu", "gelu_tanh", "tanh", "sigmoid", "leaky_relu", "selu", "kelu"])
+def test_activation_fp32_exact(sdp, act):
+    x = torch.linspace(-8, 8, 20001, device="cuda")
+    y = sdp.ops.activation(x, act)
+    assert (y - O.ACTIVATIONS[act](x)).abs().max() < 2e-6
+
+
+def test_fast_gelu_close_to_erf_gelu(sdp):
+    x = torch.linspace(-10, 10, 200001, device="cuda")
+    y = sdp.ops.activation(x, "gelu", force_fast=True)
+    ref = F.gelu(x.double()).float()
+    assert (y - ref).abs().max() < 2e-6      # << bf16 resolution; documented in DESIGN.md
+
+
+# --------------------------------------------------------------------------------------------
+# LayerNorm rows / pooled head front / register fill / layout bridges / im2col
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,C", [(1, 8), (37, 32), (1000, 128), (523, 512), (2610, 768), (33, 1024), (20, 36), (9, 2048),
+                                 (5, 4096)])
+def test_layernorm_rows(sdp, dtype, M, C):
+    x = (rnd(M, C, seed=20) * 3 + 1.5).to(dtype)
+    w, b = rnd(C, seed=21) + 1, rnd(C, seed=22)
+    out = torch.empty_like(x)
+    sdp.ops.layernorm_rows(x, w, b, out, 1e-5)
+    ref = F.layer_norm(x.float(), (C,), w, b, 1e-5)
+    tol = 3e-2 if dtype == torch.bfloat16 else 2e-5
+    assert (out.float() - ref).abs().max() < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pool_ln_and_fill_registers(sdp, dtype):
+    B, S, R, C = 6, 21, 5, 96
+    table = rnd(R, C, seed=23)
+    act = rnd(B, S, C, seed=24).to(dtype)
+    sdp.ops.fill_registers(act, table)
+    assert torch.allclose(act[:, :R].float(), table.to(dtype).float().expand(B, R, C))
+    w, b = rnd(C, seed=25) + 1, rnd(C, seed=26)
+    out = torch.empty(B, C, device="cuda", dtype=dtype)
+    sdp.ops.pool_ln(act, 0, R, w, b, out, 1e-5)
+    ref = F.layer_norm(act[:, :R].float().mean(1), (C,), w, b, 1e-5)
+    assert (out.float() - ref).abs().max() < (3e-2 if dtype == torch.bfloat16 else 2e-5)
+    out2 = torch.empty(B, C, device="cuda", dtype=torch.float32)
+    sdp.ops.pool_ln(act, R, S - R, None, None, out2, 0.0)
+    assert (out2 - act[:, R:].float().mean(1)).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_token_bridges_roundtrip(sdp, dtype):
+    B, C, Gh, Gw, R = 3, 40, 5, 7, 4
+    x, reg = rnd(B, C, Gh, Gw, seed=27), rnd(B, R, C, seed=28)
+    act = torch.empty(B, R + Gh * Gw, C, device="cuda", dtype=dtype)
+    sdp.ops.tokens_from_nchw(x, reg, act)
+    ref = torch.cat([reg, x.flatten(2).transpose(1, 2)], 1)
+    assert torch.equal(act.float(), ref.to(dtype).float())
+    x2, r2 = torch.empty_like(x), torch.empty_like(reg)
+    sdp.ops.tokens_to_nchw(act, x2, r2, Gh * Gw, R)
+    assert torch.equal(x2, x.to(dtype).float()) and torch.equal(r2, reg.to(dtype).float())
+
+
+@pytest.mark.parametrize("p,H,W", [(14, 28, 42), (16, 32, 32), (2, 8, 6), (4, 16, 16)])
+def test_im2col_matches_conv(sdp, p, H, W):
+    B, C = 3, 24
+    x = rnd(B, 3, H, W, seed=29)
+    w = rnd(C, 3, p, p, seed=30, scale=0.1)
+    Kc = 3 * p * p
+    Kp = (Kc + 7) // 8 * 8
+    A = torch.full((B * (H // p) * (W // p), Kp), float("nan"), device="cuda")
+    sdp.ops.im2col_patches(x, A, p)
+    assert (A[:, Kc:] == 0).all()
+    y = (A[:, :Kc] @ w.reshape(C, Kc).t()).view(B, H // p, W // p, C).permute(0, 3, 1, 2)
+    assert (y - F.conv2d(x, w, stride=p)).abs().max() < 1e-4
+
+
+def test_embed_tokens(sdp):
+    B, T, R, C = 3, 12, 2, 16
+    act = rnd(B, R + T, C, seed=31)
+    pos = rnd(T, C, seed=32)
+    ref = act.clone()
+    ref[:, R:] = F.gelu(ref[:, R:] + pos)
+    sdp.ops.embed_tokens(act, pos, R, "gelu")
+    assert (act - ref).abs().max() < 2e-6
+
+
+# --------------------------------------------------------------------------------------------
+# channel LayerNorm + depthwise conv
+# --------------------------------------------------------------------------------------------
+def dw_ref(act, R, Gh, Gw, gamma, beta, wdw, bdw, eps=1e-6):
+    B, S, C = act.shape
+    k = wdw.shape[-1]
+    x = act[:, R:].float()
+    xn = F.layer_norm(x, (C,), gamma, beta, eps)            # per-token LN over channels == layers.py:12-24
+    img = xn.transpose(1, 2).reshape(B, C, Gh, Gw)
+    lo = (k - 1) // 2
+    img = F.pad(img, (lo, k - 1 - lo, lo, k - 1 - lo))      # zeros AFTER the norm
+    y = F.conv2d(img, wdw.view(C, 1, k, k), bdw, groups=C)
+    out = torch.zeros(B, S, C, device=act.device)
+    out[:, R:] = y.flatten(2).transpose(1, 2)
+    return out
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Gh,Gw,C,k,R,bias", [(16, 16, 768, 7, 5, False), (14, 14, 96, 7, 4, True), (8, 8, 32, 5, 1, True),
+                                              (4, 6, 40, 3, 2, False), (5, 3, 16, 9, 3, True), (2, 2, 128, 7, 5, False)])
+def test_ln_dwconv(sdp, dtype, Gh, Gw, C, k, R, bias):
+    B = 3
+    act = (rnd(B, R + Gh * Gw, C, seed=40) * 2 + 0.3).to(dtype)
+    gamma, beta = rnd(C, seed=41) * 0.3 + 1, rnd(C, seed=42) * 0.3
+    wdw = rnd(C, k, k, seed=43, scale=1 / k)
+    bdw = rnd(C, seed=44) if bias else None
+    out = torch.full_like(act, float("nan"))
+    sdp.ops.ln_dwconv(act, gamma, beta, wdw, bdw, out, Gh, Gw, R)
+    ref = dw_ref(act, R, Gh, Gw, gamma, beta, wdw, bdw)
+    assert (out[:, :R] == 0).all()
+    tol = 4e-2 if dtype == torch.bfloat16 else 5e-5
+    assert (out.float() - ref).abs().max() < tol
+
+
+# --------------------------------------------------------------------------------------------
+# attention with fused QK LayerNorm
+# --------------------------------------------------------------------------------------------
+def attn_ref(qkv, h, qn_w, qn_b, kn_w, kn_b, eps=1e-5):
+    B, S, C3 = qkv.shape
+    C = C3 // 3
+    d = C // h
+    q, k, v = [t.float().view(B, S, h, d).transpose(1, 2) for t in qkv.split(C, dim=-1)]
+    if qn_w is not None:
+        q = F.layer_norm(q, (d,), qn_w, qn_b, eps)
+        k = F.layer_norm(k, (d,), kn_w, kn_b, eps)
+    p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1)
+    return (p @ v).transpose(1, 2).reshape(B, S, C)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("S,h,d,norm", [(261, 8, 96, True), (201, 8, 64, True), (201, 8, 96, False), (9, 4, 32, True),
+                                        (68, 2, 16, True), (20, 4, 8, True), (33, 3, 24, False), (300, 2, 128, True),
+                                        (17, 4, 32, True), (32, 2, 64, True)])
+def test_attention(sdp, dtype, S, h, d, norm):
+    B, C = 2, h * d
+    qkv = rnd(B, S, 3 * C, seed=50, scale=1.5).to(dtype)
+    if norm:
+        qn_w, qn_b = rnd(d, seed=51) * 0.3 + 1, rnd(d, seed=52) * 0.3
+        kn_w, kn_b = rnd(d, seed=53) * 0.3 + 1, rnd(d, seed=54) * 0.3
+    else:
+        qn_w = qn_b = kn_w = kn_b = None
+    out = torch.full((B, S, C), float("nan"), device="cuda", dtype=dtype)
+    sdp.ops.attention(qkv, out, h, qn_w, qn_b, kn_w, kn_b)
+    ref = attn_ref(qkv, h, qn_w, qn_b, kn_w, kn_b)
+    assert torch.isfinite(out.float()).all()
+    tol = 3e-2 if dtype == torch.bfloat16 else 5e-5
+    assert (out.float() - ref).abs().max() < tol
+
+
+def test_launch_counter(sdp):
+    sdp.ops.launch_count(reset=True)
+    x = rnd(4, 64)
+    sdp.ops.layernorm_rows(x, None, None, torch.empty_like(x), 1e-5)
+    assert sdp.ops.launch_count() == 1
