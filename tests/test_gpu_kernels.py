@@ -165,7 +165,8 @@ def test_layernorm_rows(sdp, dtype, M, C):
     out = torch.empty_like(x)
     sdp.ops.layernorm_rows(x, w, b, out, 1e-5)
     ref = F.layer_norm(x.float(), (C,), w, b, 1e-5)
-    tol = 3e-2 if dtype == torch.bfloat16 else 2e-5
+    # bf16: half an output ulp (2^-9 relative) plus the input's own rounding through the affine
+    tol = 2 ** -7 * float(ref.abs().max()) if dtype == torch.bfloat16 else 2e-5
     assert (out.float() - ref).abs().max() < tol
 
 
