@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SDPNET_B200_ABI_VERSION 1
+#define SDPNET_B200_ABI_VERSION 2
 
 typedef enum { SDP_F32 = 0, SDP_BF16 = 1 } sdp_dtype;
 
@@ -69,6 +69,12 @@ int sdp_device_ok(void);
  * rr = res_mod ? r % res_mod : ro   (res_mod = T: broadcast the [T, C] position table), and
  * rows with (ro % pass_seq) < pass_rows are left untouched when pass_seq != 0 (the mixers
  * must not modify register rows; requires out == residual, i.e. in-place).
+ *
+ * Head-norm (bf16 only, the QKV projection): when headnorm_d != 0, before anything else every
+ * group of headnorm_d consecutive columns below 2*headnorm_C gets a LayerNorm over the group
+ * (eps headnorm_eps, affine hn_q_* for columns < headnorm_C, hn_k_* above) -- the per-head
+ * nn.LayerNorm on q and k (layers.py:236-237,286) fused into the projection's epilogue.
+ * Supported for headnorm_d in {32, 64, 96, 128} (see sdp_gemm_headnorm_ok); needs bias == NULL.
  * --------------------------------------------------------------------------------------- */
 typedef struct {
   const void *A;        int64_t lda;   /* [M, K], row pitch in elements */
@@ -85,9 +91,14 @@ typedef struct {
   int32_t res_mod;
   int32_t seq_in, seq_out, seq_off;
   int32_t pass_seq, pass_rows;
+  int32_t headnorm_d, headnorm_C;
+  float headnorm_eps;
+  const float *hn_q_w, *hn_q_b, *hn_k_w, *hn_k_b;
 } sdp_gemm_args;
 
 int sdp_gemm(const sdp_gemm_args *args, void *stream);
+/* 1 if sdp_gemm can fuse the per-head LayerNorm for this head_dim / N / dtype. */
+int sdp_gemm_headnorm_ok(int head_dim, int N, int dtype);
 
 /* im2col for kernel == stride patches (layers.py:34-42): x NCHW [B,3,H,W] (fp32 or bf16) ->
  * A [B*T, ldA] with A[b*T + i*Gw + j, c*p*p + dy*p + dx] = x[b, c, i*p+dy, j*p+dx]; columns
@@ -106,7 +117,8 @@ int sdp_layernorm_rows(const void *x, int64_t ldx, const float *w, const float *
 
 /* Mixer front half (layers.py:102 up to the depthwise conv): per image, channel-LayerNorm
  * (eps 1e-6, gamma/beta) of the patch rows, then depthwise kxk 'same' conv (zero halo applied
- * AFTER the norm), taps wdw [C, k, k] fp32, optional bias bdw [C].  act,out: [B, S, C];
+ * AFTER the norm), taps wdw TAP-MAJOR [k*k, C] fp32 (wdw[(dy*k+dx)*C + c] = conv.weight[c,0,dy,dx]),
+ * optional bias bdw [C].  act,out: [B, S, C];
  * register rows of `out` are written as zeros. */
 int sdp_ln_dwconv(const void *act, const float *gamma, const float *beta, const float *wdw,
                   const float *bdw, void *out, int B, int Gh, int Gw, int C, int k, int R,
@@ -158,7 +170,7 @@ typedef struct {          /* one EncoderLayer, layers.py:216-257 */
 
 typedef struct {          /* one ConvMixer, layers.py:63-99 */
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
-  const float *w_dw, *b_dw;                        /* [C,k,k], [C] or NULL */
+  const float *w_dw, *b_dw;                        /* tap-major [k*k, C], [C] or NULL */
   const void *w_pw;  const float *b_pw;            /* [C, C] */
   const void *w_mlp1; const float *b_mlp1;         /* [4C, C] */
   const void *w_mlp2; const float *b_mlp2;         /* [C, 4C] */

@@ -35,6 +35,8 @@ class GemmArgs(C.Structure):
         ("act", c_i32), ("res_first", c_i32), ("res_mod", c_i32),
         ("seq_in", c_i32), ("seq_out", c_i32), ("seq_off", c_i32),
         ("pass_seq", c_i32), ("pass_rows", c_i32),
+        ("headnorm_d", c_i32), ("headnorm_C", c_i32), ("headnorm_eps", c_float),
+        ("hn_q_w", c_void_p), ("hn_q_b", c_void_p), ("hn_k_w", c_void_p), ("hn_k_b", c_void_p),
     ]
 
 
@@ -74,6 +76,7 @@ SYMBOLS = {
     "sdp_last_error": (C.c_char_p, []),
     "sdp_device_ok": (c_int, []),
     "sdp_gemm": (c_int, [C.POINTER(GemmArgs), c_void_p]),
+    "sdp_gemm_headnorm_ok": (c_int, [c_int, c_int, c_int]),
     "sdp_im2col_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_fill_registers": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_layernorm_rows": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_float, c_int, c_void_p]),
@@ -108,7 +111,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)   # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if handle.sdp_abi_version() != 1:
+        if handle.sdp_abi_version() != 2:
             raise SdpNetLibraryError("libsdpnet_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

@@ -275,6 +275,285 @@ attention_bf16_mma_kernel(const bf16 *__restrict__ qkv, const float *__restrict_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tensor-core path, version 2: q and k arrive already LayerNorm-ed (fused into the QKV GEMM
+// epilogue, gemm_tc.cu head_layernorm), so K and V stream into shared memory with cp.async in
+// three commit groups that the first KV blocks overlap with; one CTA per (image, head); every
+// warp owns TPW adjacent 16-query tiles and reuses each K / V fragment for all of them, which
+// halves the shared-memory traffic per MMA relative to version 1.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int ATT2_MAXW = 8;    // register allocation is per 4 warps: 8 warps leave 255 registers per thread
+
+// NT adjacent 16-query tiles starting at row q0 against KV blocks blk0, blk0+step, ...: flash-style
+// online softmax; leaves un-normalised O, running max m and this lane's partial row sums l.
+template <int D, int NT, bool GROUP_SYNC>
+__device__ __forceinline__ void attn_tiles(const bf16 *__restrict__ base, int C, int S, int q0, int blk0, int step,
+                                           int nblk, int gblk, uint32_t sK_addr, uint32_t sV_addr, float scale_log2,
+                                           int lane, float (&o)[NT][D / 8][4], float (&m_)[NT][2],
+                                           float (&l_)[NT][2]) {
+  constexpr int PITCH = D + 8;
+  const int g = lane >> 2, qd = lane & 3;
+  const int lm = lane >> 3, lr = lane & 7;
+  uint32_t qa[NT][D / 16][4];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int rl = min(q0 + t * 16 + g, S - 1), rh = min(q0 + t * 16 + g + 8, S - 1);
+    const bf16 *plo = base + (long long)rl * 3 * C, *phi = base + (long long)rh * 3 * C;
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      const int c0 = kk * 16 + qd * 2;
+      qa[t][kk][0] = __ldg(reinterpret_cast<const uint32_t *>(plo + c0));
+      qa[t][kk][1] = __ldg(reinterpret_cast<const uint32_t *>(phi + c0));
+      qa[t][kk][2] = __ldg(reinterpret_cast<const uint32_t *>(plo + c0 + 8));
+      qa[t][kk][3] = __ldg(reinterpret_cast<const uint32_t *>(phi + c0 + 8));
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    m_[t][0] = m_[t][1] = -INFINITY;
+    l_[t][0] = l_[t][1] = 0.0f;
+#pragma unroll
+    for (int n = 0; n < D / 8; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[t][n][j] = 0.0f;
+  }
+  for (int blk = blk0; blk < nblk; blk += step) {
+    if (GROUP_SYNC) {                            // block-uniform: every warp walks all KV blocks in this mode
+      if (blk == 0) { cp_async_wait<2>(); __syncthreads(); }
+      else if (blk == gblk) { cp_async_wait<1>(); __syncthreads(); }
+      else if (blk == 2 * gblk) { cp_async_wait<0>(); __syncthreads(); }
+    }
+    const int kb = blk * KVB;
+    float sc[NT][KVB / 8][4];
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+      for (int n = 0; n < KVB / 8; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sc[t][n][j] = 0.0f;
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+#pragma unroll
+      for (int np = 0; np < KVB / 16; ++np) {
+        // matrices: (keys np*16 + 0..7, d kk*16 + 0..7) (same keys, d + 8) (keys + 8, d) (keys + 8, d + 8)
+        const int key = kb + np * 16 + (lm >> 1) * 8 + lr;
+        const int col = kk * 16 + (lm & 1) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(sK_addr + (uint32_t)(key * PITCH + col) * 2, b0, b1, b2, b3);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          mma_bf16_16816(sc[t][np * 2], qa[t][kk], b0, b1);
+          mma_bf16_16816(sc[t][np * 2 + 1], qa[t][kk], b2, b3);
+        }
+      }
+    }
+    uint32_t pa[NT][KVB / 16][4];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      float bm_lo = -INFINITY, bm_hi = -INFINITY;
+#pragma unroll
+      for (int n = 0; n < KVB / 8; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int key = kb + n * 8 + qd * 2 + (j & 1);
+          const float v = key < S ? sc[t][n][j] * scale_log2 : -INFINITY;
+          sc[t][n][j] = v;
+          if (j < 2) bm_lo = fmaxf(bm_lo, v); else bm_hi = fmaxf(bm_hi, v);
+        }
+      bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 1));
+      bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
+      bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 1));
+      bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 2));
+      // every KV block holds at least one live key, so the new maxima are finite
+      const float mn_lo = fmaxf(m_[t][0], bm_lo), mn_hi = fmaxf(m_[t][1], bm_hi);
+      const float cr_lo = fast_ex2(m_[t][0] - mn_lo), cr_hi = fast_ex2(m_[t][1] - mn_hi);
+      m_[t][0] = mn_lo; m_[t][1] = mn_hi;
+      float ps_lo = 0.0f, ps_hi = 0.0f;
+#pragma unroll
+      for (int n = 0; n < KVB / 8; ++n) {
+        const float p0 = fast_ex2(sc[t][n][0] - mn_lo), p1 = fast_ex2(sc[t][n][1] - mn_lo);
+        const float p2 = fast_ex2(sc[t][n][2] - mn_hi), p3 = fast_ex2(sc[t][n][3] - mn_hi);
+        ps_lo += p0 + p1;
+        ps_hi += p2 + p3;
+        // C-fragment of score tile n -> A-fragment of k16 step n/2 (a0,a1 from the even tile; a2,a3 from the odd)
+        pa[t][n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+        pa[t][n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      }
+      l_[t][0] = l_[t][0] * cr_lo + ps_lo;
+      l_[t][1] = l_[t][1] * cr_hi + ps_hi;
+#pragma unroll
+      for (int n = 0; n < D / 8; ++n) {
+        o[t][n][0] *= cr_lo; o[t][n][1] *= cr_lo;
+        o[t][n][2] *= cr_hi; o[t][n][3] *= cr_hi;
+      }
+    }
+#pragma unroll
+    for (int kt = 0; kt < KVB / 16; ++kt) {
+#pragma unroll
+      for (int np = 0; np < D / 16; ++np) {
+        // transposed: (keys kt*16 + 0..7, d np*16 + 0..7) (keys + 8, same d) (keys, d + 8) (keys + 8, d + 8)
+        const int key = kb + kt * 16 + (lm & 1) * 8 + lr;
+        const int col = np * 16 + (lm >> 1) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(sV_addr + (uint32_t)(key * PITCH + col) * 2, b0, b1, b2, b3);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          mma_bf16_16816(o[t][np * 2], pa[t][kt], b0, b1);
+          mma_bf16_16816(o[t][np * 2 + 1], pa[t][kt], b2, b3);
+        }
+      }
+    }
+  }
+}
+
+template <int D, int TPW>
+__global__ void __launch_bounds__(32 * ATT2_MAXW, 1)
+attention_bf16_mma2_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int S, int h, float scale_log2) {
+  constexpr int PITCH = D + 8;
+  constexpr int NV = D / 8;                     // 16-byte vectors per row
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const int S_pad = ((S + KVB - 1) / KVB) * KVB;
+  const int nblk = S_pad / KVB;
+  bf16 *sK = reinterpret_cast<bf16 *>(smem_attn);
+  bf16 *sV = sK + (size_t)S_pad * PITCH;
+  float *part = reinterpret_cast<float *>(sV + (size_t)S_pad * PITCH);   // tail partials (only if needed)
+  const int C = h * D;
+  const int b = blockIdx.x / h, head = blockIdx.x % h;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x, nw = nthreads >> 5;
+  const bf16 *base = qkv + (long long)b * S * 3 * C + head * D;
+  const uint32_t sK_addr = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
+  const uint32_t sV_addr = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
+
+  // ---- K / V: three cp.async commit groups of whole KV blocks ----
+  const int gblk = (nblk + 2) / 3;              // KV blocks per group
+  for (int grp = 0; grp < 3; ++grp) {
+    const int r0 = min(S_pad, grp * gblk * KVB), r1 = min(S_pad, (grp + 1) * gblk * KVB);
+    const int per = (r1 - r0) * NV;
+    for (int i = tid; i < 2 * per; i += nthreads) {
+      const int which = i >= per;               // 0 = K, 1 = V
+      const int j = i - which * per;
+      const int r = r0 + j / NV, cv = j % NV;
+      const uint32_t off = (uint32_t)(r * PITCH + cv * 8) * 2;
+      if (r < S) cp_async16((which ? sV_addr : sK_addr) + off, base + (long long)r * 3 * C + (which + 1) * C + cv * 8);
+      else *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(which ? sV : sK) + off) = make_uint4(0, 0, 0, 0);
+    }
+    cp_async_commit();
+  }
+
+  const int g = lane >> 2, qd = lane & 3;
+  const int tiles = (S + 15) / 16;
+  const int units = (tiles + TPW - 1) / TPW;
+  // full rounds: every warp owns one unit of TPW tiles per round (nw <= units by construction)
+  const int full_units = (units / nw) * nw;
+  bool first = true;
+  for (int unit = warp; unit < full_units; unit += nw) {
+    float o[TPW][D / 8][4], m_[TPW][2], l_[TPW][2];
+    const int q0 = unit * TPW * 16;
+    if (first)
+      attn_tiles<D, TPW, true>(base, C, S, q0, 0, 1, nblk, gblk, sK_addr, sV_addr, scale_log2, lane, o, m_, l_);
+    else
+      attn_tiles<D, TPW, false>(base, C, S, q0, 0, 1, nblk, gblk, sK_addr, sV_addr, scale_log2, lane, o, m_, l_);
+    first = false;
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      float ll = l_[t][0], lh = l_[t][1];
+      ll += __shfl_xor_sync(0xffffffffu, ll, 1); ll += __shfl_xor_sync(0xffffffffu, ll, 2);
+      lh += __shfl_xor_sync(0xffffffffu, lh, 1); lh += __shfl_xor_sync(0xffffffffu, lh, 2);
+      const float il = 1.0f / ll, ih = 1.0f / lh;
+      const int r_lo = q0 + t * 16 + g, r_hi = r_lo + 8;
+      bf16 *olo = out + ((long long)b * S + r_lo) * C + head * D;
+      bf16 *ohi = olo + 8LL * C;
+#pragma unroll
+      for (int n = 0; n < D / 8; ++n) {
+        const int c = n * 8 + qd * 2;
+        if (r_lo < S) *reinterpret_cast<uint32_t *>(olo + c) = pack_bf16x2(o[t][n][0] * il, o[t][n][1] * il);
+        if (r_hi < S) *reinterpret_cast<uint32_t *>(ohi + c) = pack_bf16x2(o[t][n][2] * ih, o[t][n][3] * ih);
+      }
+    }
+  }
+  // ---- tail tiles (e.g. the 17th tile of S = 261): all warps split the KV blocks of one tile,
+  //      partial (m, l, O) meet in shared memory ----
+  for (int tile = full_units * TPW; tile < tiles; ++tile) {
+    float o[1][D / 8][4], m_[1][2], l_[1][2];
+    attn_tiles<D, 1, false>(base, C, S, tile * 16, warp, nw, nblk, gblk, sK_addr, sV_addr, scale_log2, lane, o, m_, l_);
+    float ll = l_[0][0], lh = l_[0][1];
+    ll += __shfl_xor_sync(0xffffffffu, ll, 1); ll += __shfl_xor_sync(0xffffffffu, ll, 2);
+    lh += __shfl_xor_sync(0xffffffffu, lh, 1); lh += __shfl_xor_sync(0xffffffffu, lh, 2);
+    constexpr int PW_ = (D / 8) * 4 * 32 + 4 * 32;        // floats per warp partial
+    float *mine = part + (size_t)warp * PW_;
+#pragma unroll
+    for (int n = 0; n < D / 8; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mine[(n * 4 + j) * 32 + lane] = o[0][n][j];
+    float *ml = mine + (D / 8) * 4 * 32;
+    ml[lane] = m_[0][0]; ml[32 + lane] = m_[0][1]; ml[64 + lane] = ll; ml[96 + lane] = lh;
+    __syncthreads();
+    float M_lo = -INFINITY, M_hi = -INFINITY;
+    for (int w = 0; w < nw; ++w) {
+      const float *q = part + (size_t)w * PW_ + (D / 8) * 4 * 32;
+      M_lo = fmaxf(M_lo, q[lane]);
+      M_hi = fmaxf(M_hi, q[32 + lane]);
+    }
+    float L_lo = 0.0f, L_hi = 0.0f;
+    for (int w = 0; w < nw; ++w) {
+      const float *q = part + (size_t)w * PW_ + (D / 8) * 4 * 32;
+      L_lo += q[64 + lane] * fast_ex2(q[lane] - M_lo);
+      L_hi += q[96 + lane] * fast_ex2(q[32 + lane] - M_hi);
+    }
+    const float il = 1.0f / L_lo, ih = 1.0f / L_hi;
+    const int r_lo = tile * 16 + g, r_hi = r_lo + 8;
+    bf16 *olo = out + ((long long)b * S + r_lo) * C + head * D;
+    bf16 *ohi = olo + 8LL * C;
+    for (int n = warp; n < D / 8; n += nw) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int w = 0; w < nw; ++w) {
+        const float *pw = part + (size_t)w * PW_;
+        const float *q = pw + (D / 8) * 4 * 32;
+        const float f_lo = fast_ex2(q[lane] - M_lo), f_hi = fast_ex2(q[32 + lane] - M_hi);
+        a0 = fmaf(pw[(n * 4 + 0) * 32 + lane], f_lo, a0);
+        a1 = fmaf(pw[(n * 4 + 1) * 32 + lane], f_lo, a1);
+        a2 = fmaf(pw[(n * 4 + 2) * 32 + lane], f_hi, a2);
+        a3 = fmaf(pw[(n * 4 + 3) * 32 + lane], f_hi, a3);
+      }
+      const int c = n * 8 + qd * 2;
+      if (r_lo < S) *reinterpret_cast<uint32_t *>(olo + c) = pack_bf16x2(a0 * il, a1 * il);
+      if (r_hi < S) *reinterpret_cast<uint32_t *>(ohi + c) = pack_bf16x2(a2 * ih, a3 * ih);
+    }
+    __syncthreads();
+  }
+}
+
+template <int D, int TPW>
+static int launch_attn_mma2(const void *qkv, void *out, int B, int S, int h, cudaStream_t st) {
+  const int tiles = (S + 15) / 16;
+  const int units = (tiles + TPW - 1) / TPW;
+  const int nw = units < ATT2_MAXW ? units : ATT2_MAXW;
+  const int S_pad = ((S + KVB - 1) / KVB) * KVB;
+  const bool tail = (units / nw) * nw * TPW < tiles;
+  const size_t smem = (size_t)2 * S_pad * (D + 8) * sizeof(bf16) +
+                      (tail ? (size_t)nw * ((D / 8) * 4 * 32 + 4 * 32) * sizeof(float) : 0);
+  SDP_CHECK(smem <= 220 * 1024, "sdp_attention: S=%d d=%d needs %zu B of shared memory", S, D, smem);
+  auto kern = attention_bf16_mma2_kernel<D, TPW>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
+  kern<<<B * h, 32 * nw, smem, st>>>((const bf16 *)qkv, (bf16 *)out, S, h, scale_log2);
+  SDP_LAUNCH_OK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // CUDA-core path: fp32 verification mode and head dims the mma path does not cover.
 // grid (S, B*h) is too many tiny CTAs; use one CTA per (b, head) with 8 warps striding the queries.
@@ -400,6 +679,16 @@ extern "C" int sdp_attention(const void *qkv, const float *qn_w, const float *qn
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == SDP_BF16) {
     const bool aligned = (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && ((long long)h * d) % 8 == 0;
+    if (aligned && qn_w == nullptr) {
+      switch (d) {
+        case 16: return launch_attn_mma2<16, 2>(qkv, out, B, S, h, st);
+        case 32: return launch_attn_mma2<32, 2>(qkv, out, B, S, h, st);
+        case 64: return launch_attn_mma2<64, 2>(qkv, out, B, S, h, st);
+        case 96: return launch_attn_mma2<96, 2>(qkv, out, B, S, h, st);
+        case 128: return launch_attn_mma2<128, 1>(qkv, out, B, S, h, st);
+        default: break;
+      }
+    }
     if (aligned) {
       switch (d) {
         case 16: return launch_attn_mma<16>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, eps, st);

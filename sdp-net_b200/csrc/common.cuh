@@ -137,6 +137,9 @@ struct Epilogue {
   int act, res_first, res_mod;
   int seq_in, seq_out, seq_off;
   int pass_seq, pass_rows;
+  int hn_d, hn_C;
+  float hn_eps;
+  const float *hn_qw, *hn_qb, *hn_kw, *hn_kb;
 };
 
 struct RowMap {

@@ -118,7 +118,7 @@ ln_dwconv_kernel(const T *__restrict__ act, const float *__restrict__ gamma, con
     if (KS > 0) {
       float w[KS > 0 ? KS * KS : 1];
 #pragma unroll
-      for (int i = 0; i < KS * KS; ++i) w[i] = cok ? __ldg(wdw + (long long)c * KS * KS + i) : 0.0f;
+      for (int i = 0; i < KS * KS; ++i) w[i] = cok ? __ldg(wdw + (long long)i * C + c) : 0.0f;
       const int xchunks = (Gw + DW_XB - 1) / DW_XB;
       for (int item = grp; item < Gh * xchunks; item += GROUPS) {
         const int y = item / xchunks, x0 = (item % xchunks) * DW_XB;
@@ -149,12 +149,138 @@ ln_dwconv_kernel(const T *__restrict__ act, const float *__restrict__ gamma, con
         for (int dy = 0; dy < k; ++dy)
           for (int dx = 0; dx < k; ++dx)
             acc = fmaf(tile[((y + dy) * PW + x + dx) * CH + cl],
-                       cok ? __ldg(wdw + ((long long)c * k + dy) * k + dx) : 0.0f, acc);
+                       cok ? __ldg(wdw + (long long)(dy * k + dx) * C + c) : 0.0f, acc);
         if (cok) xout[(long long)(R + t) * C + c] = from_f<T>(acc);
       }
     }
     __syncthreads();
   }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// bf16 fast path.  Same structure, but a slab is 64 channels held as packed bf16x2 words:
+// lane = channel pair, so every global access is one 128-byte line per warp (token-major rows),
+// every shared access is a conflict-free LDS.32/STS.32, and each loaded word feeds two FMA
+// chains.  Depthwise taps are tap-major fp32 ([k*k, C]) so a warp reads them as one coalesced
+// LDG.64 per tap.  FMA-bound by design: per output pair 2*k*k FMAs against k*(XB+k-1)/XB LDS.
+// ---------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(DW_THREADS)
+ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ gamma,
+                      const float *__restrict__ beta, const float *__restrict__ wdw,
+                      const float *__restrict__ bdw, bf16 *__restrict__ out, int Gh, int Gw, int C, int R,
+                      float eps, int PW) {
+  extern __shared__ float smem[];
+  constexpr int lo = (KS - 1) / 2;
+  const int Tn = Gh * Gw, S = R + Tn;
+  const int PH = Gh + KS - 1;
+  float *s_mean = smem;
+  float *s_rstd = smem + Tn;
+  uint32_t *tile = reinterpret_cast<uint32_t *>(smem + 2 * Tn);      // [PH][PW][32] bf16x2
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = DW_THREADS / 32;
+  const bf16 *xin = act + (long long)b * S * C;
+  bf16 *xout = out + (long long)b * S * C;
+
+  for (int i = tid; i < R * C / 2; i += DW_THREADS) reinterpret_cast<uint32_t *>(xout)[i] = 0u;
+  // zero the whole tile once: the halo cells are never written again
+  for (int i = tid; i < PH * PW * 32; i += DW_THREADS) tile[i] = 0u;
+
+  for (int t = warp; t < Tn; t += NW) {
+    float mean, rstd;
+    token_stats<bf16>(xin + (long long)(R + t) * C, C, lane, eps, mean, rstd);
+    if (lane == 0) { s_mean[t] = mean; s_rstd[t] = rstd; }
+  }
+  __syncthreads();
+
+  const int xchunks = (Gw + DW_XB - 1) / DW_XB;
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    const int c = c0 + 2 * lane;
+    const bool cok = c < C;                       // C is even (bf16 mode: C % 8 == 0)
+    const float2 g = cok ? __ldg(reinterpret_cast<const float2 *>(gamma + c)) : make_float2(0.f, 0.f);
+    const float2 be = cok ? __ldg(reinterpret_cast<const float2 *>(beta + c)) : make_float2(0.f, 0.f);
+    // ---- stage: one token row slab (128 B) per warp-load, normalise, pack, store ----
+    for (int t0 = warp * 4; t0 < Tn; t0 += NW * 4) {
+      uint32_t raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u;
+        raw[u] = (cok && t < Tn) ? __ldg(reinterpret_cast<const uint32_t *>(xin + (long long)(R + t) * C + c)) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u;
+        if (t < Tn) {
+          const float2 v = unpack_bf16x2(raw[u]);
+          const float m = s_mean[t], r = s_rstd[t];
+          const int py = t / Gw + lo, px = t % Gw + lo;
+          tile[(py * PW + px) * 32 + lane] =
+              cok ? pack_bf16x2((v.x - m) * r * g.x + be.x, (v.y - m) * r * g.y + be.y) : 0u;
+        }
+      }
+    }
+    __syncthreads();
+    const float2 bias = (cok && bdw) ? __ldg(reinterpret_cast<const float2 *>(bdw + c)) : make_float2(0.f, 0.f);
+    const float *wc = wdw + (cok ? c : 0);
+    for (int item = warp; item < Gh * xchunks; item += NW) {
+      const int y = item / xchunks, x0 = (item % xchunks) * DW_XB;
+      float2 acc[DW_XB];
+#pragma unroll
+      for (int i = 0; i < DW_XB; ++i) acc[i] = bias;
+#pragma unroll
+      for (int dy = 0; dy < KS; ++dy) {
+        float2 w[KS];
+#pragma unroll
+        for (int dx = 0; dx < KS; ++dx)
+          w[dx] = __ldg(reinterpret_cast<const float2 *>(wc + (long long)(dy * KS + dx) * C));
+        const uint32_t *trow = tile + ((y + dy) * PW + x0) * 32 + lane;
+        float2 win[DW_XB + KS - 1];
+#pragma unroll
+        for (int xx = 0; xx < DW_XB + KS - 1; ++xx) {
+          const uint32_t u = trow[xx * 32];
+          win[xx].x = __uint_as_float(u << 16);
+          win[xx].y = __uint_as_float(u & 0xffff0000u);
+        }
+#pragma unroll
+        for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+          for (int i = 0; i < DW_XB; ++i) {
+            acc[i].x = fmaf(win[i + dx].x, w[dx].x, acc[i].x);
+            acc[i].y = fmaf(win[i + dx].y, w[dx].y, acc[i].y);
+          }
+      }
+      if (cok) {
+#pragma unroll
+        for (int i = 0; i < DW_XB; ++i)
+          if (x0 + i < Gw)
+            *reinterpret_cast<uint32_t *>(xout + (long long)(R + y * Gw + x0 + i) * C + c) =
+                pack_bf16x2(acc[i].x, acc[i].y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int KS>
+static int launch_dw_bf16(const void *act, const float *gamma, const float *beta, const float *wdw,
+                          const float *bdw, void *out, int B, int Gh, int Gw, int C, int R, float eps,
+                          cudaStream_t st) {
+  const int PW = ((Gw + DW_XB - 1) / DW_XB) * DW_XB + KS - 1;
+  const int PH = Gh + KS - 1;
+  const size_t smem = (size_t)(2 * Gh * Gw + (size_t)PH * PW * 32) * sizeof(float);
+  SDP_CHECK(smem <= 220 * 1024, "sdp_ln_dwconv: grid %dx%d with k=%d needs %zu B of shared memory", Gh, Gw, KS,
+            smem);
+  auto kern = ln_dwconv_bf16_kernel<KS>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  kern<<<B, DW_THREADS, smem, st>>>((const bf16 *)act, gamma, beta, wdw, bdw, (bf16 *)out, Gh, Gw, C, R, eps, PW);
+  SDP_LAUNCH_OK();
+  return 0;
 }
 
 template <typename T, int KS>
@@ -199,7 +325,16 @@ extern "C" int sdp_ln_dwconv(const void *act, const float *gamma, const float *b
   SDP_CHECK(B > 0 && Gh > 0 && Gw > 0 && C > 0 && k > 0 && R >= 0, "sdp_ln_dwconv: bad sizes");
   SDP_CHECK(act != out, "sdp_ln_dwconv: must not run in place (spatial neighbours are read)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == SDP_BF16) return dispatch_dw<bf16>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, st);
+  if (dtype == SDP_BF16) {
+    const bool fast = C % 2 == 0 && (reinterpret_cast<uintptr_t>(act) & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(out) & 3) == 0 && (reinterpret_cast<uintptr_t>(wdw) & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(gamma) & 7) == 0 && (reinterpret_cast<uintptr_t>(beta) & 7) == 0 &&
+                      (bdw == nullptr || (reinterpret_cast<uintptr_t>(bdw) & 7) == 0);
+    if (fast && k == 7) return launch_dw_bf16<7>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+    if (fast && k == 5) return launch_dw_bf16<5>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+    if (fast && k == 3) return launch_dw_bf16<3>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+    return dispatch_dw<bf16>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, st);
+  }
   SDP_CHECK(dtype == SDP_F32, "sdp_ln_dwconv: unknown dtype %d", dtype);
   return dispatch_dw<float>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, st);
 }

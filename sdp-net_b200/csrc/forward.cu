@@ -63,8 +63,24 @@ int encoder(const Ctx &c, const sdp_encoder_weights &w) {
   const sdp_model_desc &m = *c.m;
   const int C = m.C, M = c.B * c.S, dt = m.dtype, F = m.ff_mult * C;
   if (int rc = sdp_layernorm_rows(c.ws->act, C, w.norm1_w, w.norm1_b, c.ws->norm, C, M, C, 1e-5f, dt, c.st)) return rc;
-  if (int rc = gemm(c, c.ws->norm, C, w.w_qkv, C, nullptr, M, 3 * C, C, SDP_ACT_NONE, nullptr, c.ws->qkv, 3 * C, dt, false)) return rc;
-  if (int rc = sdp_attention(c.ws->qkv, w.qn_w, w.qn_b, w.kn_w, w.kn_b, c.ws->attn, c.B, c.S, m.n_head, C / m.n_head, 1e-5f, dt, c.st)) return rc;
+  // q/k LayerNorm (layers.py:286): fused into the QKV GEMM epilogue when the tile holds whole heads,
+  // otherwise applied by the attention kernel while it loads q and k
+  const int d = C / m.n_head;
+  const bool fuse_qk = w.qn_w != nullptr && sdp_gemm_headnorm_ok(d, 3 * C, dt);
+  {
+    sdp_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.A = c.ws->norm; a.lda = C; a.W = w.w_qkv; a.ldw = C; a.out = c.ws->qkv; a.ldo = 3 * C;
+    a.M = M; a.N = 3 * C; a.K = C; a.dtype = dt; a.out_dtype = dt; a.res_dtype = dt;
+    if (fuse_qk) {
+      a.headnorm_d = d; a.headnorm_C = C; a.headnorm_eps = 1e-5f;
+      a.hn_q_w = w.qn_w; a.hn_q_b = w.qn_b; a.hn_k_w = w.kn_w; a.hn_k_b = w.kn_b;
+    }
+    if (int rc = sdp_gemm(&a, c.st)) return rc;
+  }
+  if (int rc = sdp_attention(c.ws->qkv, fuse_qk ? nullptr : w.qn_w, fuse_qk ? nullptr : w.qn_b,
+                             fuse_qk ? nullptr : w.kn_w, fuse_qk ? nullptr : w.kn_b, c.ws->attn, c.B, c.S, m.n_head, d,
+                             1e-5f, dt, c.st)) return rc;
   if (int rc = gemm(c, c.ws->attn, C, w.w_o, C, nullptr, M, C, C, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, false)) return rc;
   if (int rc = sdp_layernorm_rows(c.ws->act, C, w.norm2_w, w.norm2_b, c.ws->norm, C, M, C, 1e-5f, dt, c.st)) return rc;
   if (int rc = gemm(c, c.ws->norm, C, w.w_ff1, C, w.b_ff1, M, F, C, m.act, nullptr, c.ws->hidden, F, dt, false)) return rc;

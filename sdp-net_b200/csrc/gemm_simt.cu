@@ -67,6 +67,10 @@ gemm_f32_simt_kernel(const float *__restrict__ A, long long lda, const float *__
 
 using namespace sdp;
 
+extern "C" int sdp_gemm_headnorm_ok(int d, int N, int dtype) {
+  return dtype == SDP_BF16 && (d == 32 || d == 64 || d == 96 || d == 128) && N % d == 0 ? 1 : 0;
+}
+
 extern "C" int sdp_gemm(const sdp_gemm_args *a, void *stream) {
   SDP_CHECK(a != nullptr, "sdp_gemm: null args");
   SDP_CHECK(a->M > 0 && a->N > 0 && a->K > 0, "sdp_gemm: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
@@ -92,6 +96,17 @@ extern "C" int sdp_gemm(const sdp_gemm_args *a, void *stream) {
   e.seq_off = a->seq_off;
   e.pass_seq = a->pass_seq;
   e.pass_rows = a->pass_rows;
+  e.hn_d = a->headnorm_d;
+  e.hn_C = a->headnorm_C;
+  e.hn_eps = a->headnorm_eps;
+  e.hn_qw = a->hn_q_w; e.hn_qb = a->hn_q_b; e.hn_kw = a->hn_k_w; e.hn_kb = a->hn_k_b;
+  if (a->headnorm_d) {
+    SDP_CHECK(sdp_gemm_headnorm_ok(a->headnorm_d, a->N, a->dtype), "sdp_gemm: head-norm unsupported for d=%d N=%d dtype=%d",
+              a->headnorm_d, a->N, a->dtype);
+    SDP_CHECK(a->bias == nullptr && a->hn_q_w && a->hn_q_b && a->hn_k_w && a->hn_k_b && a->headnorm_C > 0 &&
+                  a->headnorm_C % a->headnorm_d == 0,
+              "sdp_gemm: head-norm needs q/k affine parameters, no bias, and C %% d == 0");
+  }
   if (a->dtype == SDP_BF16) {
     SDP_CHECK(sdp_device_ok(), "sdp_gemm: bf16 path needs an sm_100 device (tcgen05/TMEM); none found");
     return gemm_bf16_tc(*a, e, st);

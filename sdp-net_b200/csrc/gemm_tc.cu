@@ -124,7 +124,37 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
 };
 
-template <int BN, int STAGES, int ACT>
+__host__ __device__ constexpr uint32_t tmem_cols_for(int bn) {
+  return 2 * bn <= 32 ? 32u : 2 * bn <= 64 ? 64u : 2 * bn <= 128 ? 128u : 2 * bn <= 256 ? 256u : 512u;
+}
+
+// Per-head LayerNorm over HN accumulator columns held by one thread (its own row): no shuffles.
+template <int HN>
+__device__ __forceinline__ void head_layernorm(float *v, const float *__restrict__ w, const float *__restrict__ b,
+                                               float eps) {
+  float s = 0.0f;
+#pragma unroll
+  for (int j = 0; j < HN; ++j) s += v[j];
+  const float mean = s * (1.0f / HN);
+  float q = 0.0f;
+#pragma unroll
+  for (int j = 0; j < HN; ++j) {
+    const float d = v[j] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(q * (1.0f / HN) + eps);
+#pragma unroll
+  for (int j = 0; j < HN; j += 4) {
+    const float4 wv = __ldg(reinterpret_cast<const float4 *>(w + j));
+    const float4 bv = __ldg(reinterpret_cast<const float4 *>(b + j));
+    v[j] = (v[j] - mean) * rstd * wv.x + bv.x;
+    v[j + 1] = (v[j + 1] - mean) * rstd * wv.y + bv.y;
+    v[j + 2] = (v[j + 2] - mean) * rstd * wv.z + bv.z;
+    v[j + 3] = (v[j + 3] - mean) * rstd * wv.w + bv.w;
+  }
+}
+
+template <int BN, int STAGES, int ACT, int HN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const Epilogue epi, const int K, const int vec_ok) {
@@ -142,7 +172,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t TMEM_COLS = 2 * BN;   // 128 / 256 / 512: powers of two >= 32
+  constexpr uint32_t TMEM_COLS = tmem_cols_for(BN);   // power of two >= 2 * BN
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -236,12 +266,31 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const RowMap rm = map_row(epi, m0 + quad * 32 + lane);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      if constexpr (HN > 0) {
+        static_assert(BN % HN == 0 && HN % 32 == 0, "head-norm groups must tile the N block");
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        tmem_ld32(taddr + c, v);
-        tmem_ld_wait();
-        if (n0 + c < epi.N) epilogue_row<32, false, ACT>(epi, rm, n0 + c, v, vec_ok != 0);
+        for (int c = 0; c < BN; c += HN) {
+          float v[HN];
+#pragma unroll
+          for (int i = 0; i < HN / 32; ++i) tmem_ld32(taddr + c + 32 * i, v + 32 * i);
+          tmem_ld_wait();
+          const int col0 = n0 + c;                    // a multiple of the head dim
+          if (col0 < 2 * epi.hn_C) {
+            const bool is_q = col0 < epi.hn_C;
+            head_layernorm<HN>(v, is_q ? epi.hn_qw : epi.hn_kw, is_q ? epi.hn_qb : epi.hn_kb, epi.hn_eps);
+          }
+#pragma unroll
+          for (int i = 0; i < HN / 32; ++i)
+            if (col0 + 32 * i < epi.N) epilogue_row<32, false, ACT>(epi, rm, col0 + 32 * i, v + 32 * i, vec_ok != 0);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          float v[32];
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+          if (n0 + c < epi.N) epilogue_row<32, false, ACT>(epi, rm, n0 + c, v, vec_ok != 0);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -345,10 +394,10 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, int ACT>
+template <int BN, int STAGES, int ACT, int HN = 0>
 static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tw, const Epilogue &e, int K, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
-  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT>;
+  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT, HN>;
   static bool configured = false;
   if (!configured) {
     SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -370,6 +419,23 @@ static int launch_tc_act(const CUtensorMap &ta, const CUtensorMap &tw, const Epi
 }
 
 int gemm_bf16_tc(const sdp_gemm_args &a, const Epilogue &e, cudaStream_t st) {
+  if (e.hn_d) {
+    // QKV projection with the per-head LayerNorm fused: the N block must hold whole heads
+    const int bn = e.hn_d == 96 ? 192 : (a.N % 256 == 0 ? 256 : 128);
+    SDP_CHECK(e.act == SDP_ACT_NONE, "sdp_gemm: head-norm epilogue has no activation");
+    CUtensorMap ta, tw;
+    if (int rc = get_tensor_map(a.A, a.M, a.K, a.lda, BLOCK_M, &ta)) return rc;
+    if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, bn, &tw)) return rc;
+    if (e.hn_d == 96) return launch_tc<192, 5, SDP_ACT_NONE, 96>(ta, tw, e, a.K, st);
+    if (bn == 256) {
+      if (e.hn_d == 32) return launch_tc<256, 4, SDP_ACT_NONE, 32>(ta, tw, e, a.K, st);
+      if (e.hn_d == 64) return launch_tc<256, 4, SDP_ACT_NONE, 64>(ta, tw, e, a.K, st);
+      return launch_tc<256, 4, SDP_ACT_NONE, 128>(ta, tw, e, a.K, st);
+    }
+    if (e.hn_d == 32) return launch_tc<128, 6, SDP_ACT_NONE, 32>(ta, tw, e, a.K, st);
+    if (e.hn_d == 64) return launch_tc<128, 6, SDP_ACT_NONE, 64>(ta, tw, e, a.K, st);
+    return launch_tc<128, 6, SDP_ACT_NONE, 128>(ta, tw, e, a.K, st);
+  }
   // BLOCK_N minimising padded columns; ties -> the larger tile
   int bn = 256;
   {

@@ -77,13 +77,16 @@ ln_rows_vec_kernel(const T *__restrict__ x, long long ldx, const float *__restri
     const int iv = lane + 32 * i;
     if (iv < nvec) {
       float y[EPV];
+      const int c0 = iv * EPV;
 #pragma unroll
-      for (int j = 0; j < EPV; ++j) {
-        const int c = iv * EPV + j;
-        float t = (v[i][j] - mean) * rstd;
-        if (w) t *= __ldg(w + c);
-        if (b) t += __ldg(b + c);
-        y[j] = t;
+      for (int j = 0; j < EPV; j += 4) {          // affine parameters as 128-bit loads (L1/L2 resident)
+        float4 wv = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (w) wv = __ldg(reinterpret_cast<const float4 *>(w + c0 + j));
+        if (b) bv = __ldg(reinterpret_cast<const float4 *>(b + c0 + j));
+        y[j] = (v[i][j] - mean) * rstd * wv.x + bv.x;
+        y[j + 1] = (v[i][j + 1] - mean) * rstd * wv.y + bv.y;
+        y[j + 2] = (v[i][j + 2] - mean) * rstd * wv.z + bv.z;
+        y[j + 3] = (v[i][j + 3] - mean) * rstd * wv.w + bv.w;
       }
       Vec<T>::store(orow + iv * EPV, y);
     }
@@ -126,7 +129,8 @@ static int launch_ln_rows(const void *x, long long ldx, const float *w, const fl
   const int wpb = 8;
   const dim3 grid((M + wpb - 1) / wpb), block(32 * wpb);
   const bool vec = C % EPV == 0 && (ldx * sizeof(T)) % 16 == 0 && (ldo * sizeof(T)) % 16 == 0 &&
-                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0;
   const int need = vec ? (C / EPV + 31) / 32 : 99;
 #define LN_CASE(V)                                                                             \
   if (need <= V) {                                                                             \

@@ -127,7 +127,8 @@ class Packer:
         return dict(
             ln1_g=self._f(g("layer_norm_1.gamma")), ln1_b=self._f(g("layer_norm_1.beta")),
             ln2_g=self._f(g("layer_norm_2.gamma")), ln2_b=self._f(g("layer_norm_2.beta")),
-            w_dw=self._f(wd.reshape(wd.shape[0], wd.shape[-2], wd.shape[-1])), b_dw=self._f(g("conv2d.0.bias")),
+            w_dw=self._f(wd.reshape(wd.shape[0], -1).t()),   # tap-major [k*k, C]
+            b_dw=self._f(g("conv2d.0.bias")), conv_k=int(wd.shape[-1]),
             w_pw=self._w(g("conv2d.1.weight")), b_pw=self._f(g("conv2d.1.bias")),
             w_mlp1=self._w(g("conv1d.0.weight")), b_mlp1=self._f(g("conv1d.0.bias")),
             w_mlp2=self._w(g("conv1d.2.weight")), b_mlp2=self._f(g("conv1d.2.bias")),
@@ -243,8 +244,15 @@ def run_encoder(pw: Packer, w: dict, bufs: Buffers, act_name: Optional[str] = No
     a2, n2 = bufs.act.view(M, C_), bufs.norm.view(M, C_)
     hid = bufs.hidden.view(-1)[: M * mult].view(M, mult)
     ops.layernorm_rows(a2, w["norm1_w"], w["norm1_b"], n2, 1e-5)
-    ops.gemm(n2, w["w_qkv"], bufs.qkv.view(M, 3 * C_))
-    ops.attention(bufs.qkv, bufs.attn, pw.n_head, w["qn_w"], w["qn_b"], w["kn_w"], w["kn_b"], 1e-5)
+    d = C_ // pw.n_head
+    if w["qn_w"] is not None and ops.gemm_headnorm_ok(d, 3 * C_, pw.dtype):
+        # q/k LayerNorm fused into the QKV epilogue; attention receives normalised q, k
+        ops.gemm(n2, w["w_qkv"], bufs.qkv.view(M, 3 * C_),
+                 headnorm=(d, C_, 1e-5, w["qn_w"], w["qn_b"], w["kn_w"], w["kn_b"]))
+        ops.attention(bufs.qkv, bufs.attn, pw.n_head, None, None, None, None, 1e-5)
+    else:
+        ops.gemm(n2, w["w_qkv"], bufs.qkv.view(M, 3 * C_))
+        ops.attention(bufs.qkv, bufs.attn, pw.n_head, w["qn_w"], w["qn_b"], w["kn_w"], w["kn_b"], 1e-5)
     ops.gemm(bufs.attn.view(M, C_), w["w_o"], a2, residual=a2)
     ops.layernorm_rows(a2, w["norm2_w"], w["norm2_b"], n2, 1e-5)
     ops.gemm(n2, w["w_ff1"], hid, bias=w["b_ff1"], act=act_name or pw.act)

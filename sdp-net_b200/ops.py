@@ -55,7 +55,7 @@ def act_id(name) -> int:
 def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, act="none", res_first: bool = False, res_mod: int = 0,
          seq_remap=(0, 0, 0), pass_rows=(0, 0), M: Optional[int] = None, N: Optional[int] = None,
-         K: Optional[int] = None) -> torch.Tensor:
+         K: Optional[int] = None, headnorm=None) -> torch.Tensor:
     """out = epi(A[M,K] @ W[N,K]^T); see sdp_gemm in the header for the epilogue definition."""
     if A.dim() != 2 or W.dim() != 2 or out.dim() != 2:
         raise ValueError("gemm operands must be 2-D (views with a row pitch are fine)")
@@ -79,8 +79,17 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, bias: Optional[
     a.act, a.res_first, a.res_mod = act_id(act), int(res_first), int(res_mod)
     a.seq_in, a.seq_out, a.seq_off = (int(v) for v in seq_remap)
     a.pass_seq, a.pass_rows = (int(v) for v in pass_rows)
+    if headnorm is not None:      # (head_dim, C, eps, q_w, q_b, k_w, k_b): per-head LayerNorm on the q|k columns
+        d, Cm, eps, qw, qb, kw, kb = headnorm
+        a.headnorm_d, a.headnorm_C, a.headnorm_eps = int(d), int(Cm), float(eps)
+        a.hn_q_w, a.hn_q_b = _p(_f32(qw, "q_norm.weight")), _p(_f32(qb, "q_norm.bias"))
+        a.hn_k_w, a.hn_k_b = _p(_f32(kw, "k_norm.weight")), _p(_f32(kb, "k_norm.bias"))
     L.check(L.lib().sdp_gemm(C.byref(a), _stream()), "sdp_gemm")
     return out
+
+
+def gemm_headnorm_ok(head_dim: int, N: int, dtype: torch.dtype) -> bool:
+    return bool(L.lib().sdp_gemm_headnorm_ok(int(head_dim), int(N), _DT[dtype]))
 
 
 def im2col_patches(x: torch.Tensor, A: torch.Tensor, patch: int) -> torch.Tensor:
@@ -116,7 +125,9 @@ def ln_dwconv(act: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, wdw: t
     B, S, Cc = act.shape
     if S != R + Gh * Gw or not act.is_contiguous() or not out.is_contiguous():
         raise ValueError("ln_dwconv: act must be contiguous [B, R + Gh*Gw, C]")
-    k = wdw.shape[-1]
+    k = int(round(wdw.shape[0] ** 0.5))      # wdw is tap-major [k*k, C]
+    if wdw.dim() != 2 or k * k != wdw.shape[0] or wdw.shape[1] != Cc:
+        raise ValueError("ln_dwconv: wdw must be tap-major [k*k, C]")
     L.check(L.lib().sdp_ln_dwconv(_p(act), _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")),
                                   _p(_f32(wdw, "wdw")), _p(_f32(bdw, "bdw")), _p(out), B, Gh, Gw, Cc, k, R,
                                   float(eps), _dt(act), _stream()), "sdp_ln_dwconv")

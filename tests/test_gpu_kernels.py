@@ -119,6 +119,27 @@ def test_gemm_bf16_patch_embed_epilogue(sdp):
     assert (act[:, :R] == 7.0).all()                 # register rows untouched
 
 
+@pytest.mark.parametrize("C,h", [(768, 8), (512, 8), (128, 4), (256, 2), (192, 2)])
+def test_gemm_bf16_headnorm_epilogue(sdp, C, h):
+    """QKV projection with the per-head q/k LayerNorm (layers.py:236-237,286) fused in the epilogue."""
+    d, M = C // h, 333
+    assert sdp.ops.gemm_headnorm_ok(d, 3 * C, torch.bfloat16)
+    A = rnd(M, C, seed=60, dtype=torch.bfloat16)
+    W = rnd(3 * C, C, seed=61, scale=2 / math.sqrt(C), dtype=torch.bfloat16)
+    qw, qb = rnd(d, seed=62) * 0.3 + 1, rnd(d, seed=63) * 0.3
+    kw, kb = rnd(d, seed=64) * 0.3 + 1, rnd(d, seed=65) * 0.3
+    out = torch.empty(M, 3 * C, device="cuda", dtype=torch.float32)
+    sdp.ops.gemm(A, W, out, headnorm=(d, C, 1e-5, qw, qb, kw, kb))
+    raw = A.float() @ W.float().t()
+    q, k, v = raw.split(C, dim=-1)
+    q = F.layer_norm(q.view(M, h, d), (d,), qw, qb, 1e-5).view(M, C)
+    k = F.layer_norm(k.view(M, h, d), (d,), kw, kb, 1e-5).view(M, C)
+    ref = torch.cat([q, k, v], -1)
+    assert (out - ref).abs().max() < 2e-3
+    assert not sdp.ops.gemm_headnorm_ok(16, 96, torch.bfloat16)
+    assert not sdp.ops.gemm_headnorm_ok(96, 2304, torch.float32)
+
+
 @pytest.mark.parametrize("M,N,K", [(70, 50, 33), (129, 65, 100), (300, 128, 64)])
 def test_gemm_fp32(sdp, M, N, K):
     A, W = rnd(M, K, seed=13), rnd(N, K, seed=14, scale=1 / math.sqrt(K))
@@ -251,7 +272,7 @@ def test_ln_dwconv(sdp, dtype, Gh, Gw, C, k, R, bias):
     wdw = rnd(C, k, k, seed=43, scale=1 / k)
     bdw = rnd(C, seed=44) if bias else None
     out = torch.full_like(act, float("nan"))
-    sdp.ops.ln_dwconv(act, gamma, beta, wdw, bdw, out, Gh, Gw, R)
+    sdp.ops.ln_dwconv(act, gamma, beta, wdw.reshape(C, k * k).t().contiguous(), bdw, out, Gh, Gw, R)
     ref = dw_ref(act, R, Gh, Gw, gamma, beta, wdw, bdw)
     assert (out[:, :R] == 0).all()
     tol = 4e-2 if dtype == torch.bfloat16 else 5e-5
@@ -276,7 +297,9 @@ def attn_ref(qkv, h, qn_w, qn_b, kn_w, kn_b, eps=1e-5):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("S,h,d,norm", [(261, 8, 96, True), (201, 8, 64, True), (201, 8, 96, False), (9, 4, 32, True),
                                         (68, 2, 16, True), (20, 4, 8, True), (33, 3, 24, False), (300, 2, 128, True),
-                                        (17, 4, 32, True), (32, 2, 64, True)])
+                                        (17, 4, 32, True), (32, 2, 64, True), (261, 8, 96, False), (201, 8, 64, False),
+                                        (513, 2, 96, False), (400, 2, 64, False), (256, 4, 32, False),
+                                        (16, 2, 16, False), (300, 1, 128, False), (1, 2, 32, False)])
 def test_attention(sdp, dtype, S, h, d, norm):
     B, C = 2, h * d
     qkv = rnd(B, S, 3 * C, seed=50, scale=1.5).to(dtype)
