@@ -166,7 +166,7 @@ ln_dwconv_kernel(const T *__restrict__ act, const float *__restrict__ gamma, con
 // LDG.64 per tap.  FMA-bound by design: per output pair 2*k*k FMAs against k*(XB+k-1)/XB LDS.
 // ---------------------------------------------------------------------------------------
 template <int KS>
-__global__ void __launch_bounds__(DW_THREADS)
+__global__ void __launch_bounds__(DW_THREADS, 2)
 ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ gamma,
                       const float *__restrict__ beta, const float *__restrict__ wdw,
                       const float *__restrict__ bdw, bf16 *__restrict__ out, int Gh, int Gw, int C, int R,
@@ -175,9 +175,11 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
   constexpr int lo = (KS - 1) / 2;
   const int Tn = Gh * Gw, S = R + Tn;
   const int PH = Gh + KS - 1;
-  float *s_mean = smem;
-  float *s_rstd = smem + Tn;
-  uint32_t *tile = reinterpret_cast<uint32_t *>(smem + 2 * Tn);      // [PH][PW][32] bf16x2
+  float *s_mean = smem;                                              // [Tn]
+  float *s_rstd = smem + Tn;                                         // [Tn]
+  int *s_off = reinterpret_cast<int *>(smem + 2 * Tn);               // [Tn] tile cell of token t
+  float2 *s_w = reinterpret_cast<float2 *>(smem + 3 * Tn + (Tn & 1));   // [KS*KS][32] taps of the slab (8B aligned)
+  uint32_t *tile = reinterpret_cast<uint32_t *>(s_w + KS * KS * 32);    // [PH][PW][32] bf16x2
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = DW_THREADS / 32;
@@ -187,6 +189,7 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
   for (int i = tid; i < R * C / 2; i += DW_THREADS) reinterpret_cast<uint32_t *>(xout)[i] = 0u;
   // zero the whole tile once: the halo cells are never written again
   for (int i = tid; i < PH * PW * 32; i += DW_THREADS) tile[i] = 0u;
+  for (int t = tid; t < Tn; t += DW_THREADS) s_off[t] = ((t / Gw + lo) * PW + (t % Gw + lo)) * 32;
 
   for (int t = warp; t < Tn; t += NW) {
     float mean, rstd;
@@ -201,31 +204,32 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
     const bool cok = c < C;                       // C is even (bf16 mode: C % 8 == 0)
     const float2 g = cok ? __ldg(reinterpret_cast<const float2 *>(gamma + c)) : make_float2(0.f, 0.f);
     const float2 be = cok ? __ldg(reinterpret_cast<const float2 *>(beta + c)) : make_float2(0.f, 0.f);
-    // ---- stage: one token row slab (128 B) per warp-load, normalise, pack, store ----
-    for (int t0 = warp * 4; t0 < Tn; t0 += NW * 4) {
-      uint32_t raw[4];
+    // slab taps -> shared (one coalesced 256-byte row per tap)
+    for (int i = warp; i < KS * KS; i += NW)
+      s_w[i * 32 + lane] = cok ? __ldg(reinterpret_cast<const float2 *>(wdw + (long long)i * C + c)) : make_float2(0.f, 0.f);
+    // ---- stage: 8 token rows (128 B each) in flight per warp; normalise, pack, store ----
+    const bf16 *xc = xin + (long long)R * C + (cok ? c : 0);
+    for (int t0 = warp; t0 < Tn; t0 += NW * 8) {
+      uint32_t raw[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int t = t0 + u;
-        raw[u] = (cok && t < Tn) ? __ldg(reinterpret_cast<const uint32_t *>(xin + (long long)(R + t) * C + c)) : 0u;
+      for (int u = 0; u < 8; ++u) {
+        const int t = t0 + u * NW;
+        raw[u] = (t < Tn) ? __ldg(reinterpret_cast<const uint32_t *>(xc + (long long)t * C)) : 0u;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int t = t0 + u;
+      for (int u = 0; u < 8; ++u) {
+        const int t = t0 + u * NW;
         if (t < Tn) {
-          const float2 v = unpack_bf16x2(raw[u]);
           const float m = s_mean[t], r = s_rstd[t];
-          const int py = t / Gw + lo, px = t % Gw + lo;
-          tile[(py * PW + px) * 32 + lane] =
-              cok ? pack_bf16x2((v.x - m) * r * g.x + be.x, (v.y - m) * r * g.y + be.y) : 0u;
+          const float lo_v = __uint_as_float(raw[u] << 16), hi_v = __uint_as_float(raw[u] & 0xffff0000u);
+          tile[s_off[t] + lane] = cok ? pack_bf16x2((lo_v - m) * r * g.x + be.x, (hi_v - m) * r * g.y + be.y) : 0u;
         }
       }
     }
     __syncthreads();
     const float2 bias = (cok && bdw) ? __ldg(reinterpret_cast<const float2 *>(bdw + c)) : make_float2(0.f, 0.f);
-    const float *wc = wdw + (cok ? c : 0);
     for (int item = warp; item < Gh * xchunks; item += NW) {
-      const int y = item / xchunks, x0 = (item % xchunks) * DW_XB;
+      const int y = item / xchunks, x0 = (item - y * xchunks) * DW_XB;
       float2 acc[DW_XB];
 #pragma unroll
       for (int i = 0; i < DW_XB; ++i) acc[i] = bias;
@@ -233,8 +237,7 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
       for (int dy = 0; dy < KS; ++dy) {
         float2 w[KS];
 #pragma unroll
-        for (int dx = 0; dx < KS; ++dx)
-          w[dx] = __ldg(reinterpret_cast<const float2 *>(wc + (long long)(dy * KS + dx) * C));
+        for (int dx = 0; dx < KS; ++dx) w[dx] = s_w[(dy * KS + dx) * 32 + lane];
         const uint32_t *trow = tile + ((y + dy) * PW + x0) * 32 + lane;
         float2 win[DW_XB + KS - 1];
 #pragma unroll
@@ -252,11 +255,10 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
           }
       }
       if (cok) {
+        bf16 *op = xout + (long long)(R + y * Gw + x0) * C + c;
 #pragma unroll
         for (int i = 0; i < DW_XB; ++i)
-          if (x0 + i < Gw)
-            *reinterpret_cast<uint32_t *>(xout + (long long)(R + y * Gw + x0 + i) * C + c) =
-                pack_bf16x2(acc[i].x, acc[i].y);
+          if (x0 + i < Gw) *reinterpret_cast<uint32_t *>(op + (long long)i * C) = pack_bf16x2(acc[i].x, acc[i].y);
       }
     }
     __syncthreads();
@@ -269,7 +271,8 @@ static int launch_dw_bf16(const void *act, const float *gamma, const float *beta
                           cudaStream_t st) {
   const int PW = ((Gw + DW_XB - 1) / DW_XB) * DW_XB + KS - 1;
   const int PH = Gh + KS - 1;
-  const size_t smem = (size_t)(2 * Gh * Gw + (size_t)PH * PW * 32) * sizeof(float);
+  const int Tn = Gh * Gw;
+  const size_t smem = (size_t)(3 * Tn + (Tn & 1) + 2 * KS * KS * 32 + (size_t)PH * PW * 32) * sizeof(float);
   SDP_CHECK(smem <= 220 * 1024, "sdp_ln_dwconv: grid %dx%d with k=%d needs %zu B of shared memory", Gh, Gw, KS,
             smem);
   auto kern = ln_dwconv_bf16_kernel<KS>;

@@ -18,8 +18,8 @@ namespace sdp {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;      // 64 bf16 = 128 bytes = one swizzle-128B atom row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
-constexpr int EPI_WARP0 = 2;
+constexpr int GEMM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_WARPS = 8;
 
 // ---------------------------------------------------------------------------------------
 // PTX wrappers
@@ -128,32 +128,6 @@ __host__ __device__ constexpr uint32_t tmem_cols_for(int bn) {
   return 2 * bn <= 32 ? 32u : 2 * bn <= 64 ? 64u : 2 * bn <= 128 ? 128u : 2 * bn <= 256 ? 256u : 512u;
 }
 
-// Per-head LayerNorm over HN accumulator columns held by one thread (its own row): no shuffles.
-template <int HN>
-__device__ __forceinline__ void head_layernorm(float *v, const float *__restrict__ w, const float *__restrict__ b,
-                                               float eps) {
-  float s = 0.0f;
-#pragma unroll
-  for (int j = 0; j < HN; ++j) s += v[j];
-  const float mean = s * (1.0f / HN);
-  float q = 0.0f;
-#pragma unroll
-  for (int j = 0; j < HN; ++j) {
-    const float d = v[j] - mean;
-    q = fmaf(d, d, q);
-  }
-  const float rstd = rsqrtf(q * (1.0f / HN) + eps);
-#pragma unroll
-  for (int j = 0; j < HN; j += 4) {
-    const float4 wv = __ldg(reinterpret_cast<const float4 *>(w + j));
-    const float4 bv = __ldg(reinterpret_cast<const float4 *>(b + j));
-    v[j] = (v[j] - mean) * rstd * wv.x + bv.x;
-    v[j + 1] = (v[j + 1] - mean) * rstd * wv.y + bv.y;
-    v[j + 2] = (v[j + 2] - mean) * rstd * wv.z + bv.z;
-    v[j + 3] = (v[j + 3] - mean) * rstd * wv.w + bv.w;
-  }
-}
-
 template <int BN, int STAGES, int ACT, int HN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -183,7 +157,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);        // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), EPI_WARPS);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -255,7 +229,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ================= epilogue =================
+    // Two warps per TMEM lane quadrant: warps 2..5 take the low half of the tile's columns,
+    // warps 6..9 the high half.  One thread = one output row.
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;
+    constexpr int UNIT = HN > 0 ? HN : 32;     // columns finished together (whole heads with head-norm)
+    constexpr int UNITS = BN / UNIT;
+    constexpr int U_LO = (UNITS + 1) / 2;      // units of the low half
+    const int u_begin = half == 0 ? 0 : U_LO, u_end = half == 0 ? U_LO : UNITS;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -266,30 +247,64 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const RowMap rm = map_row(epi, m0 + quad * 32 + lane);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
-      if constexpr (HN > 0) {
-        static_assert(BN % HN == 0 && HN % 32 == 0, "head-norm groups must tile the N block");
 #pragma unroll 1
-        for (int c = 0; c < BN; c += HN) {
-          float v[HN];
-#pragma unroll
-          for (int i = 0; i < HN / 32; ++i) tmem_ld32(taddr + c + 32 * i, v + 32 * i);
-          tmem_ld_wait();
-          const int col0 = n0 + c;                    // a multiple of the head dim
+      for (int u = u_begin; u < u_end; ++u) {
+        const int c = u * UNIT;
+        const int col0 = n0 + c;
+        if (col0 >= epi.N) break;
+        float mean = 0.0f, rstd = 1.0f;
+        const float *hw = nullptr, *hb = nullptr;
+        if constexpr (HN > 0) {
+          // per-head LayerNorm over this thread's HN accumulator columns: TMEM is re-read per pass
+          // (cheap) instead of holding HN values in registers
           if (col0 < 2 * epi.hn_C) {
-            const bool is_q = col0 < epi.hn_C;
-            head_layernorm<HN>(v, is_q ? epi.hn_qw : epi.hn_kw, is_q ? epi.hn_qb : epi.hn_kb, epi.hn_eps);
-          }
-#pragma unroll
-          for (int i = 0; i < HN / 32; ++i)
-            if (col0 + 32 * i < epi.N) epilogue_row<32, false, ACT>(epi, rm, col0 + 32 * i, v + 32 * i, vec_ok != 0);
-        }
-      } else {
+            float s = 0.0f;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+            for (int i = 0; i < HN; i += 32) {
+              float v[32];
+              tmem_ld32(taddr + c + i, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s += v[j];
+            }
+            mean = s * (1.0f / HN);
+            float q = 0.0f;
+#pragma unroll 1
+            for (int i = 0; i < HN; i += 32) {
+              float v[32];
+              tmem_ld32(taddr + c + i, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float dlt = v[j] - mean;
+                q = fmaf(dlt, dlt, q);
+              }
+            }
+            rstd = rsqrtf(q * (1.0f / HN) + epi.hn_eps);
+            const bool is_q = col0 < epi.hn_C;
+            hw = is_q ? epi.hn_qw : epi.hn_kw;
+            hb = is_q ? epi.hn_qb : epi.hn_kb;
+          }
+        }
+#pragma unroll 1
+        for (int i = 0; i < UNIT; i += 32) {
           float v[32];
-          tmem_ld32(taddr + c, v);
+          tmem_ld32(taddr + c + i, v);
           tmem_ld_wait();
-          if (n0 + c < epi.N) epilogue_row<32, false, ACT>(epi, rm, n0 + c, v, vec_ok != 0);
+          if constexpr (HN > 0) {
+            if (hw != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 wv = __ldg(reinterpret_cast<const float4 *>(hw + i + j));
+                const float4 bv = __ldg(reinterpret_cast<const float4 *>(hb + i + j));
+                v[j] = (v[j] - mean) * rstd * wv.x + bv.x;
+                v[j + 1] = (v[j + 1] - mean) * rstd * wv.y + bv.y;
+                v[j + 2] = (v[j + 2] - mean) * rstd * wv.z + bv.z;
+                v[j + 3] = (v[j + 3] - mean) * rstd * wv.w + bv.w;
+              }
+            }
+          }
+          if (col0 + i < epi.N) epilogue_row<32, false, ACT>(epi, rm, col0 + i, v, vec_ok != 0);
         }
       }
       tc_fence_before();
