@@ -356,44 +356,58 @@ __device__ __forceinline__ void attn_tiles(const bf16 *__restrict__ base, int C,
       }
     }
     uint32_t pa[NT][KVB / 16][4];
+    const bool last = kb + KVB > S;              // only the final KV block holds padded keys (block-uniform)
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
+      if (last) {
+#pragma unroll
+        for (int n = 0; n < KVB / 8; ++n)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (kb + n * 8 + qd * 2 + (j & 1) >= S) sc[t][n][j] = -INFINITY;
+      }
       float bm_lo = -INFINITY, bm_hi = -INFINITY;
 #pragma unroll
-      for (int n = 0; n < KVB / 8; ++n)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int key = kb + n * 8 + qd * 2 + (j & 1);
-          const float v = key < S ? sc[t][n][j] * scale_log2 : -INFINITY;
-          sc[t][n][j] = v;
-          if (j < 2) bm_lo = fmaxf(bm_lo, v); else bm_hi = fmaxf(bm_hi, v);
-        }
+      for (int n = 0; n < KVB / 8; ++n) {
+        bm_lo = fmaxf(bm_lo, fmaxf(sc[t][n][0], sc[t][n][1]));
+        bm_hi = fmaxf(bm_hi, fmaxf(sc[t][n][2], sc[t][n][3]));
+      }
       bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 1));
       bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
       bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 1));
       bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 2));
-      // every KV block holds at least one live key, so the new maxima are finite
-      const float mn_lo = fmaxf(m_[t][0], bm_lo), mn_hi = fmaxf(m_[t][1], bm_hi);
-      const float cr_lo = fast_ex2(m_[t][0] - mn_lo), cr_hi = fast_ex2(m_[t][1] - mn_hi);
-      m_[t][0] = mn_lo; m_[t][1] = mn_hi;
+      bm_lo *= scale_log2;                       // maxima live in the exp2 domain; every block has a live key
+      bm_hi *= scale_log2;
+      // Lazy rescale: the reference max only moves when a row's block max exceeds it by more than
+      // 2^8 (p then stays <= 256, exact enough in fp32 / bf16); O and l always share one reference,
+      // so the final O / l is unchanged.  After the first block this almost never fires.
+      const bool need = bm_lo > m_[t][0] + 8.0f || bm_hi > m_[t][1] + 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float mn_lo = fmaxf(m_[t][0], bm_lo), mn_hi = fmaxf(m_[t][1], bm_hi);
+        const float cr_lo = fast_ex2(m_[t][0] - mn_lo), cr_hi = fast_ex2(m_[t][1] - mn_hi);
+        m_[t][0] = mn_lo; m_[t][1] = mn_hi;
+        l_[t][0] *= cr_lo;
+        l_[t][1] *= cr_hi;
+#pragma unroll
+        for (int n = 0; n < D / 8; ++n) {
+          o[t][n][0] *= cr_lo; o[t][n][1] *= cr_lo;
+          o[t][n][2] *= cr_hi; o[t][n][3] *= cr_hi;
+        }
+      }
+      const float nm_lo = -m_[t][0], nm_hi = -m_[t][1];
       float ps_lo = 0.0f, ps_hi = 0.0f;
 #pragma unroll
       for (int n = 0; n < KVB / 8; ++n) {
-        const float p0 = fast_ex2(sc[t][n][0] - mn_lo), p1 = fast_ex2(sc[t][n][1] - mn_lo);
-        const float p2 = fast_ex2(sc[t][n][2] - mn_hi), p3 = fast_ex2(sc[t][n][3] - mn_hi);
+        const float p0 = fast_ex2(fmaf(sc[t][n][0], scale_log2, nm_lo)), p1 = fast_ex2(fmaf(sc[t][n][1], scale_log2, nm_lo));
+        const float p2 = fast_ex2(fmaf(sc[t][n][2], scale_log2, nm_hi)), p3 = fast_ex2(fmaf(sc[t][n][3], scale_log2, nm_hi));
         ps_lo += p0 + p1;
         ps_hi += p2 + p3;
         // C-fragment of score tile n -> A-fragment of k16 step n/2 (a0,a1 from the even tile; a2,a3 from the odd)
         pa[t][n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0, p1);
         pa[t][n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p2, p3);
       }
-      l_[t][0] = l_[t][0] * cr_lo + ps_lo;
-      l_[t][1] = l_[t][1] * cr_hi + ps_hi;
-#pragma unroll
-      for (int n = 0; n < D / 8; ++n) {
-        o[t][n][0] *= cr_lo; o[t][n][1] *= cr_lo;
-        o[t][n][2] *= cr_hi; o[t][n][3] *= cr_hi;
-      }
+      l_[t][0] += ps_lo;
+      l_[t][1] += ps_hi;
     }
 #pragma unroll
     for (int kt = 0; kt < KVB / 16; ++kt) {
@@ -541,7 +555,7 @@ static int launch_attn_mma2(const void *qkv, void *out, int B, int S, int h, cud
   const bool tail = (units / nw) * nw * TPW < tiles;
   const size_t smem = (size_t)2 * S_pad * (D + 8) * sizeof(bf16) +
                       (tail ? (size_t)nw * ((D / 8) * 4 * 32 + 4 * 32) * sizeof(float) : 0);
-  SDP_CHECK(smem <= 220 * 1024, "sdp_attention: S=%d d=%d needs %zu B of shared memory", S, D, smem);
+  if (smem > 220 * 1024) return -1;             // does not fit: the dispatcher tries the next kernel
   auto kern = attention_bf16_mma2_kernel<D, TPW>;
   static size_t configured = 0;
   if (smem > configured) {
@@ -632,7 +646,7 @@ static int launch_attn_mma(const void *qkv, const float *qn_w, const float *qn_b
   const int tpc = (tiles + ny - 1) / ny;
   const int S_pad = ((S + KVB - 1) / KVB) * KVB;
   const size_t smem = (size_t)2 * S_pad * (D + 8) * sizeof(bf16);
-  SDP_CHECK(smem <= 220 * 1024, "sdp_attention: S=%d d=%d needs %zu B of shared memory", S, D, smem);
+  if (smem > 220 * 1024) return -1;             // does not fit: the dispatcher falls back to the CUDA-core kernel
   auto kern = attention_bf16_mma_kernel<D>;
   static size_t configured = 0;
   if (smem > configured) {
@@ -679,25 +693,28 @@ extern "C" int sdp_attention(const void *qkv, const float *qn_w, const float *qn
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == SDP_BF16) {
     const bool aligned = (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && ((long long)h * d) % 8 == 0;
+    int rc = -1;
     if (aligned && qn_w == nullptr) {
       switch (d) {
-        case 16: return launch_attn_mma2<16, 2>(qkv, out, B, S, h, st);
-        case 32: return launch_attn_mma2<32, 2>(qkv, out, B, S, h, st);
-        case 64: return launch_attn_mma2<64, 2>(qkv, out, B, S, h, st);
-        case 96: return launch_attn_mma2<96, 2>(qkv, out, B, S, h, st);
-        case 128: return launch_attn_mma2<128, 1>(qkv, out, B, S, h, st);
+        case 16: rc = launch_attn_mma2<16, 2>(qkv, out, B, S, h, st); break;
+        case 32: rc = launch_attn_mma2<32, 2>(qkv, out, B, S, h, st); break;
+        case 64: rc = launch_attn_mma2<64, 2>(qkv, out, B, S, h, st); break;
+        case 96: rc = launch_attn_mma2<96, 2>(qkv, out, B, S, h, st); break;
+        case 128: rc = launch_attn_mma2<128, 1>(qkv, out, B, S, h, st); break;
         default: break;
       }
+      if (rc >= 0) return rc;
     }
     if (aligned) {
       switch (d) {
-        case 16: return launch_attn_mma<16>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, eps, st);
-        case 32: return launch_attn_mma<32>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, eps, st);
-        case 64: return launch_attn_mma<64>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, eps, st);
-        case 96: return launch_attn_mma<96>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, eps, st);
-        case 128: return launch_attn_mma<128>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, eps, st);
+        case 16: rc = launch_attn_mma<16>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, eps, st); break;
+        case 32: rc = launch_attn_mma<32>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, eps, st); break;
+        case 64: rc = launch_attn_mma<64>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, eps, st); break;
+        case 96: rc = launch_attn_mma<96>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, eps, st); break;
+        case 128: rc = launch_attn_mma<128>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, eps, st); break;
         default: break;
       }
+      if (rc >= 0) return rc;
     }
     return launch_attn_simt<bf16>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, d, eps, st);
   }

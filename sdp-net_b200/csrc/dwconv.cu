@@ -165,69 +165,128 @@ ln_dwconv_kernel(const T *__restrict__ act, const float *__restrict__ gamma, con
 // chains.  Depthwise taps are tap-major fp32 ([k*k, C]) so a warp reads them as one coalesced
 // LDG.64 per tap.  FMA-bound by design: per output pair 2*k*k FMAs against k*(XB+k-1)/XB LDS.
 // ---------------------------------------------------------------------------------------
+constexpr int DWF_THREADS = 512;   // fast path: one 16-warp CTA per SM
+
+__device__ __forceinline__ void dw_cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// Shared-memory carve-up of the fast kernel (floats); shared with the launcher.
+struct DwLayout {
+  int stats, off, w, raw, tile, total;
+  __host__ __device__ DwLayout(int Tn, int PH, int PW, int KS) {
+    stats = 0;                                 // mean[Tn], rstd[Tn]
+    off = 2 * Tn;                              // int[Tn]
+    w = (3 * Tn + 3) & ~3;                     // 2 x [KS*KS][32] float2 (16-byte aligned)
+    raw = w + 2 * KS * KS * 64;                // [Tn][32] raw bf16x2 words of the NEXT slab
+    tile = raw + Tn * 32;                      // [PH][PW][32] normalised bf16x2, zero halo
+    total = tile + PH * PW * 32;
+  }
+};
+
 template <int KS>
-__global__ void __launch_bounds__(DW_THREADS, 2)
+__global__ void __launch_bounds__(DWF_THREADS, 1)
 ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ gamma,
                       const float *__restrict__ beta, const float *__restrict__ wdw,
                       const float *__restrict__ bdw, bf16 *__restrict__ out, int Gh, int Gw, int C, int R,
                       float eps, int PW) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   constexpr int lo = (KS - 1) / 2;
+  constexpr int NW = DWF_THREADS / 32;
   const int Tn = Gh * Gw, S = R + Tn;
   const int PH = Gh + KS - 1;
-  float *s_mean = smem;                                              // [Tn]
-  float *s_rstd = smem + Tn;                                         // [Tn]
-  int *s_off = reinterpret_cast<int *>(smem + 2 * Tn);               // [Tn] tile cell of token t
-  float2 *s_w = reinterpret_cast<float2 *>(smem + 3 * Tn + (Tn & 1));   // [KS*KS][32] taps of the slab (8B aligned)
-  uint32_t *tile = reinterpret_cast<uint32_t *>(s_w + KS * KS * 32);    // [PH][PW][32] bf16x2
+  const DwLayout L(Tn, PH, PW, KS);
+  float *s_mean = smem + L.stats;
+  float *s_rstd = s_mean + Tn;
+  int *s_off = reinterpret_cast<int *>(smem + L.off);
+  float2 *s_w = reinterpret_cast<float2 *>(smem + L.w);
+  uint32_t *s_raw = reinterpret_cast<uint32_t *>(smem + L.raw);
+  uint32_t *tile = reinterpret_cast<uint32_t *>(smem + L.tile);
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = DW_THREADS / 32;
-  const bf16 *xin = act + (long long)b * S * C;
+  const bf16 *xin = act + ((long long)b * S + R) * C;       // first patch row of this image
   bf16 *xout = out + (long long)b * S * C;
+  const uint32_t raw_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_raw));
+  const uint32_t w_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_w));
 
-  for (int i = tid; i < R * C / 2; i += DW_THREADS) reinterpret_cast<uint32_t *>(xout)[i] = 0u;
+  // async prefetch of one slab: raw token rows (128 B each) and the slab's taps (256 B per tap)
+  auto prefetch = [&](int c0, int buf) {
+    const int chunks = min(8, (C - c0) / 8);               // 16-byte chunks of live channels per token
+    for (int i = tid; i < Tn * 8; i += DWF_THREADS) {
+      const int t = i >> 3, ch = i & 7;
+      if (ch < chunks) dw_cp_async16(raw_addr + (uint32_t)(t * 128 + ch * 16), xin + (long long)t * C + c0 + ch * 8);
+    }
+    const int wchunks = min(16, (C - c0) / 4);
+    for (int i = tid; i < KS * KS * 16; i += DWF_THREADS) {
+      const int tap = i >> 4, ch = i & 15;
+      if (ch < wchunks)
+        dw_cp_async16(w_addr + (uint32_t)((buf * KS * KS + tap) * 256 + ch * 16), wdw + (long long)tap * C + c0 + ch * 4);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(0, 0);
+
+  for (int i = tid; i < R * C / 2; i += DWF_THREADS) reinterpret_cast<uint32_t *>(xout)[i] = 0u;
   // zero the whole tile once: the halo cells are never written again
-  for (int i = tid; i < PH * PW * 32; i += DW_THREADS) tile[i] = 0u;
-  for (int t = tid; t < Tn; t += DW_THREADS) s_off[t] = ((t / Gw + lo) * PW + (t % Gw + lo)) * 32;
+  for (int i = tid; i < PH * PW * 32; i += DWF_THREADS) tile[i] = 0u;
+  for (int t = tid; t < Tn; t += DWF_THREADS) s_off[t] = ((t / Gw + lo) * PW + (t % Gw + lo)) * 32;
 
-  for (int t = warp; t < Tn; t += NW) {
-    float mean, rstd;
-    token_stats<bf16>(xin + (long long)(R + t) * C, C, lane, eps, mean, rstd);
-    if (lane == 0) { s_mean[t] = mean; s_rstd[t] = rstd; }
-  }
-  __syncthreads();
-
-  const int xchunks = (Gw + DW_XB - 1) / DW_XB;
-  for (int c0 = 0; c0 < C; c0 += 64) {
-    const int c = c0 + 2 * lane;
-    const bool cok = c < C;                       // C is even (bf16 mode: C % 8 == 0)
-    const float2 g = cok ? __ldg(reinterpret_cast<const float2 *>(gamma + c)) : make_float2(0.f, 0.f);
-    const float2 be = cok ? __ldg(reinterpret_cast<const float2 *>(beta + c)) : make_float2(0.f, 0.f);
-    // slab taps -> shared (one coalesced 256-byte row per tap)
-    for (int i = warp; i < KS * KS; i += NW)
-      s_w[i * 32 + lane] = cok ? __ldg(reinterpret_cast<const float2 *>(wdw + (long long)i * C + c)) : make_float2(0.f, 0.f);
-    // ---- stage: 8 token rows (128 B each) in flight per warp; normalise, pack, store ----
-    const bf16 *xc = xin + (long long)R * C + (cok ? c : 0);
-    for (int t0 = warp; t0 < Tn; t0 += NW * 8) {
-      uint32_t raw[8];
+  // ---- phase 1: token statistics, one pass with the row's first element as shift (no
+  //      cancellation: the shift is within a few sigma of the mean), 4 tokens in flight per warp ----
+  {
+    const int nv = C >> 3;
+    for (int t0 = warp * 4; t0 < Tn; t0 += NW * 4) {
+      float s1[4], s2[4], sh[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int t = t0 + u * NW;
-        raw[u] = (t < Tn) ? __ldg(reinterpret_cast<const uint32_t *>(xc + (long long)t * C)) : 0u;
+      for (int u = 0; u < 4; ++u) {
+        const int t = min(t0 + u, Tn - 1);
+        const uint4 *rv = reinterpret_cast<const uint4 *>(xin + (long long)t * C);
+        sh[u] = __bfloat162float(xin[(long long)t * C]);
+        s1[u] = s2[u] = 0.0f;
+        for (int i = lane; i < nv; i += 32) {
+          const uint4 v = __ldg(rv + i);
+          const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = __uint_as_float(wd[j] << 16) - sh[u], c2 = __uint_as_float(wd[j] & 0xffff0000u) - sh[u];
+            s1[u] += a + c2;
+            s2[u] = fmaf(a, a, fmaf(c2, c2, s2[u]));
+          }
+        }
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int t = t0 + u * NW;
-        if (t < Tn) {
-          const float m = s_mean[t], r = s_rstd[t];
-          const float lo_v = __uint_as_float(raw[u] << 16), hi_v = __uint_as_float(raw[u] & 0xffff0000u);
-          tile[s_off[t] + lane] = cok ? pack_bf16x2((lo_v - m) * r * g.x + be.x, (hi_v - m) * r * g.y + be.y) : 0u;
+      for (int u = 0; u < 4; ++u) {
+        const float a = warp_sum(s1[u]), q = warp_sum(s2[u]);
+        const float dm = a / (float)C;
+        const float var = fmaxf(q / (float)C - dm * dm, 0.0f);
+        if (lane == 0 && t0 + u < Tn) {
+          s_mean[t0 + u] = sh[u] + dm;
+          s_rstd[t0 + u] = 1.0f / sqrtf(var + eps);
         }
       }
     }
-    __syncthreads();
+  }
+
+  const int xchunks = (Gw + DW_XB - 1) / DW_XB;
+  int buf = 0;
+  for (int c0 = 0; c0 < C; c0 += 64, buf ^= 1) {
+    const int c = c0 + 2 * lane;
+    const bool cok = c < C;                       // C % 8 == 0 on this path
+    const float2 g = cok ? __ldg(reinterpret_cast<const float2 *>(gamma + c)) : make_float2(0.f, 0.f);
+    const float2 be = cok ? __ldg(reinterpret_cast<const float2 *>(beta + c)) : make_float2(0.f, 0.f);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                               // this slab's raw rows + taps (and the stats) are visible
+    // ---- transform: raw -> normalised tile ----
+    for (int t = warp; t < Tn; t += NW) {
+      const uint32_t u = s_raw[t * 32 + lane];
+      const float m = s_mean[t], r = s_rstd[t];
+      const float lo_v = __uint_as_float(u << 16), hi_v = __uint_as_float(u & 0xffff0000u);
+      tile[s_off[t] + lane] = cok ? pack_bf16x2((lo_v - m) * r * g.x + be.x, (hi_v - m) * r * g.y + be.y) : 0u;
+    }
+    __syncthreads();                               // tile ready; s_raw free
+    if (c0 + 64 < C) prefetch(c0 + 64, buf ^ 1);   // next slab streams in under this slab's FMAs
     const float2 bias = (cok && bdw) ? __ldg(reinterpret_cast<const float2 *>(bdw + c)) : make_float2(0.f, 0.f);
+    const float2 *wslab = s_w + buf * KS * KS * 32 + lane;
     for (int item = warp; item < Gh * xchunks; item += NW) {
       const int y = item / xchunks, x0 = (item - y * xchunks) * DW_XB;
       float2 acc[DW_XB];
@@ -237,7 +296,7 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
       for (int dy = 0; dy < KS; ++dy) {
         float2 w[KS];
 #pragma unroll
-        for (int dx = 0; dx < KS; ++dx) w[dx] = s_w[(dy * KS + dx) * 32 + lane];
+        for (int dx = 0; dx < KS; ++dx) w[dx] = cok ? wslab[(dy * KS + dx) * 32] : make_float2(0.f, 0.f);
         const uint32_t *trow = tile + ((y + dy) * PW + x0) * 32 + lane;
         float2 win[DW_XB + KS - 1];
 #pragma unroll
@@ -261,7 +320,7 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
           if (x0 + i < Gw) *reinterpret_cast<uint32_t *>(op + (long long)i * C) = pack_bf16x2(acc[i].x, acc[i].y);
       }
     }
-    __syncthreads();
+    // the next iteration's first __syncthreads orders this slab's tile reads before its overwrite
   }
 }
 
@@ -271,17 +330,16 @@ static int launch_dw_bf16(const void *act, const float *gamma, const float *beta
                           cudaStream_t st) {
   const int PW = ((Gw + DW_XB - 1) / DW_XB) * DW_XB + KS - 1;
   const int PH = Gh + KS - 1;
-  const int Tn = Gh * Gw;
-  const size_t smem = (size_t)(3 * Tn + (Tn & 1) + 2 * KS * KS * 32 + (size_t)PH * PW * 32) * sizeof(float);
-  SDP_CHECK(smem <= 220 * 1024, "sdp_ln_dwconv: grid %dx%d with k=%d needs %zu B of shared memory", Gh, Gw, KS,
-            smem);
+  const DwLayout L(Gh * Gw, PH, PW, KS);
+  const size_t smem = (size_t)L.total * sizeof(float);
+  if (smem > 220 * 1024) return -1;             // caller falls back to the generic kernel
   auto kern = ln_dwconv_bf16_kernel<KS>;
   static size_t configured = 0;
   if (smem > configured) {
     SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  kern<<<B, DW_THREADS, smem, st>>>((const bf16 *)act, gamma, beta, wdw, bdw, (bf16 *)out, Gh, Gw, C, R, eps, PW);
+  kern<<<B, DWF_THREADS, smem, st>>>((const bf16 *)act, gamma, beta, wdw, bdw, (bf16 *)out, Gh, Gw, C, R, eps, PW);
   SDP_LAUNCH_OK();
   return 0;
 }
@@ -329,13 +387,15 @@ extern "C" int sdp_ln_dwconv(const void *act, const float *gamma, const float *b
   SDP_CHECK(act != out, "sdp_ln_dwconv: must not run in place (spatial neighbours are read)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == SDP_BF16) {
-    const bool fast = C % 2 == 0 && (reinterpret_cast<uintptr_t>(act) & 3) == 0 &&
-                      (reinterpret_cast<uintptr_t>(out) & 3) == 0 && (reinterpret_cast<uintptr_t>(wdw) & 7) == 0 &&
+    const bool fast = C % 8 == 0 && (reinterpret_cast<uintptr_t>(act) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(out) & 3) == 0 && (reinterpret_cast<uintptr_t>(wdw) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(gamma) & 7) == 0 && (reinterpret_cast<uintptr_t>(beta) & 7) == 0 &&
                       (bdw == nullptr || (reinterpret_cast<uintptr_t>(bdw) & 7) == 0);
-    if (fast && k == 7) return launch_dw_bf16<7>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
-    if (fast && k == 5) return launch_dw_bf16<5>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
-    if (fast && k == 3) return launch_dw_bf16<3>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+    int rc = -1;
+    if (fast && k == 7) rc = launch_dw_bf16<7>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+    if (fast && k == 5) rc = launch_dw_bf16<5>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+    if (fast && k == 3) rc = launch_dw_bf16<3>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+    if (rc >= 0) return rc;
     return dispatch_dw<bf16>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, st);
   }
   SDP_CHECK(dtype == SDP_F32, "sdp_ln_dwconv: unknown dtype %d", dtype);
