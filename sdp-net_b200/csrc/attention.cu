@@ -290,7 +290,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int ATT2_MAXW = 8;    // register allocation is per 4 warps: 8 warps leave 255 registers per thread
+constexpr int ATT2_TAILW = 8;   // warps cooperating on a tail tile (bounds the partial buffer)
 
 // NT adjacent 16-query tiles starting at row q0 against KV blocks blk0, blk0+step, ...: flash-style
 // online softmax; leaves un-normalised O, running max m and this lane's partial row sums l.
@@ -428,8 +428,10 @@ __device__ __forceinline__ void attn_tiles(const bf16 *__restrict__ base, int C,
   }
 }
 
-template <int D, int TPW>
-__global__ void __launch_bounds__(32 * ATT2_MAXW, 1)
+// MAXW warps of TPW tiles each: <96, 1, 16> keeps 16 warps (128 registers) resident per SM, which hides
+// the mma.sync / ldmatrix / MUFU latencies far better than 8 fat warps (measured on B200).
+template <int D, int TPW, int MAXW>
+__global__ void __launch_bounds__(32 * MAXW, 1)
 attention_bf16_mma2_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int S, int h, float scale_log2) {
   constexpr int PITCH = D + 8;
   constexpr int NV = D / 8;                     // 16-byte vectors per row
@@ -496,29 +498,32 @@ attention_bf16_mma2_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out,
   }
   // ---- tail tiles (e.g. the 17th tile of S = 261): all warps split the KV blocks of one tile,
   //      partial (m, l, O) meet in shared memory ----
+  const int tw = nw < ATT2_TAILW ? nw : ATT2_TAILW;
   for (int tile = full_units * TPW; tile < tiles; ++tile) {
-    float o[1][D / 8][4], m_[1][2], l_[1][2];
-    attn_tiles<D, 1, false>(base, C, S, tile * 16, warp, nw, nblk, gblk, sK_addr, sV_addr, scale_log2, lane, o, m_, l_);
-    float ll = l_[0][0], lh = l_[0][1];
-    ll += __shfl_xor_sync(0xffffffffu, ll, 1); ll += __shfl_xor_sync(0xffffffffu, ll, 2);
-    lh += __shfl_xor_sync(0xffffffffu, lh, 1); lh += __shfl_xor_sync(0xffffffffu, lh, 2);
     constexpr int PW_ = (D / 8) * 4 * 32 + 4 * 32;        // floats per warp partial
-    float *mine = part + (size_t)warp * PW_;
+    if (warp < tw) {
+      float o[1][D / 8][4], m_[1][2], l_[1][2];
+      attn_tiles<D, 1, false>(base, C, S, tile * 16, warp, tw, nblk, gblk, sK_addr, sV_addr, scale_log2, lane, o, m_, l_);
+      float ll = l_[0][0], lh = l_[0][1];
+      ll += __shfl_xor_sync(0xffffffffu, ll, 1); ll += __shfl_xor_sync(0xffffffffu, ll, 2);
+      lh += __shfl_xor_sync(0xffffffffu, lh, 1); lh += __shfl_xor_sync(0xffffffffu, lh, 2);
+      float *mine = part + (size_t)warp * PW_;
 #pragma unroll
-    for (int n = 0; n < D / 8; ++n)
+      for (int n = 0; n < D / 8; ++n)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) mine[(n * 4 + j) * 32 + lane] = o[0][n][j];
-    float *ml = mine + (D / 8) * 4 * 32;
-    ml[lane] = m_[0][0]; ml[32 + lane] = m_[0][1]; ml[64 + lane] = ll; ml[96 + lane] = lh;
+        for (int j = 0; j < 4; ++j) mine[(n * 4 + j) * 32 + lane] = o[0][n][j];
+      float *ml = mine + (D / 8) * 4 * 32;
+      ml[lane] = m_[0][0]; ml[32 + lane] = m_[0][1]; ml[64 + lane] = ll; ml[96 + lane] = lh;
+    }
     __syncthreads();
     float M_lo = -INFINITY, M_hi = -INFINITY;
-    for (int w = 0; w < nw; ++w) {
+    for (int w = 0; w < tw; ++w) {
       const float *q = part + (size_t)w * PW_ + (D / 8) * 4 * 32;
       M_lo = fmaxf(M_lo, q[lane]);
       M_hi = fmaxf(M_hi, q[32 + lane]);
     }
     float L_lo = 0.0f, L_hi = 0.0f;
-    for (int w = 0; w < nw; ++w) {
+    for (int w = 0; w < tw; ++w) {
       const float *q = part + (size_t)w * PW_ + (D / 8) * 4 * 32;
       L_lo += q[64 + lane] * fast_ex2(q[lane] - M_lo);
       L_hi += q[96 + lane] * fast_ex2(q[32 + lane] - M_hi);
@@ -529,7 +534,7 @@ attention_bf16_mma2_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out,
     bf16 *ohi = olo + 8LL * C;
     for (int n = warp; n < D / 8; n += nw) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int w = 0; w < nw; ++w) {
+      for (int w = 0; w < tw; ++w) {
         const float *pw = part + (size_t)w * PW_;
         const float *q = pw + (D / 8) * 4 * 32;
         const float f_lo = fast_ex2(q[lane] - M_lo), f_hi = fast_ex2(q[32 + lane] - M_hi);
@@ -546,17 +551,17 @@ attention_bf16_mma2_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out,
   }
 }
 
-template <int D, int TPW>
+template <int D, int TPW, int MAXW>
 static int launch_attn_mma2(const void *qkv, void *out, int B, int S, int h, cudaStream_t st) {
   const int tiles = (S + 15) / 16;
   const int units = (tiles + TPW - 1) / TPW;
-  const int nw = units < ATT2_MAXW ? units : ATT2_MAXW;
+  const int nw = units < MAXW ? units : MAXW;
   const int S_pad = ((S + KVB - 1) / KVB) * KVB;
   const bool tail = (units / nw) * nw * TPW < tiles;
   const size_t smem = (size_t)2 * S_pad * (D + 8) * sizeof(bf16) +
-                      (tail ? (size_t)nw * ((D / 8) * 4 * 32 + 4 * 32) * sizeof(float) : 0);
+                      (tail ? (size_t)(nw < ATT2_TAILW ? nw : ATT2_TAILW) * ((D / 8) * 4 * 32 + 4 * 32) * sizeof(float) : 0);
   if (smem > 220 * 1024) return -1;             // does not fit: the dispatcher tries the next kernel
-  auto kern = attention_bf16_mma2_kernel<D, TPW>;
+  auto kern = attention_bf16_mma2_kernel<D, TPW, MAXW>;
   static size_t configured = 0;
   if (smem > configured) {
     SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -696,11 +701,11 @@ extern "C" int sdp_attention(const void *qkv, const float *qn_w, const float *qn
     int rc = -1;
     if (aligned && qn_w == nullptr) {
       switch (d) {
-        case 16: rc = launch_attn_mma2<16, 2>(qkv, out, B, S, h, st); break;
-        case 32: rc = launch_attn_mma2<32, 2>(qkv, out, B, S, h, st); break;
-        case 64: rc = launch_attn_mma2<64, 2>(qkv, out, B, S, h, st); break;
-        case 96: rc = launch_attn_mma2<96, 2>(qkv, out, B, S, h, st); break;
-        case 128: rc = launch_attn_mma2<128, 1>(qkv, out, B, S, h, st); break;
+        case 16: rc = launch_attn_mma2<16, 1, 16>(qkv, out, B, S, h, st); break;
+        case 32: rc = launch_attn_mma2<32, 1, 16>(qkv, out, B, S, h, st); break;
+        case 64: rc = launch_attn_mma2<64, 1, 16>(qkv, out, B, S, h, st); break;
+        case 96: rc = launch_attn_mma2<96, 1, 16>(qkv, out, B, S, h, st); break;
+        case 128: rc = launch_attn_mma2<128, 1, 8>(qkv, out, B, S, h, st); break;
         default: break;
       }
       if (rc >= 0) return rc;

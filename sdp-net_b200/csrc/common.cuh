@@ -145,6 +145,7 @@ struct Epilogue {
 struct RowMap {
   long long ro, rr;   // output row, residual row
   bool live;          // row < M and not a pass-through (register) row
+  bool pass;          // row < M and a pass-through row (keeps its residual value)
 };
 
 __device__ __forceinline__ RowMap map_row(const Epilogue &e, int r) {
@@ -153,16 +154,18 @@ __device__ __forceinline__ RowMap map_row(const Epilogue &e, int r) {
   const int rc = m.live ? r : 0;
   m.ro = e.seq_in ? (long long)(rc / e.seq_in) * e.seq_out + e.seq_off + rc % e.seq_in : rc;
   m.rr = e.res_mod ? rc % e.res_mod : m.ro;
-  if (e.pass_seq && (int)(m.ro % e.pass_seq) < e.pass_rows) m.live = false;
+  m.pass = false;
+  if (m.live && e.pass_seq && (int)(m.ro % e.pass_seq) < e.pass_rows) {
+    m.live = false;
+    m.pass = true;
+  }
   return m;
 }
 
 // Finish NV consecutive columns [c0, c0+NV) of one row held in v[] (fp32 accumulators).
 // NV is a multiple of 8.  VEC = the pointers/pitches allow 16-byte accesses.
 template <int NV, bool EXACT, int ACT>   // ACT < 0: runtime e.act
-__device__ __forceinline__ void epilogue_row(const Epilogue &e, const RowMap &m, int c0, float *v,
-                                             bool vec) {
-  if (!m.live) return;
+__device__ __forceinline__ void epilogue_math(const Epilogue &e, const RowMap &m, int c0, float *v, bool vec) {
   const int act = ACT < 0 ? e.act : ACT;
   const bool full = vec && (c0 + NV <= e.N);
   if (e.bias) {
@@ -219,6 +222,11 @@ __device__ __forceinline__ void epilogue_row(const Epilogue &e, const RowMap &m,
       for (int j = 0; j < NV; ++j) v[j] = apply_act<EXACT>(v[j], act);
     }
   }
+}
+
+template <int NV>
+__device__ __forceinline__ void epilogue_store(const Epilogue &e, const RowMap &m, int c0, const float *v, bool vec) {
+  const bool full = vec && (c0 + NV <= e.N);
   if (e.out_dtype == SDP_BF16) {
     bf16 *op = reinterpret_cast<bf16 *>(e.out) + m.ro * e.ldo + c0;
     if (full) {
@@ -247,6 +255,35 @@ __device__ __forceinline__ void epilogue_row(const Epilogue &e, const RowMap &m,
       for (int j = 0; j < NV; ++j)
         if (c0 + j < e.N) op[j] = v[j];
     }
+  }
+}
+
+// bias / activation / residual, then a direct global store (row-per-thread layout)
+template <int NV, bool EXACT, int ACT>
+__device__ __forceinline__ void epilogue_row(const Epilogue &e, const RowMap &m, int c0, float *v, bool vec) {
+  if (!m.live) return;
+  epilogue_math<NV, EXACT, ACT>(e, m, c0, v, vec);
+  epilogue_store<NV>(e, m, c0, v, vec);
+}
+
+// Pass-through row in a staged (TMA-store) epilogue: the tile box is written as a whole, so the
+// row re-emits its residual (== current output, in place) bit for bit; rows past M emit zeros
+// (clipped by the TMA store anyway).
+template <int NV>
+__device__ __forceinline__ void epilogue_passthrough(const Epilogue &e, const RowMap &m, int c0, float *v) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = 0.0f;
+  if (!m.pass || e.residual == nullptr) return;
+  if (e.res_dtype == SDP_BF16) {
+    const bf16 *rp = reinterpret_cast<const bf16 *>(e.residual) + m.rr * e.ldr + c0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      if (c0 + j < e.N) v[j] = __bfloat162float(rp[j]);
+  } else {
+    const float *rp = reinterpret_cast<const float *>(e.residual) + m.rr * e.ldr + c0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      if (c0 + j < e.N) v[j] = rp[j];
   }
 }
 

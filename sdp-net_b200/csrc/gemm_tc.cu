@@ -66,6 +66,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -120,18 +131,23 @@ struct SmemLayout {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int OUT_OFF = STAGES * STAGE_BYTES;              // epilogue staging: 8 warps x 2 x [32 rows x 64 B]
+  static constexpr int OUT_BYTES = EPI_WARPS * 2 * 2048;
+  static constexpr int BAR_OFF = OUT_OFF + OUT_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
+  static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
 
 __host__ __device__ constexpr uint32_t tmem_cols_for(int bn) {
   return 2 * bn <= 32 ? 32u : 2 * bn <= 64 ? 64u : 2 * bn <= 128 ? 128u : 2 * bn <= 256 ? 256u : 512u;
 }
 
-template <int BN, int STAGES, int ACT, int HN>
+// STAGED: bf16 output tiles leave through shared memory and TMA stores (one 32 x 32 box per warp and
+// 32-column chunk, 64B-swizzled, double-buffered per warp) instead of 16-byte-per-row global stores.
+template <int BN, int STAGES, int ACT, int HN, bool STAGED>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                    const Epilogue epi, const int K, const int vec_ok) {
+                    const __grid_constant__ CUtensorMap tmO, const Epilogue epi, const int K, const int vec_ok) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   // swizzle-128B tiles need 1024-byte alignment
@@ -151,6 +167,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    if (STAGED) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -237,6 +254,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int UNITS = BN / UNIT;
     constexpr int U_LO = (UNITS + 1) / 2;      // units of the low half
     const int u_begin = half == 0 ? 0 : U_LO, u_end = half == 0 ? U_LO : UNITS;
+    const uint32_t stage_base = smem_base + L::OUT_OFF + static_cast<uint32_t>(warp - 2) * 4096;
+    uint32_t cc = 0;                           // chunks this warp has staged (slot = cc & 1)
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -304,13 +323,43 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           }
-          if (col0 + i < epi.N) epilogue_row<32, false, ACT>(epi, rm, col0 + i, v, vec_ok != 0);
+          if (col0 + i < epi.N) {
+            if constexpr (!STAGED) {
+              epilogue_row<32, false, ACT>(epi, rm, col0 + i, v, vec_ok != 0);
+            } else {
+              if (rm.live) epilogue_math<32, false, ACT>(epi, rm, col0 + i, v, vec_ok != 0);
+              else epilogue_passthrough<32>(epi, rm, col0 + i, v);
+              const uint32_t slot = stage_base + ((cc & 1) << 11);
+              if (cc >= 2) {                     // the store issued from this slot two chunks ago has read it
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+              }
+              const uint32_t rowp = slot + lane * 64;
+              const uint32_t sw = (lane >> 1) & 3;   // 64-byte swizzle: 16B chunk index ^ address bits [7:8]
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t p0 = pack_bf16x2(v[8 * j], v[8 * j + 1]), p1 = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                const uint32_t p2 = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), p3 = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + ((j ^ sw) << 4)), "r"(p0), "r"(p1),
+                             "r"(p2), "r"(p3)
+                             : "memory");
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmO, slot, col0 + i, m0 + quad * 32);
+                bulk_commit();
+              }
+              ++cc;
+            }
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
+    if (STAGED && lane == 0) bulk_wait_read<0>();   // staging slots must outlive their last store's read
   }
 
   tc_fence_before();
@@ -346,9 +395,10 @@ static EncodeTiledFn get_encode_fn() {
 struct MapKey {
   const void *ptr;
   uint64_t rows, cols, pitch;
-  uint32_t box_rows;
+  uint32_t box_rows, box_cols;
   bool operator==(const MapKey &o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && pitch == o.pitch && box_rows == o.box_rows;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && pitch == o.pitch && box_rows == o.box_rows &&
+           box_cols == o.box_cols;
   }
 };
 struct MapKeyHash {
@@ -358,16 +408,18 @@ struct MapKeyHash {
     h = h * 1315423911u ^ k.cols;
     h = h * 1315423911u ^ k.pitch;
     h = h * 1315423911u ^ k.box_rows;
+    h = h * 1315423911u ^ k.box_cols;
     return h;
   }
 };
 
-// [rows, cols] bf16 row-major with `pitch` elements per row; box = box_rows x 64, 128B swizzle.
+// [rows, cols] bf16 row-major with `pitch` elements per row; box = box_rows x box_cols with the
+// swizzle span equal to the box row (64 cols -> 128B operand tiles, 32 cols -> 64B output boxes).
 static int get_tensor_map(const void *ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows,
-                          CUtensorMap *out) {
+                          CUtensorMap *out, uint32_t box_cols = BLOCK_K) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, rows, cols, pitch, box_rows};
+  MapKey key{ptr, rows, cols, pitch, box_rows, box_cols};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -383,11 +435,12 @@ static int get_tensor_map(const void *ptr, uint64_t rows, uint64_t cols, uint64_
             (unsigned long long)pitch);
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {pitch * 2};
-  cuuint32_t box[2] = {BLOCK_K, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SDP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   {
@@ -409,10 +462,16 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, int ACT, int HN = 0>
-static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tw, const Epilogue &e, int K, cudaStream_t st) {
+static bool staged_ok(const Epilogue &e) {
+  return e.out_dtype == SDP_BF16 && e.seq_in == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 &&
+         (e.ldo * 2) % 16 == 0 && (e.pass_seq == 0 || e.residual != nullptr);
+}
+
+template <int BN, int STAGES, int ACT, int HN, bool STAGED>
+static int launch_tc2(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &to, const Epilogue &e, int K,
+                      cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
-  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT, HN>;
+  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT, HN, STAGED>;
   static bool configured = false;
   if (!configured) {
     SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -420,9 +479,19 @@ static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tw, const Epilogu
   }
   const int tiles = ((e.M + BLOCK_M - 1) / BLOCK_M) * ((e.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, L::TOTAL, st>>>(ta, tw, e, K, epilogue_vec_ok(e) ? 1 : 0);
+  kern<<<grid, GEMM_THREADS, L::TOTAL, st>>>(ta, tw, to, e, K, epilogue_vec_ok(e) ? 1 : 0);
   SDP_LAUNCH_OK();
   return 0;
+}
+
+template <int BN, int STAGES, int ACT, int HN = 0>
+static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tw, const Epilogue &e, int K, cudaStream_t st) {
+  if (staged_ok(e)) {
+    CUtensorMap to;
+    if (int rc = get_tensor_map(e.out, e.M, e.N, e.ldo, 32, &to, 32)) return rc;
+    return launch_tc2<BN, STAGES, ACT, HN, true>(ta, tw, to, e, K, st);
+  }
+  return launch_tc2<BN, STAGES, ACT, HN, false>(ta, tw, ta, e, K, st);
 }
 
 template <int BN, int STAGES>
@@ -441,7 +510,7 @@ int gemm_bf16_tc(const sdp_gemm_args &a, const Epilogue &e, cudaStream_t st) {
     CUtensorMap ta, tw;
     if (int rc = get_tensor_map(a.A, a.M, a.K, a.lda, BLOCK_M, &ta)) return rc;
     if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, bn, &tw)) return rc;
-    if (e.hn_d == 96) return launch_tc<192, 5, SDP_ACT_NONE, 96>(ta, tw, e, a.K, st);
+    if (e.hn_d == 96) return launch_tc<192, 4, SDP_ACT_NONE, 96>(ta, tw, e, a.K, st);
     if (bn == 256) {
       if (e.hn_d == 32) return launch_tc<256, 4, SDP_ACT_NONE, 32>(ta, tw, e, a.K, st);
       if (e.hn_d == 64) return launch_tc<256, 4, SDP_ACT_NONE, 64>(ta, tw, e, a.K, st);
