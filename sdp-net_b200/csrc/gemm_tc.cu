@@ -8,6 +8,7 @@
 // Replaces every nn.Linear / 1x1 conv of the reference forward (see include/sdpnet_b200.h).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -77,6 +78,45 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// ---- 2-CTA (cta_group::2) variants: the CTA pair of one TPC runs 256 x BN tiles; each CTA stages its own
+// 128 A rows and HALF of the B rows, the leader (cluster rank 0) issues the MMAs for both.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the peer bit (bit 24) of a shared::cluster address selects the CTA of the pair; clearing it names the leader
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -126,10 +166,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG = 1>
 struct SmemLayout {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BN / CG) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_OFF = STAGES * STAGE_BYTES;              // epilogue staging: 8 warps x 2 x [32 rows x 64 B]
   static constexpr int OUT_BYTES = EPI_WARPS * 2 * 2048;
@@ -144,11 +184,14 @@ __host__ __device__ constexpr uint32_t tmem_cols_for(int bn) {
 
 // STAGED: bf16 output tiles leave through shared memory and TMA stores (one 32 x 32 box per warp and
 // 32-column chunk, 64B-swizzled, double-buffered per warp) instead of 16-byte-per-row global stores.
-template <int BN, int STAGES, int ACT, int HN, bool STAGED>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: launched as clusters of 2 (one TPC); the pair owns a
+// 256 x BN tile, B traffic from L2 halves and the smem ring gets deeper for the same capacity.
+template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO, const Epilogue epi, const int K, const int vec_ok) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, CG>;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   // swizzle-128B tiles need 1024-byte alignment
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -174,55 +217,72 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), EPI_WARPS);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), CG * EPI_WARPS);   // one arrive per epilogue warp (of both CTAs when paired)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(const_cast<uint32_t *>(tmem_slot))),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(const_cast<uint32_t *>(tmem_slot))),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {     // issued by the same warp of BOTH CTAs of the pair
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(const_cast<uint32_t *>(tmem_slot))),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int m_tiles = (epi.M + BLOCK_M - 1) / BLOCK_M;
+  constexpr int TILE_M = BLOCK_M * CG;
+  const int m_tiles = (epi.M + TILE_M - 1) / TILE_M;
   const int n_tiles = (epi.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int unit0 = blockIdx.x / CG, unit_stride = gridDim.x / CG;
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BLOCK_M;
-        const int n0 = (tile % n_tiles) * BN;
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+        const int m0 = (tile / n_tiles) * TILE_M + rank * BLOCK_M;
+        const int n0 = (tile % n_tiles) * BN + rank * (BN / CG);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
-          tma_load_2d(sa + L::A_BYTES, &tmW, full_bar(stage), kb * BLOCK_K, n0);
+          if constexpr (CG == 1) {
+            mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
+            tma_load_2d(sa + L::A_BYTES, &tmW, full_bar(stage), kb * BLOCK_K, n0);
+          } else {
+            // both CTAs' bytes complete on the LEADER's full barrier; only the leader arms it
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+            tma_load_2d_2sm(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
+            tma_load_2d_2sm(sa + L::A_BYTES, &tmW, full_bar(stage), kb * BLOCK_K, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    constexpr uint32_t idesc = make_idesc(BLOCK_M, BN);
+    constexpr uint32_t idesc = make_idesc(TILE_M, BN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      if (lane == 0) {
+      if (lane == 0 && rank == 0) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -235,10 +295,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes (16 bf16) inside the 128B swizzle atom: +2 in the >>4 address field
-            tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CG == 1) tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else tc_mma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          tc_commit(empty_bar(stage));                   // smem slot free once these MMAs retire
-          if (kb == num_kb - 1) tc_commit(tfull_bar(acc));
+          if constexpr (CG == 1) {
+            tc_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
+            if (kb == num_kb - 1) tc_commit(tfull_bar(acc));
+          } else {                                       // same barriers in both CTAs of the pair
+            tc_commit_2sm(empty_bar(stage));
+            if (kb == num_kb - 1) tc_commit_2sm(tfull_bar(acc));
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -257,10 +323,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t stage_base = smem_base + L::OUT_OFF + static_cast<uint32_t>(warp - 2) * 4096;
     uint32_t cc = 0;                           // chunks this warp has staged (slot = cc & 1)
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * BLOCK_M;
+      const int m0 = (tile / n_tiles) * TILE_M + rank * BLOCK_M;
       const int n0 = (tile % n_tiles) * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -357,17 +423,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cta(tempty_bar(acc), 0);        // the leader's MMA warp waits for both CTAs' epilogues
+      }
     }
     if (STAGED && lane == 0) bulk_wait_read<0>();   // staging slots must outlive their last store's read
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody may still signal or read a peer
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
-                 : "memory");
+    if constexpr (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -467,58 +538,89 @@ static bool staged_ok(const Epilogue &e) {
          (e.ldo * 2) % 16 == 0 && (e.pass_seq == 0 || e.residual != nullptr);
 }
 
-template <int BN, int STAGES, int ACT, int HN, bool STAGED>
+template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1>
 static int launch_tc2(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &to, const Epilogue &e, int K,
                       cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES>;
-  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT, HN, STAGED>;
+  using L = SmemLayout<BN, STAGES, CG>;
+  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT, HN, STAGED, CG>;
   static bool configured = false;
   if (!configured) {
     SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  const int tiles = ((e.M + BLOCK_M - 1) / BLOCK_M) * ((e.N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, L::TOTAL, st>>>(ta, tw, to, e, K, epilogue_vec_ok(e) ? 1 : 0);
+  const int units = ((e.M + BLOCK_M * CG - 1) / (BLOCK_M * CG)) * ((e.N + BN - 1) / BN);
+  const int slots = num_sms() / CG;
+  const int grid = CG * (units < slots ? units : slots);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG > 1 ? 1 : 0;
+  SDP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw, to, e, K, epilogue_vec_ok(e) ? 1 : 0));
   SDP_LAUNCH_OK();
   return 0;
 }
 
+// 0 / unset: automatic (pairs whenever the staged epilogue applies and M spans a pair); 1: never; 2: always if legal
+static int cta_group_pref() {
+  static int v = -1;
+  if (v < 0) {
+    const char *s = getenv("SDP_GEMM_CTA_GROUP");
+    v = s ? atoi(s) : 0;
+  }
+  return v;
+}
+
 template <int BN, int STAGES, int ACT, int HN = 0>
-static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tw, const Epilogue &e, int K, cudaStream_t st) {
+static int launch_tc(const sdp_gemm_args &a, const CUtensorMap &ta, const Epilogue &e, cudaStream_t st) {
+  CUtensorMap tw;
   if (staged_ok(e)) {
     CUtensorMap to;
     if (int rc = get_tensor_map(e.out, e.M, e.N, e.ldo, 32, &to, 32)) return rc;
-    return launch_tc2<BN, STAGES, ACT, HN, true>(ta, tw, to, e, K, st);
+    if constexpr (BN >= 128) {
+      const int pref = cta_group_pref();
+      if (pref != 1 && e.M > BLOCK_M && (pref == 2 || e.M >= 8 * BLOCK_M)) {
+        constexpr int ST2 = (STAGES * (BLOCK_M + BN)) / (BLOCK_M + BN / 2);   // same bytes, deeper ring
+        if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, BN / 2, &tw)) return rc;
+        return launch_tc2<BN, ST2, ACT, HN, true, 2>(ta, tw, to, e, a.K, st);
+      }
+    }
+    if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, BN, &tw)) return rc;
+    return launch_tc2<BN, STAGES, ACT, HN, true>(ta, tw, to, e, a.K, st);
   }
-  return launch_tc2<BN, STAGES, ACT, HN, false>(ta, tw, ta, e, K, st);
+  if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, BN, &tw)) return rc;
+  return launch_tc2<BN, STAGES, ACT, HN, false>(ta, tw, ta, e, a.K, st);
 }
 
 template <int BN, int STAGES>
-static int launch_tc_act(const CUtensorMap &ta, const CUtensorMap &tw, const Epilogue &e, int K,
-                         cudaStream_t st) {
-  if (e.act == SDP_ACT_NONE) return launch_tc<BN, STAGES, SDP_ACT_NONE>(ta, tw, e, K, st);
-  if (e.act == SDP_ACT_GELU) return launch_tc<BN, STAGES, SDP_ACT_GELU>(ta, tw, e, K, st);
-  return launch_tc<BN, STAGES, -1>(ta, tw, e, K, st);
+static int launch_tc_act(const sdp_gemm_args &a, const CUtensorMap &ta, const Epilogue &e, cudaStream_t st) {
+  if (e.act == SDP_ACT_NONE) return launch_tc<BN, STAGES, SDP_ACT_NONE>(a, ta, e, st);
+  if (e.act == SDP_ACT_GELU) return launch_tc<BN, STAGES, SDP_ACT_GELU>(a, ta, e, st);
+  return launch_tc<BN, STAGES, -1>(a, ta, e, st);
 }
 
 int gemm_bf16_tc(const sdp_gemm_args &a, const Epilogue &e, cudaStream_t st) {
+  CUtensorMap ta;
+  if (int rc = get_tensor_map(a.A, a.M, a.K, a.lda, BLOCK_M, &ta)) return rc;
   if (e.hn_d) {
     // QKV projection with the per-head LayerNorm fused: the N block must hold whole heads
-    const int bn = e.hn_d == 96 ? 192 : (a.N % 256 == 0 ? 256 : 128);
     SDP_CHECK(e.act == SDP_ACT_NONE, "sdp_gemm: head-norm epilogue has no activation");
-    CUtensorMap ta, tw;
-    if (int rc = get_tensor_map(a.A, a.M, a.K, a.lda, BLOCK_M, &ta)) return rc;
-    if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, bn, &tw)) return rc;
-    if (e.hn_d == 96) return launch_tc<192, 4, SDP_ACT_NONE, 96>(ta, tw, e, a.K, st);
-    if (bn == 256) {
-      if (e.hn_d == 32) return launch_tc<256, 4, SDP_ACT_NONE, 32>(ta, tw, e, a.K, st);
-      if (e.hn_d == 64) return launch_tc<256, 4, SDP_ACT_NONE, 64>(ta, tw, e, a.K, st);
-      return launch_tc<256, 4, SDP_ACT_NONE, 128>(ta, tw, e, a.K, st);
+    if (e.hn_d == 96) return launch_tc<192, 4, SDP_ACT_NONE, 96>(a, ta, e, st);
+    if (a.N % 256 == 0) {
+      if (e.hn_d == 32) return launch_tc<256, 4, SDP_ACT_NONE, 32>(a, ta, e, st);
+      if (e.hn_d == 64) return launch_tc<256, 4, SDP_ACT_NONE, 64>(a, ta, e, st);
+      return launch_tc<256, 4, SDP_ACT_NONE, 128>(a, ta, e, st);
     }
-    if (e.hn_d == 32) return launch_tc<128, 6, SDP_ACT_NONE, 32>(ta, tw, e, a.K, st);
-    if (e.hn_d == 64) return launch_tc<128, 6, SDP_ACT_NONE, 64>(ta, tw, e, a.K, st);
-    return launch_tc<128, 6, SDP_ACT_NONE, 128>(ta, tw, e, a.K, st);
+    if (e.hn_d == 32) return launch_tc<128, 6, SDP_ACT_NONE, 32>(a, ta, e, st);
+    if (e.hn_d == 64) return launch_tc<128, 6, SDP_ACT_NONE, 64>(a, ta, e, st);
+    return launch_tc<128, 6, SDP_ACT_NONE, 128>(a, ta, e, st);
   }
   // BLOCK_N minimising padded columns; ties -> the larger tile
   int bn = 256;
@@ -530,13 +632,10 @@ int gemm_bf16_tc(const sdp_gemm_args &a, const Epilogue &e, cudaStream_t st) {
       if (best < 0 || padded < best) { best = padded; bn = cand[i]; }
     }
   }
-  CUtensorMap ta, tw;
-  if (int rc = get_tensor_map(a.A, a.M, a.K, a.lda, BLOCK_M, &ta)) return rc;
-  if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, bn, &tw)) return rc;
   switch (bn) {
-    case 256: return launch_tc_act<256, 4>(ta, tw, e, a.K, st);
-    case 128: return launch_tc_act<128, 6>(ta, tw, e, a.K, st);
-    default: return launch_tc_act<64, 8>(ta, tw, e, a.K, st);
+    case 256: return launch_tc_act<256, 4>(a, ta, e, st);
+    case 128: return launch_tc_act<128, 6>(a, ta, e, st);
+    default: return launch_tc_act<64, 8>(a, ta, e, st);
   }
 }
 
