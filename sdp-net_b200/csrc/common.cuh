@@ -81,19 +81,22 @@ __device__ __forceinline__ float fast_ex2(float x) {
   return y;
 }
 
-// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 7 FMA.
+// Exact-erf GELU with ONE special-function op:  gelu(x) = relu(x) - 0.5|x| * erfc(|x|/sqrt2), and
+// log2(erfc(t/sqrt2)) is smooth on t >= 0 with value 0 at 0, so erfc = 2^(t*Q(t)) with a degree-6 Q
+// (weighted minimax fit on [0, 6], |P err| <= 5.6e-6  =>  |gelu err| <= 6.5e-7, far below bf16
+// resolution; checked against erff in tests/test_gpu_kernels.py::test_fast_gelu_close_to_erf_gelu).
+// 7 FMA-pipe ops + 1 MUFU.EX2 + 3, instead of rcp + ex2 + 12: the GELU epilogue of the C->4C GEMMs
+// is the hottest non-MMA code of the forward.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = fast_ex2(-1.4426950408889634f * z * z);
-  const float erf_abs = fmaf(-p, e, 1.0f);          // erf(|x|/sqrt2)
-  const float half_x = 0.5f * x;
-  return fmaf(fabsf(half_x), erf_abs, half_x);      // 0.5x + 0.5|x|erf(|x|/sqrt2) == 0.5x(1+erf(x/sqrt2))
+  const float t = fminf(fabsf(x), 8.0f);
+  float q = fmaf(-1.79379024e-06f, t, 6.07263591e-05f);
+  q = fmaf(q, t, -9.23187284e-04f);
+  q = fmaf(q, t, 8.47685316e-03f);
+  q = fmaf(q, t, -5.38909494e-02f);
+  q = fmaf(q, t, -4.58541575e-01f);
+  q = fmaf(q, t, -1.15121437e+00f);
+  const float e = fast_ex2(q * t);                  // erfc(|x|/sqrt2)
+  return fmaf(-0.5f * t, e, fmaxf(x, 0.0f));
 }
 
 __device__ __forceinline__ float kelu_f(float x) {
@@ -224,6 +227,35 @@ __device__ __forceinline__ void epilogue_math(const Epilogue &e, const RowMap &m
   }
 }
 
+// bias + activation + residual taken from registers (bf16 residual prefetched by the caller):
+// the staged tensor-core epilogue issues the next chunk's residual loads before it finishes this one.
+template <int ACT>
+__device__ __forceinline__ void epilogue_math_preres(const Epilogue &e, int c0, float *v, const uint4 *r, bool pass) {
+  const int act = ACT < 0 ? e.act : ACT;
+  if (pass) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+  } else {
+    if (e.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(e.bias + c0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act<false>(v[j], act);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f;
+    f = unpack_bf16x2(r[j].x); v[8 * j] += f.x; v[8 * j + 1] += f.y;
+    f = unpack_bf16x2(r[j].y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+    f = unpack_bf16x2(r[j].z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+    f = unpack_bf16x2(r[j].w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+  }
+}
+
 template <int NV>
 __device__ __forceinline__ void epilogue_store(const Epilogue &e, const RowMap &m, int c0, const float *v, bool vec) {
   const bool full = vec && (c0 + NV <= e.N);
@@ -270,15 +302,27 @@ __device__ __forceinline__ void epilogue_row(const Epilogue &e, const RowMap &m,
 // row re-emits its residual (== current output, in place) bit for bit; rows past M emit zeros
 // (clipped by the TMA store anyway).
 template <int NV>
-__device__ __forceinline__ void epilogue_passthrough(const Epilogue &e, const RowMap &m, int c0, float *v) {
+__device__ __forceinline__ void epilogue_passthrough(const Epilogue &e, const RowMap &m, int c0, float *v, bool vec) {
 #pragma unroll
   for (int j = 0; j < NV; ++j) v[j] = 0.0f;
   if (!m.pass || e.residual == nullptr) return;
   if (e.res_dtype == SDP_BF16) {
     const bf16 *rp = reinterpret_cast<const bf16 *>(e.residual) + m.rr * e.ldr + c0;
+    if (vec && c0 + NV <= e.N) {
 #pragma unroll
-    for (int j = 0; j < NV; ++j)
-      if (c0 + j < e.N) v[j] = __bfloat162float(rp[j]);
+      for (int j = 0; j < NV; j += 8) {
+        const uint4 u = *reinterpret_cast<const uint4 *>(rp + j);
+        float2 f;
+        f = unpack_bf16x2(u.x); v[j] = f.x; v[j + 1] = f.y;
+        f = unpack_bf16x2(u.y); v[j + 2] = f.x; v[j + 3] = f.y;
+        f = unpack_bf16x2(u.z); v[j + 4] = f.x; v[j + 5] = f.y;
+        f = unpack_bf16x2(u.w); v[j + 6] = f.x; v[j + 7] = f.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (c0 + j < e.N) v[j] = __bfloat162float(rp[j]);
+    }
   } else {
     const float *rp = reinterpret_cast<const float *>(e.residual) + m.rr * e.ldr + c0;
 #pragma unroll

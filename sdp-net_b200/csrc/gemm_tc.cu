@@ -322,15 +322,29 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int u_begin = half == 0 ? 0 : U_LO, u_end = half == 0 ? U_LO : UNITS;
     const uint32_t stage_base = smem_base + L::OUT_OFF + static_cast<uint32_t>(warp - 2) * 4096;
     uint32_t cc = 0;                           // chunks this warp has staged (slot = cc & 1)
+    // in-place bf16 residual (the common case): each chunk's residual is fetched one chunk ahead
+    const bool res_fast = STAGED && epi.residual != nullptr && epi.res_dtype == SDP_BF16 && !epi.res_first &&
+                          epi.res_mod == 0 && vec_ok != 0;
+    const int col_end = (half == 0 ? U_LO : UNITS) * UNIT;   // end of this warp's column range inside the tile
     int it = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * TILE_M + rank * BLOCK_M;
       const int n0 = (tile % n_tiles) * BN;
+      const RowMap rm = map_row(epi, m0 + quad * 32 + lane);
+      uint4 rnext[4] = {};
+      const bf16 *res_row = reinterpret_cast<const bf16 *>(epi.residual) + rm.rr * epi.ldr;
+      auto fetch_res = [&](int col) {            // col: absolute column of a 32-wide chunk
+        if (res_fast && (rm.live || rm.pass) && col + 32 <= epi.N) {
+          const uint4 *p = reinterpret_cast<const uint4 *>(res_row + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rnext[j] = p[j];
+        }
+      };
+      fetch_res(n0 + u_begin * UNIT);            // before the accumulator is even ready
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const RowMap rm = map_row(epi, m0 + quad * 32 + lane);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int u = u_begin; u < u_end; ++u) {
@@ -393,8 +407,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if constexpr (!STAGED) {
               epilogue_row<32, false, ACT>(epi, rm, col0 + i, v, vec_ok != 0);
             } else {
-              if (rm.live) epilogue_math<32, false, ACT>(epi, rm, col0 + i, v, vec_ok != 0);
-              else epilogue_passthrough<32>(epi, rm, col0 + i, v);
+              const int col = col0 + i;
+              if (res_fast && col + 32 <= epi.N) {
+                uint4 rcur[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+                if (c + i + 32 < col_end) fetch_res(col + 32);
+                if (rm.live || rm.pass) epilogue_math_preres<ACT>(epi, col, v, rcur, rm.pass);
+              } else if (rm.live) {
+                epilogue_math<32, false, ACT>(epi, rm, col, v, vec_ok != 0);
+              } else {
+                epilogue_passthrough<32>(epi, rm, col, v, vec_ok != 0);
+              }
               const uint32_t slot = stage_base + ((cc & 1) << 11);
               if (cc >= 2) {                     // the store issued from this slot two chunks ago has read it
                 if (lane == 0) bulk_wait_read<1>();
