@@ -12,6 +12,8 @@
 // 1/sqrt(d)*log2(e) scale folded in.  The tcgen05 version of this kernel is the planned upgrade;
 // attention is 2.3 % of the model FLOPs.
 // fp32 / odd head_dim path: CUDA-core kernel, one warp per query row (verification mode).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sdp {
@@ -290,7 +292,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int ATT2_TAILW = 8;   // warps cooperating on a tail tile (bounds the partial buffer)
+constexpr int ATT2_TAILW = 10;  // max warps cooperating on a tail tile (bounds the partial buffer)
 
 // NT adjacent 16-query tiles starting at row q0 against KV blocks blk0, blk0+step, ...: flash-style
 // online softmax; leaves un-normalised O, running max m and this lane's partial row sums l.
@@ -302,6 +304,11 @@ __device__ __forceinline__ void attn_tiles(const bf16 *__restrict__ base, int C,
   constexpr int PITCH = D + 8;
   const int g = lane >> 2, qd = lane & 3;
   const int lm = lane >> 3, lr = lane & 7;
+  // per-lane ldmatrix row addresses; everything else is a compile-time offset
+  // K: matrices (keys 0..7, d 0..7) (same keys, d + 8) (keys + 8, d) (keys + 8, d + 8)
+  // V (transposed): (keys 0..7, d 0..7) (keys + 8, same d) (keys, d + 8) (keys + 8, d + 8)
+  const uint32_t k_lane = sK_addr + (uint32_t)((((lm >> 1) * 8 + lr) * PITCH + (lm & 1) * 8) * 2);
+  const uint32_t v_lane = sV_addr + (uint32_t)((((lm & 1) * 8 + lr) * PITCH + (lm >> 1) * 8) * 2);
   uint32_t qa[NT][D / 16][4];
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
@@ -332,6 +339,8 @@ __device__ __forceinline__ void attn_tiles(const bf16 *__restrict__ base, int C,
       else if (blk == 2 * gblk) { cp_async_wait<0>(); __syncthreads(); }
     }
     const int kb = blk * KVB;
+    const uint32_t k_blk = k_lane + (uint32_t)blk * (KVB * PITCH * 2);
+    const uint32_t v_blk = v_lane + (uint32_t)blk * (KVB * PITCH * 2);
     float sc[NT][KVB / 8][4];
 #pragma unroll
     for (int t = 0; t < NT; ++t)
@@ -343,11 +352,8 @@ __device__ __forceinline__ void attn_tiles(const bf16 *__restrict__ base, int C,
     for (int kk = 0; kk < D / 16; ++kk) {
 #pragma unroll
       for (int np = 0; np < KVB / 16; ++np) {
-        // matrices: (keys np*16 + 0..7, d kk*16 + 0..7) (same keys, d + 8) (keys + 8, d) (keys + 8, d + 8)
-        const int key = kb + np * 16 + (lm >> 1) * 8 + lr;
-        const int col = kk * 16 + (lm & 1) * 8;
         uint32_t b0, b1, b2, b3;
-        ldmatrix_x4(sK_addr + (uint32_t)(key * PITCH + col) * 2, b0, b1, b2, b3);
+        ldmatrix_x4(k_blk + (np * 16 * PITCH + kk * 16) * 2, b0, b1, b2, b3);
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           mma_bf16_16816(sc[t][np * 2], qa[t][kk], b0, b1);
@@ -413,11 +419,8 @@ __device__ __forceinline__ void attn_tiles(const bf16 *__restrict__ base, int C,
     for (int kt = 0; kt < KVB / 16; ++kt) {
 #pragma unroll
       for (int np = 0; np < D / 16; ++np) {
-        // transposed: (keys kt*16 + 0..7, d np*16 + 0..7) (keys + 8, same d) (keys, d + 8) (keys + 8, d + 8)
-        const int key = kb + kt * 16 + (lm & 1) * 8 + lr;
-        const int col = np * 16 + (lm >> 1) * 8;
         uint32_t b0, b1, b2, b3;
-        ldmatrix_x4_trans(sV_addr + (uint32_t)(key * PITCH + col) * 2, b0, b1, b2, b3);
+        ldmatrix_x4_trans(v_blk + (kt * 16 * PITCH + np * 16) * 2, b0, b1, b2, b3);
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           mma_bf16_16816(o[t][np * 2], pa[t][kt], b0, b1);
@@ -498,7 +501,7 @@ attention_bf16_mma2_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out,
   }
   // ---- tail tiles (e.g. the 17th tile of S = 261): all warps split the KV blocks of one tile,
   //      partial (m, l, O) meet in shared memory ----
-  const int tw = nw < ATT2_TAILW ? nw : ATT2_TAILW;
+  const int tw = min(min(nw, nblk), ATT2_TAILW);   // ideally one KV block per cooperating warp
   for (int tile = full_units * TPW; tile < tiles; ++tile) {
     constexpr int PW_ = (D / 8) * 4 * 32 + 4 * 32;        // floats per warp partial
     if (warp < tw) {
@@ -559,7 +562,7 @@ static int launch_attn_mma2(const void *qkv, void *out, int B, int S, int h, cud
   const int S_pad = ((S + KVB - 1) / KVB) * KVB;
   const bool tail = (units / nw) * nw * TPW < tiles;
   const size_t smem = (size_t)2 * S_pad * (D + 8) * sizeof(bf16) +
-                      (tail ? (size_t)(nw < ATT2_TAILW ? nw : ATT2_TAILW) * ((D / 8) * 4 * 32 + 4 * 32) * sizeof(float) : 0);
+                      (tail ? (size_t)std::min(std::min(nw, S_pad / KVB), ATT2_TAILW) * ((D / 8) * 4 * 32 + 4 * 32) * sizeof(float) : 0);
   if (smem > 220 * 1024) return -1;             // does not fit: the dispatcher tries the next kernel
   auto kern = attention_bf16_mma2_kernel<D, TPW, MAXW>;
   static size_t configured = 0;

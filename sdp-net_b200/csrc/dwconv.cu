@@ -179,8 +179,8 @@ struct DwLayout {
     off = 2 * Tn;                              // int[Tn]
     w = (3 * Tn + 3) & ~3;                     // 2 x [KS*KS][32] float2 (16-byte aligned)
     raw = w + 2 * KS * KS * 64;                // [Tn][32] raw bf16x2 words of the NEXT slab
-    tile = raw + Tn * 32;                      // [PH][PW][32] normalised bf16x2, zero halo
-    total = tile + PH * PW * 32;
+    tile = (raw + Tn * 32 + 1) & ~1;           // [PH][PW][32] normalised float2 (channel pair), zero halo
+    total = tile + PH * PW * 64;
   }
 };
 
@@ -201,7 +201,7 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
   int *s_off = reinterpret_cast<int *>(smem + L.off);
   float2 *s_w = reinterpret_cast<float2 *>(smem + L.w);
   uint32_t *s_raw = reinterpret_cast<uint32_t *>(smem + L.raw);
-  uint32_t *tile = reinterpret_cast<uint32_t *>(smem + L.tile);
+  float2 *tile = reinterpret_cast<float2 *>(smem + L.tile);
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bf16 *xin = act + ((long long)b * S + R) * C;       // first patch row of this image
@@ -228,7 +228,7 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
 
   for (int i = tid; i < R * C / 2; i += DWF_THREADS) reinterpret_cast<uint32_t *>(xout)[i] = 0u;
   // zero the whole tile once: the halo cells are never written again
-  for (int i = tid; i < PH * PW * 32; i += DWF_THREADS) tile[i] = 0u;
+  for (int i = tid; i < PH * PW * 32; i += DWF_THREADS) tile[i] = make_float2(0.f, 0.f);
   for (int t = tid; t < Tn; t += DWF_THREADS) s_off[t] = ((t / Gw + lo) * PW + (t % Gw + lo)) * 32;
 
   // ---- phase 1: token statistics, one pass with the row's first element as shift (no
@@ -281,7 +281,9 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
       const uint32_t u = s_raw[t * 32 + lane];
       const float m = s_mean[t], r = s_rstd[t];
       const float lo_v = __uint_as_float(u << 16), hi_v = __uint_as_float(u & 0xffff0000u);
-      tile[s_off[t] + lane] = cok ? pack_bf16x2((lo_v - m) * r * g.x + be.x, (hi_v - m) * r * g.y + be.y) : 0u;
+      // kept in fp32: no unpack in the FMA loop (the normalised value is not re-rounded either)
+      tile[s_off[t] + lane] = cok ? make_float2((lo_v - m) * r * g.x + be.x, (hi_v - m) * r * g.y + be.y)
+                                  : make_float2(0.f, 0.f);
     }
     __syncthreads();                               // tile ready; s_raw free
     if (c0 + 64 < C) prefetch(c0 + 64, buf ^ 1);   // next slab streams in under this slab's FMAs
@@ -297,14 +299,10 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
         float2 w[KS];
 #pragma unroll
         for (int dx = 0; dx < KS; ++dx) w[dx] = cok ? wslab[(dy * KS + dx) * 32] : make_float2(0.f, 0.f);
-        const uint32_t *trow = tile + ((y + dy) * PW + x0) * 32 + lane;
+        const float2 *trow = tile + ((y + dy) * PW + x0) * 32 + lane;
         float2 win[DW_XB + KS - 1];
 #pragma unroll
-        for (int xx = 0; xx < DW_XB + KS - 1; ++xx) {
-          const uint32_t u = trow[xx * 32];
-          win[xx].x = __uint_as_float(u << 16);
-          win[xx].y = __uint_as_float(u & 0xffff0000u);
-        }
+        for (int xx = 0; xx < DW_XB + KS - 1; ++xx) win[xx] = trow[xx * 32];
 #pragma unroll
         for (int dx = 0; dx < KS; ++dx)
 #pragma unroll

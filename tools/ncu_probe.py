@@ -31,14 +31,17 @@ a2, n2 = act.view(M, C), norm.view(M, C)
 
 
 def timed(name, fn, flops=0, nbytes=0):
+    ts = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-    extra = ""
+        ts.append(e0.elapsed_time(e1))
+    ts = sorted(ts[1:] or ts)
+    ms = ts[len(ts) // 2]                      # median of the warm repetitions
+    extra = f"  (min {ts[0]:.3f})"
     if flops:
         extra += f"  {flops / ms / 1e9:8.1f} TFLOP/s"
     if nbytes:
