@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SDPNET_B200_ABI_VERSION 2
+#define SDPNET_B200_ABI_VERSION 3
 
 typedef enum { SDP_F32 = 0, SDP_BF16 = 1 } sdp_dtype;
 
@@ -75,6 +75,16 @@ int sdp_device_ok(void);
  * (eps headnorm_eps, affine hn_q_* for columns < headnorm_C, hn_k_* above) -- the per-head
  * nn.LayerNorm on q and k (layers.py:236-237,286) fused into the projection's epilogue.
  * Supported for headnorm_d in {32, 64, 96, 128} (see sdp_gemm_headnorm_ok); needs bias == NULL.
+ *
+ * LayerNorm folding (bf16 only; removes the stand-alone token-LayerNorm pass of layers.py:280,307 and
+ * :103).  A producer GEMM whose output is the residual stream (N == C) also emits, per output row and
+ * per column part, the partial (sum, sum of squares) of the bf16 values it stores:
+ *     stats_out[(ro * stats_parts + part) * 2 + {0,1}],  stats_parts == sdp_gemm_stats_parts(N)
+ * A consumer GEMM reading that stream as A applies LN(x) @ W^T without ever materialising LN(x):
+ * with W' = W * diag(gamma) (given as `W`), ln_s[n] = sum_k W'[n,k], ln_t[n] = sum_k beta[k] W[n,k] + b[n]:
+ *     v = rstd_r * (acc - mean_r * ln_s[c]) + ln_t[c]
+ * where (mean_r, rstd_r) come from ln_stats (ln_parts partials per row, eps ln_eps, dim K).  Applied
+ * before the head-norm / activation / residual steps; needs bias == NULL.
  * --------------------------------------------------------------------------------------- */
 typedef struct {
   const void *A;        int64_t lda;   /* [M, K], row pitch in elements */
@@ -94,11 +104,20 @@ typedef struct {
   int32_t headnorm_d, headnorm_C;
   float headnorm_eps;
   const float *hn_q_w, *hn_q_b, *hn_k_w, *hn_k_b;
+  float *stats_out;     int32_t stats_parts;      /* producer side, or NULL */
+  const float *ln_stats; int32_t ln_parts;        /* consumer side, or NULL */
+  float ln_eps;
+  const float *ln_s, *ln_t;                       /* [N] each */
 } sdp_gemm_args;
 
 int sdp_gemm(const sdp_gemm_args *args, void *stream);
 /* 1 if sdp_gemm can fuse the per-head LayerNorm for this head_dim / N / dtype. */
 int sdp_gemm_headnorm_ok(int head_dim, int N, int dtype);
+/* Number of per-row column parts a producer GEMM of width N emits into stats_out (0: unsupported). */
+int sdp_gemm_stats_parts(int N, int dtype);
+/* Stand-alone producer of the same statistics layout (after the patch embedding / register fill):
+ * part 0 holds the row's full (sum, sum of squares), the other parts are zero.  x: [M, C]. */
+int sdp_row_stats(const void *x, int64_t ldx, float *stats, int parts, int M, int C, int dtype, void *stream);
 
 /* im2col for kernel == stride patches (layers.py:34-42): x NCHW [B,3,H,W] (fp32 or bf16) ->
  * A [B*T, ldA] with A[b*T + i*Gw + j, c*p*p + dy*p + dx] = x[b, c, i*p+dy, j*p+dx]; columns
@@ -123,6 +142,11 @@ int sdp_layernorm_rows(const void *x, int64_t ldx, const float *w, const float *
 int sdp_ln_dwconv(const void *act, const float *gamma, const float *beta, const float *wdw,
                   const float *bdw, void *out, int B, int Gh, int Gw, int C, int k, int R,
                   float eps, int dtype, void *stream);
+/* Same, with the token statistics supplied by the producer GEMM (stats layout as above; row index =
+ * b * S + R + t) instead of being recomputed from `act`.  stats == NULL behaves like sdp_ln_dwconv. */
+int sdp_ln_dwconv_stats(const void *act, const float *stats, int parts, const float *gamma, const float *beta,
+                        const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int k,
+                        int R, float eps, int dtype, void *stream);
 
 /* Fused QK-LayerNorm + softmax attention (layers.py:282-300): qkv [B, S, 3C] with column
  * blocks q | k | v, each [h, d]; q/k get a per-head LayerNorm(d) (eps, affine) when
@@ -162,10 +186,11 @@ int sdp_activation(const void *x, void *y, int64_t n, int act, int dtype, void *
 typedef struct {          /* one EncoderLayer, layers.py:216-257 */
   const float *norm1_w, *norm1_b, *norm2_w, *norm2_b;
   const float *qn_w, *qn_b, *kn_w, *kn_b;          /* NULL when normalize_qv=False */
-  const void *w_qkv;                               /* [3C, C] = cat(q_proj, k_proj, v_proj) */
+  const void *w_qkv;                               /* [3C, C] = cat(q_proj, k_proj, v_proj); * diag(norm1_w) when ln_fold */
   const void *w_o;                                 /* [C, C] */
   const void *w_ff1; const float *b_ff1;           /* [mC, C], [mC] */
   const void *w_ff2; const float *b_ff2;           /* [C, mC], [C] */
+  const float *s_qkv, *t_qkv, *s_ff1, *t_ff1;      /* LN-fold vectors ([3C], [3C], [mC], [mC]) or NULL */
 } sdp_encoder_weights;
 
 typedef struct {          /* one ConvMixer, layers.py:63-99 */
@@ -174,6 +199,7 @@ typedef struct {          /* one ConvMixer, layers.py:63-99 */
   const void *w_pw;  const float *b_pw;            /* [C, C] */
   const void *w_mlp1; const float *b_mlp1;         /* [4C, C] */
   const void *w_mlp2; const float *b_mlp2;         /* [C, 4C] */
+  const float *s_mlp1, *t_mlp1;                    /* LN-fold vectors [4C] or NULL */
 } sdp_mixer_weights;
 
 typedef struct {
@@ -183,6 +209,7 @@ typedef struct {
   int32_t head_from_register, head_simple;
   int32_t Kp;                    /* padded 3*p*p (pitch of w_patch and of the im2col buffer) */
   int32_t Kc;                    /* padded `classes` (pitch of w_head2 and of the hidden buffer) */
+  int32_t ln_fold;               /* 1: token LayerNorms are folded into their consumer GEMMs (bf16 only) */
   const void *w_patch;           /* [C, Kp] */
   const float *pos_table;        /* [T, C] fp32, precomputed for this grid (layers.py:158-163 / :205) */
   const float *reg_table;        /* [R, C] fp32, the R selected register rows */
@@ -202,6 +229,7 @@ typedef struct {                 /* caller-allocated device workspaces */
   void *im2col;   /* [B*T, Kp] */
   void *pooled;   /* [B, C] */
   void *head_h;   /* [B, Kc] */
+  float *stats;   /* [B*S, sdp_gemm_stats_parts(C), 2] fp32 (ln_fold only) */
 } sdp_workspace;
 
 /* x: NCHW [B,3,H,W] in x_dtype; logits: fp32 [B, classes]. */

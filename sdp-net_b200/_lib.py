@@ -37,26 +37,29 @@ class GemmArgs(C.Structure):
         ("pass_seq", c_i32), ("pass_rows", c_i32),
         ("headnorm_d", c_i32), ("headnorm_C", c_i32), ("headnorm_eps", c_float),
         ("hn_q_w", c_void_p), ("hn_q_b", c_void_p), ("hn_k_w", c_void_p), ("hn_k_b", c_void_p),
+        ("stats_out", c_void_p), ("stats_parts", c_i32),
+        ("ln_stats", c_void_p), ("ln_parts", c_i32), ("ln_eps", c_float),
+        ("ln_s", c_void_p), ("ln_t", c_void_p),
     ]
 
 
 class EncoderWeights(C.Structure):
     _fields_ = [(n, c_void_p) for n in (
         "norm1_w", "norm1_b", "norm2_w", "norm2_b", "qn_w", "qn_b", "kn_w", "kn_b",
-        "w_qkv", "w_o", "w_ff1", "b_ff1", "w_ff2", "b_ff2")]
+        "w_qkv", "w_o", "w_ff1", "b_ff1", "w_ff2", "b_ff2", "s_qkv", "t_qkv", "s_ff1", "t_ff1")]
 
 
 class MixerWeights(C.Structure):
     _fields_ = [(n, c_void_p) for n in (
         "ln1_g", "ln1_b", "ln2_g", "ln2_b", "w_dw", "b_dw", "w_pw", "b_pw",
-        "w_mlp1", "b_mlp1", "w_mlp2", "b_mlp2")]
+        "w_mlp1", "b_mlp1", "w_mlp2", "b_mlp2", "s_mlp1", "t_mlp1")]
 
 
 class ModelDesc(C.Structure):
     _fields_ = [(n, c_i32) for n in (
         "dtype", "C", "n_head", "num_blocks", "conv_block_num", "ff_mult", "conv_k", "patch",
         "classes", "act", "embed_act", "conv_first", "head_from_register", "head_simple",
-        "Kp", "Kc")] + [
+        "Kp", "Kc", "ln_fold")] + [
         ("w_patch", c_void_p), ("pos_table", c_void_p), ("reg_table", c_void_p),
         ("enc", C.POINTER(EncoderWeights)), ("mix", C.POINTER(MixerWeights)),
         ("head_ln_w", c_void_p), ("head_ln_b", c_void_p),
@@ -67,7 +70,7 @@ class ModelDesc(C.Structure):
 
 class Workspace(C.Structure):
     _fields_ = [(n, c_void_p) for n in (
-        "act", "norm", "qkv", "attn", "hidden", "im2col", "pooled", "head_h")]
+        "act", "norm", "qkv", "attn", "hidden", "im2col", "pooled", "head_h", "stats")]
 
 
 # every symbol include/sdpnet_b200.h declares: name -> (restype, argtypes)
@@ -77,6 +80,9 @@ SYMBOLS = {
     "sdp_device_ok": (c_int, []),
     "sdp_gemm": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "sdp_gemm_headnorm_ok": (c_int, [c_int, c_int, c_int]),
+    "sdp_gemm_stats_parts": (c_int, [c_int, c_int]),
+    "sdp_row_stats": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "sdp_ln_dwconv_stats": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "sdp_im2col_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_fill_registers": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_layernorm_rows": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_float, c_int, c_void_p]),
@@ -111,7 +117,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)   # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if handle.sdp_abi_version() != 2:
+        if handle.sdp_abi_version() != 3:
             raise SdpNetLibraryError("libsdpnet_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

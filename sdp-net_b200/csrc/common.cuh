@@ -143,6 +143,12 @@ struct Epilogue {
   int hn_d, hn_C;
   float hn_eps;
   const float *hn_qw, *hn_qb, *hn_kw, *hn_kb;
+  float *stats_out;          // producer: per-row column-part (sum, sumsq) of the stored bf16 values
+  int stats_parts;
+  const float *ln_stats;     // consumer: LayerNorm folded into this GEMM
+  int ln_parts, ln_K;
+  float ln_eps;
+  const float *ln_s, *ln_t;
 };
 
 struct RowMap {

@@ -186,10 +186,10 @@ struct DwLayout {
 
 template <int KS>
 __global__ void __launch_bounds__(DWF_THREADS, 1)
-ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ gamma,
-                      const float *__restrict__ beta, const float *__restrict__ wdw,
-                      const float *__restrict__ bdw, bf16 *__restrict__ out, int Gh, int Gw, int C, int R,
-                      float eps, int PW) {
+ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ stats, int parts,
+                      const float *__restrict__ gamma, const float *__restrict__ beta,
+                      const float *__restrict__ wdw, const float *__restrict__ bdw, bf16 *__restrict__ out, int Gh,
+                      int Gw, int C, int R, float eps, int PW) {
   extern __shared__ __align__(16) float smem[];
   constexpr int lo = (KS - 1) / 2;
   constexpr int NW = DWF_THREADS / 32;
@@ -231,9 +231,23 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
   for (int i = tid; i < PH * PW * 32; i += DWF_THREADS) tile[i] = make_float2(0.f, 0.f);
   for (int t = tid; t < Tn; t += DWF_THREADS) s_off[t] = ((t / Gw + lo) * PW + (t % Gw + lo)) * 32;
 
-  // ---- phase 1: token statistics, one pass with the row's first element as shift (no
-  //      cancellation: the shift is within a few sigma of the mean), 4 tokens in flight per warp ----
-  {
+  // ---- phase 1: token statistics.  Preferred: the (sum, sumsq) column parts the producer GEMM emitted
+  //      for exactly these bf16 values; otherwise one pass over the rows with the first element as
+  //      shift (no cancellation: the shift is within a few sigma of the mean), 4 tokens per warp ----
+  if (stats != nullptr) {
+    const float *sp = stats + ((long long)b * S + R) * parts * 2;
+    for (int t = tid; t < Tn; t += DWF_THREADS) {
+      float s1 = 0.0f, s2 = 0.0f;
+      for (int p = 0; p < parts; ++p) {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(sp + ((long long)t * parts + p) * 2));
+        s1 += v.x;
+        s2 += v.y;
+      }
+      const float mean = s1 / (float)C;
+      s_mean[t] = mean;
+      s_rstd[t] = 1.0f / sqrtf(fmaxf(s2 / (float)C - mean * mean, 0.0f) + eps);
+    }
+  } else {
     const int nv = C >> 3;
     for (int t0 = warp * 4; t0 < Tn; t0 += NW * 4) {
       float s1[4], s2[4], sh[4];
@@ -323,9 +337,9 @@ ln_dwconv_bf16_kernel(const bf16 *__restrict__ act, const float *__restrict__ ga
 }
 
 template <int KS>
-static int launch_dw_bf16(const void *act, const float *gamma, const float *beta, const float *wdw,
-                          const float *bdw, void *out, int B, int Gh, int Gw, int C, int R, float eps,
-                          cudaStream_t st) {
+static int launch_dw_bf16(const void *act, const float *stats, int parts, const float *gamma, const float *beta,
+                          const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int R,
+                          float eps, cudaStream_t st) {
   const int PW = ((Gw + DW_XB - 1) / DW_XB) * DW_XB + KS - 1;
   const int PH = Gh + KS - 1;
   const DwLayout L(Gh * Gw, PH, PW, KS);
@@ -337,7 +351,8 @@ static int launch_dw_bf16(const void *act, const float *gamma, const float *beta
     SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  kern<<<B, DWF_THREADS, smem, st>>>((const bf16 *)act, gamma, beta, wdw, bdw, (bf16 *)out, Gh, Gw, C, R, eps, PW);
+  kern<<<B, DWF_THREADS, smem, st>>>((const bf16 *)act, stats, parts, gamma, beta, wdw, bdw, (bf16 *)out, Gh, Gw, C, R, eps,
+                                     PW);
   SDP_LAUNCH_OK();
   return 0;
 }
@@ -380,7 +395,15 @@ using namespace sdp;
 extern "C" int sdp_ln_dwconv(const void *act, const float *gamma, const float *beta, const float *wdw,
                              const float *bdw, void *out, int B, int Gh, int Gw, int C, int k, int R, float eps,
                              int dtype, void *stream) {
+  return sdp_ln_dwconv_stats(act, nullptr, 0, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, dtype, stream);
+}
+
+extern "C" int sdp_ln_dwconv_stats(const void *act, const float *stats, int parts, const float *gamma,
+                                   const float *beta, const float *wdw, const float *bdw, void *out, int B, int Gh,
+                                   int Gw, int C, int k, int R, float eps, int dtype, void *stream) {
   SDP_CHECK(act && gamma && beta && wdw && out, "sdp_ln_dwconv: null pointer");
+  SDP_CHECK(stats == nullptr || (parts > 0 && dtype == SDP_BF16 && (k == 3 || k == 5 || k == 7) && C % 8 == 0),
+            "sdp_ln_dwconv_stats: producer statistics are consumed by the bf16 k in {3,5,7} kernel only");
   SDP_CHECK(B > 0 && Gh > 0 && Gw > 0 && C > 0 && k > 0 && R >= 0, "sdp_ln_dwconv: bad sizes");
   SDP_CHECK(act != out, "sdp_ln_dwconv: must not run in place (spatial neighbours are read)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -390,10 +413,11 @@ extern "C" int sdp_ln_dwconv(const void *act, const float *gamma, const float *b
                       (reinterpret_cast<uintptr_t>(gamma) & 7) == 0 && (reinterpret_cast<uintptr_t>(beta) & 7) == 0 &&
                       (bdw == nullptr || (reinterpret_cast<uintptr_t>(bdw) & 7) == 0);
     int rc = -1;
-    if (fast && k == 7) rc = launch_dw_bf16<7>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
-    if (fast && k == 5) rc = launch_dw_bf16<5>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
-    if (fast && k == 3) rc = launch_dw_bf16<3>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+    if (fast && k == 7) rc = launch_dw_bf16<7>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+    if (fast && k == 5) rc = launch_dw_bf16<5>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+    if (fast && k == 3) rc = launch_dw_bf16<3>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
     if (rc >= 0) return rc;
+    SDP_CHECK(stats == nullptr, "sdp_ln_dwconv_stats: the fast kernel does not fit this shape; pass stats == NULL");
     return dispatch_dw<bf16>(act, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, st);
   }
   SDP_CHECK(dtype == SDP_F32, "sdp_ln_dwconv: unknown dtype %d", dtype);

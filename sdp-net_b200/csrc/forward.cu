@@ -42,11 +42,18 @@ struct Ctx {
   const sdp_model_desc *m;
   const sdp_workspace *ws;
   int B, S, T, R, Gh, Gw;
+  int parts;       // column parts of the row-statistics buffer (ln_fold)
   void *st;
 };
 
+struct Fold {                 // LayerNorm folded into the consumer GEMM (bf16 only)
+  const float *s = nullptr, *t = nullptr;
+  float eps = 0.0f;
+};
+
 int gemm(const Ctx &c, const void *A, long long lda, const void *W, long long ldw, const float *bias, int M, int N,
-         int K, int act, const void *res, void *out, long long ldo, int out_dtype, bool mask_regs) {
+         int K, int act, const void *res, void *out, long long ldo, int out_dtype, bool mask_regs,
+         const Fold *fold = nullptr, bool emit_stats = false, const sdp_encoder_weights *qk = nullptr) {
   sdp_gemm_args a;
   memset(&a, 0, sizeof(a));
   a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.bias = bias;
@@ -55,6 +62,14 @@ int gemm(const Ctx &c, const void *A, long long lda, const void *W, long long ld
   a.dtype = c.m->dtype; a.out_dtype = out_dtype; a.res_dtype = c.m->dtype;
   a.act = act;
   if (mask_regs && c.R > 0) { a.pass_seq = c.S; a.pass_rows = c.R; }
+  if (fold) {
+    a.ln_stats = c.ws->stats; a.ln_parts = c.parts; a.ln_eps = fold->eps; a.ln_s = fold->s; a.ln_t = fold->t;
+  }
+  if (emit_stats) { a.stats_out = c.ws->stats; a.stats_parts = c.parts; }
+  if (qk) {     // per-head q/k LayerNorm in the QKV epilogue
+    a.headnorm_d = c.m->C / c.m->n_head; a.headnorm_C = c.m->C; a.headnorm_eps = 1e-5f;
+    a.hn_q_w = qk->qn_w; a.hn_q_b = qk->qn_b; a.hn_k_w = qk->kn_w; a.hn_k_b = qk->kn_b;
+  }
   return sdp_gemm(&a, c.st);
 }
 
@@ -62,40 +77,52 @@ int gemm(const Ctx &c, const void *A, long long lda, const void *W, long long ld
 int encoder(const Ctx &c, const sdp_encoder_weights &w) {
   const sdp_model_desc &m = *c.m;
   const int C = m.C, M = c.B * c.S, dt = m.dtype, F = m.ff_mult * C;
-  if (int rc = sdp_layernorm_rows(c.ws->act, C, w.norm1_w, w.norm1_b, c.ws->norm, C, M, C, 1e-5f, dt, c.st)) return rc;
+  const bool fold = m.ln_fold != 0;
   // q/k LayerNorm (layers.py:286): fused into the QKV GEMM epilogue when the tile holds whole heads,
   // otherwise applied by the attention kernel while it loads q and k
   const int d = C / m.n_head;
   const bool fuse_qk = w.qn_w != nullptr && sdp_gemm_headnorm_ok(d, 3 * C, dt);
-  {
-    sdp_gemm_args a;
-    memset(&a, 0, sizeof(a));
-    a.A = c.ws->norm; a.lda = C; a.W = w.w_qkv; a.ldw = C; a.out = c.ws->qkv; a.ldo = 3 * C;
-    a.M = M; a.N = 3 * C; a.K = C; a.dtype = dt; a.out_dtype = dt; a.res_dtype = dt;
-    if (fuse_qk) {
-      a.headnorm_d = d; a.headnorm_C = C; a.headnorm_eps = 1e-5f;
-      a.hn_q_w = w.qn_w; a.hn_q_b = w.qn_b; a.hn_k_w = w.kn_w; a.hn_k_b = w.kn_b;
-    }
-    if (int rc = sdp_gemm(&a, c.st)) return rc;
+  const void *xin = c.ws->act;                  // with folding the GEMMs read the residual stream itself
+  if (!fold) {
+    if (int rc = sdp_layernorm_rows(c.ws->act, C, w.norm1_w, w.norm1_b, c.ws->norm, C, M, C, 1e-5f, dt, c.st)) return rc;
+    xin = c.ws->norm;
   }
+  Fold f1; f1.s = w.s_qkv; f1.t = w.t_qkv; f1.eps = 1e-5f;
+  if (int rc = gemm(c, xin, C, w.w_qkv, C, nullptr, M, 3 * C, C, SDP_ACT_NONE, nullptr, c.ws->qkv, 3 * C, dt, false,
+                    fold ? &f1 : nullptr, false, fuse_qk ? &w : nullptr)) return rc;
   if (int rc = sdp_attention(c.ws->qkv, fuse_qk ? nullptr : w.qn_w, fuse_qk ? nullptr : w.qn_b,
                              fuse_qk ? nullptr : w.kn_w, fuse_qk ? nullptr : w.kn_b, c.ws->attn, c.B, c.S, m.n_head, d,
                              1e-5f, dt, c.st)) return rc;
-  if (int rc = gemm(c, c.ws->attn, C, w.w_o, C, nullptr, M, C, C, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, false)) return rc;
-  if (int rc = sdp_layernorm_rows(c.ws->act, C, w.norm2_w, w.norm2_b, c.ws->norm, C, M, C, 1e-5f, dt, c.st)) return rc;
-  if (int rc = gemm(c, c.ws->norm, C, w.w_ff1, C, w.b_ff1, M, F, C, m.act, nullptr, c.ws->hidden, F, dt, false)) return rc;
-  return gemm(c, c.ws->hidden, F, w.w_ff2, F, w.b_ff2, M, C, F, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, false);
+  if (int rc = gemm(c, c.ws->attn, C, w.w_o, C, nullptr, M, C, C, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, false,
+                    nullptr, fold)) return rc;
+  if (!fold) {
+    if (int rc = sdp_layernorm_rows(c.ws->act, C, w.norm2_w, w.norm2_b, c.ws->norm, C, M, C, 1e-5f, dt, c.st)) return rc;
+  }
+  Fold f2; f2.s = w.s_ff1; f2.t = w.t_ff1; f2.eps = 1e-5f;
+  if (int rc = gemm(c, xin, C, w.w_ff1, C, fold ? nullptr : w.b_ff1, M, F, C, m.act, nullptr, c.ws->hidden, F, dt, false,
+                    fold ? &f2 : nullptr)) return rc;
+  return gemm(c, c.ws->hidden, F, w.w_ff2, F, w.b_ff2, M, C, F, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, false, nullptr,
+              fold);
 }
 
 // layers.py:101-104
 int mixer(const Ctx &c, const sdp_mixer_weights &w) {
   const sdp_model_desc &m = *c.m;
   const int C = m.C, M = c.B * c.S, dt = m.dtype;
-  if (int rc = sdp_ln_dwconv(c.ws->act, w.ln1_g, w.ln1_b, w.w_dw, w.b_dw, c.ws->norm, c.B, c.Gh, c.Gw, C, m.conv_k, c.R, 1e-6f, dt, c.st)) return rc;
-  if (int rc = gemm(c, c.ws->norm, C, w.w_pw, C, w.b_pw, M, C, C, m.act, c.ws->act, c.ws->act, C, dt, true)) return rc;
-  if (int rc = sdp_layernorm_rows(c.ws->act, C, w.ln2_g, w.ln2_b, c.ws->norm, C, M, C, 1e-6f, dt, c.st)) return rc;
-  if (int rc = gemm(c, c.ws->norm, C, w.w_mlp1, C, w.b_mlp1, M, 4 * C, C, m.act, nullptr, c.ws->hidden, 4 * C, dt, false)) return rc;
-  return gemm(c, c.ws->hidden, 4 * C, w.w_mlp2, 4 * C, w.b_mlp2, M, C, 4 * C, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, true);
+  const bool fold = m.ln_fold != 0;
+  if (int rc = sdp_ln_dwconv_stats(c.ws->act, fold ? c.ws->stats : nullptr, c.parts, w.ln1_g, w.ln1_b, w.w_dw, w.b_dw,
+                                   c.ws->norm, c.B, c.Gh, c.Gw, C, m.conv_k, c.R, 1e-6f, dt, c.st)) return rc;
+  if (int rc = gemm(c, c.ws->norm, C, w.w_pw, C, w.b_pw, M, C, C, m.act, c.ws->act, c.ws->act, C, dt, true, nullptr, fold)) return rc;
+  const void *xin = c.ws->act;
+  if (!fold) {
+    if (int rc = sdp_layernorm_rows(c.ws->act, C, w.ln2_g, w.ln2_b, c.ws->norm, C, M, C, 1e-6f, dt, c.st)) return rc;
+    xin = c.ws->norm;
+  }
+  Fold f; f.s = w.s_mlp1; f.t = w.t_mlp1; f.eps = 1e-6f;
+  if (int rc = gemm(c, xin, C, w.w_mlp1, C, fold ? nullptr : w.b_mlp1, M, 4 * C, C, m.act, nullptr, c.ws->hidden, 4 * C, dt,
+                    false, fold ? &f : nullptr)) return rc;
+  return gemm(c, c.ws->hidden, 4 * C, w.w_mlp2, 4 * C, w.b_mlp2, M, C, 4 * C, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, true,
+              nullptr, fold);
 }
 
 }  // namespace
@@ -112,6 +139,9 @@ extern "C" int sdp_forward(const sdp_model_desc *m, const sdp_workspace *ws, con
   c.Gh = H / m->patch; c.Gw = W / m->patch;
   c.T = c.Gh * c.Gw; c.S = c.T + R;
   const int C = m->C, dt = m->dtype, Kc3 = 3 * m->patch * m->patch;
+  c.parts = m->ln_fold ? sdp_gemm_stats_parts(C, dt) : 0;
+  SDP_CHECK(!m->ln_fold || (dt == SDP_BF16 && c.parts > 0 && ws->stats != nullptr),
+            "sdp_forward: ln_fold needs bf16 and a statistics workspace");
 
   // patcher + position table + embedding activation, scattered behind the register rows
   // (layers.py:34-42, :152-168 / :202-209)
@@ -127,6 +157,8 @@ extern "C" int sdp_forward(const sdp_model_desc *m, const sdp_workspace *ws, con
     if (int rc = sdp_gemm(&a, stream)) return rc;
   }
   if (int rc = sdp_fill_registers(ws->act, dt, m->reg_table, B, c.S, R, C, stream)) return rc;
+  if (m->ln_fold)   // first statistics of the residual stream; every later producer GEMM refreshes its rows
+    if (int rc = sdp_row_stats(ws->act, C, ws->stats, c.parts, B * c.S, C, dt, stream)) return rc;
 
   for (int i = 0; i < m->num_blocks; ++i) {            // model.py:139-140, layers.py:377-386
     if (m->conv_first)

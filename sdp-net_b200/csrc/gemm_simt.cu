@@ -6,6 +6,7 @@
 namespace sdp {
 
 int gemm_bf16_tc(const sdp_gemm_args &a, const Epilogue &e, cudaStream_t st);
+int gemm_stats_parts(int N);
 
 constexpr int SB_M = 64, SB_N = 64, SB_K = 16;
 
@@ -71,6 +72,8 @@ extern "C" int sdp_gemm_headnorm_ok(int d, int N, int dtype) {
   return dtype == SDP_BF16 && (d == 32 || d == 64 || d == 96 || d == 128) && N % d == 0 ? 1 : 0;
 }
 
+extern "C" int sdp_gemm_stats_parts(int N, int dtype) { return dtype == SDP_BF16 && N > 0 ? gemm_stats_parts(N) : 0; }
+
 extern "C" int sdp_gemm(const sdp_gemm_args *a, void *stream) {
   SDP_CHECK(a != nullptr, "sdp_gemm: null args");
   SDP_CHECK(a->M > 0 && a->N > 0 && a->K > 0, "sdp_gemm: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
@@ -100,6 +103,19 @@ extern "C" int sdp_gemm(const sdp_gemm_args *a, void *stream) {
   e.hn_C = a->headnorm_C;
   e.hn_eps = a->headnorm_eps;
   e.hn_qw = a->hn_q_w; e.hn_qb = a->hn_q_b; e.hn_kw = a->hn_k_w; e.hn_kb = a->hn_k_b;
+  e.stats_out = a->stats_out; e.stats_parts = a->stats_parts;
+  e.ln_stats = a->ln_stats; e.ln_parts = a->ln_parts; e.ln_K = a->K; e.ln_eps = a->ln_eps;
+  e.ln_s = a->ln_s; e.ln_t = a->ln_t;
+  if (a->stats_out) {
+    SDP_CHECK(a->stats_parts > 0 && a->stats_parts == sdp_gemm_stats_parts(a->N, a->dtype) && a->out_dtype == SDP_BF16 &&
+                  a->seq_in == 0,
+              "sdp_gemm: stats_out needs a bf16 tensor-core GEMM with stats_parts == sdp_gemm_stats_parts(N)");
+  }
+  if (a->ln_stats) {
+    SDP_CHECK(a->dtype == SDP_BF16 && a->ln_parts > 0 && a->ln_parts % 2 == 0 && a->ln_s && a->ln_t && a->bias == nullptr &&
+                  (reinterpret_cast<uintptr_t>(a->ln_stats) & 15) == 0,
+              "sdp_gemm: LN folding needs bf16, ln_s/ln_t, an even ln_parts and no bias");
+  }
   if (a->headnorm_d) {
     SDP_CHECK(sdp_gemm_headnorm_ok(a->headnorm_d, a->N, a->dtype), "sdp_gemm: head-norm unsupported for d=%d N=%d dtype=%d",
               a->headnorm_d, a->N, a->dtype);

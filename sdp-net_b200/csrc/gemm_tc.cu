@@ -343,6 +343,33 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       };
       fetch_res(n0 + u_begin * UNIT);            // before the accumulator is even ready
+      // LayerNorm folded into this GEMM: the row's (mean, rstd) from the producer's column-part sums
+      const bool lnf = epi.ln_stats != nullptr;
+      float ln_mean = 0.0f, ln_rstd = 1.0f;
+      if (lnf && rm.live) {
+        const float4 *sp = reinterpret_cast<const float4 *>(epi.ln_stats + (long long)(m0 + quad * 32 + lane) * epi.ln_parts * 2);
+        float s1 = 0.0f, s2 = 0.0f;
+        for (int p2 = 0; p2 < epi.ln_parts / 2; ++p2) {
+          const float4 t = __ldg(sp + p2);
+          s1 += t.x + t.z;
+          s2 += t.y + t.w;
+        }
+        const float inv = 1.0f / (float)epi.ln_K;
+        ln_mean = s1 * inv;
+        ln_rstd = rsqrtf(fmaxf(s2 * inv - ln_mean * ln_mean, 0.0f) + epi.ln_eps);
+      }
+      auto ln_fold = [&](float *v, int col) {      // v = rstd * (acc - mean * s[col..]) + t[col..], 32 columns
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 sv = __ldg(reinterpret_cast<const float4 *>(epi.ln_s + col + j));
+          const float4 tv = __ldg(reinterpret_cast<const float4 *>(epi.ln_t + col + j));
+          v[j] = fmaf(ln_rstd, fmaf(-ln_mean, sv.x, v[j]), tv.x);
+          v[j + 1] = fmaf(ln_rstd, fmaf(-ln_mean, sv.y, v[j + 1]), tv.y);
+          v[j + 2] = fmaf(ln_rstd, fmaf(-ln_mean, sv.z, v[j + 2]), tv.z);
+          v[j + 3] = fmaf(ln_rstd, fmaf(-ln_mean, sv.w, v[j + 3]), tv.w);
+        }
+      };
+      float st1 = 0.0f, st2 = 0.0f;              // producer side: sums of the bf16 values this thread stores
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
@@ -363,6 +390,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               float v[32];
               tmem_ld32(taddr + c + i, v);
               tmem_ld_wait();
+              if (lnf) ln_fold(v, col0 + i);
 #pragma unroll
               for (int j = 0; j < 32; ++j) s += v[j];
             }
@@ -373,6 +401,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               float v[32];
               tmem_ld32(taddr + c + i, v);
               tmem_ld_wait();
+              if (lnf) ln_fold(v, col0 + i);
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float dlt = v[j] - mean;
@@ -390,6 +419,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[32];
           tmem_ld32(taddr + c + i, v);
           tmem_ld_wait();
+          if (lnf && col0 + i + 32 <= epi.N) ln_fold(v, col0 + i);
           if constexpr (HN > 0) {
             if (hw != nullptr) {
 #pragma unroll
@@ -433,6 +463,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + ((j ^ sw) << 4)), "r"(p0), "r"(p1),
                              "r"(p2), "r"(p3)
                              : "memory");
+                if (epi.stats_out != nullptr) {  // statistics of exactly the values consumers will read
+                  const uint32_t pw[4] = {p0, p1, p2, p3};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float lo = __uint_as_float(pw[q] << 16), hi = __uint_as_float(pw[q] & 0xffff0000u);
+                    const bool in_lo = col + 8 * j + 2 * q < epi.N, in_hi = col + 8 * j + 2 * q + 1 < epi.N;
+                    if (in_lo) { st1 += lo; st2 = fmaf(lo, lo, st2); }
+                    if (in_hi) { st1 += hi; st2 = fmaf(hi, hi, st2); }
+                  }
+                }
               }
               fence_proxy_async_smem();
               __syncwarp();
@@ -444,6 +484,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
+      }
+      if (STAGED && epi.stats_out != nullptr && rm.live) {
+        const int part = (tile % n_tiles) * 2 + half;
+        *reinterpret_cast<float2 *>(epi.stats_out + (rm.ro * epi.stats_parts + part) * 2) = make_float2(st1, st2);
       }
       tc_fence_before();
       __syncwarp();
@@ -557,6 +601,19 @@ static int num_sms() {
   return n;
 }
 
+static int pick_bn(int N) {   // BLOCK_N minimising padded columns; ties -> the larger tile
+  int bn = 256;
+  long best = -1;
+  const int cand[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const long padded = (long)((N + cand[i] - 1) / cand[i]) * cand[i];
+    if (best < 0 || padded < best) { best = padded; bn = cand[i]; }
+  }
+  return bn;
+}
+
+int gemm_stats_parts(int N) { const int bn = pick_bn(N); return 2 * ((N + bn - 1) / bn); }
+
 static bool staged_ok(const Epilogue &e) {
   return e.out_dtype == SDP_BF16 && e.seq_in == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 &&
          (e.ldo * 2) % 16 == 0 && (e.pass_seq == 0 || e.residual != nullptr);
@@ -636,6 +693,8 @@ int gemm_bf16_tc(const sdp_gemm_args &a, const Epilogue &e, cudaStream_t st) {
   if (e.hn_d) {
     // QKV projection with the per-head LayerNorm fused: the N block must hold whole heads
     SDP_CHECK(e.act == SDP_ACT_NONE, "sdp_gemm: head-norm epilogue has no activation");
+    SDP_CHECK(e.stats_out == nullptr, "sdp_gemm: head-norm GEMMs do not emit row statistics");
+    SDP_CHECK(e.ln_stats == nullptr || (staged_ok(e) && epilogue_vec_ok(e)), "sdp_gemm: LN folding needs the staged bf16 epilogue");
     if (e.hn_d == 96) return launch_tc<192, 4, SDP_ACT_NONE, 96>(a, ta, e, st);
     if (a.N % 256 == 0) {
       if (e.hn_d == 32) return launch_tc<256, 4, SDP_ACT_NONE, 32>(a, ta, e, st);
@@ -646,16 +705,10 @@ int gemm_bf16_tc(const sdp_gemm_args &a, const Epilogue &e, cudaStream_t st) {
     if (e.hn_d == 64) return launch_tc<128, 6, SDP_ACT_NONE, 64>(a, ta, e, st);
     return launch_tc<128, 6, SDP_ACT_NONE, 128>(a, ta, e, st);
   }
-  // BLOCK_N minimising padded columns; ties -> the larger tile
-  int bn = 256;
-  {
-    long best = -1;
-    const int cand[3] = {256, 128, 64};
-    for (int i = 0; i < 3; ++i) {
-      const long padded = (long)((a.N + cand[i] - 1) / cand[i]) * cand[i];
-      if (best < 0 || padded < best) { best = padded; bn = cand[i]; }
-    }
-  }
+  SDP_CHECK(e.stats_out == nullptr || staged_ok(e), "sdp_gemm: stats_out needs the staged bf16 epilogue");
+  SDP_CHECK(e.ln_stats == nullptr || (staged_ok(e) && a.N % 32 == 0 && epilogue_vec_ok(e)),
+            "sdp_gemm: LN folding needs the staged bf16 epilogue and N %% 32 == 0");
+  const int bn = pick_bn(a.N);
   switch (bn) {
     case 256: return launch_tc_act<256, 4>(a, ta, e, st);
     case 128: return launch_tc_act<128, 6>(a, ta, e, st);

@@ -145,6 +145,29 @@ static int launch_ln_rows(const void *x, long long ldx, const float *w, const fl
   return 0;
 }
 
+// Row (sum, sum of squares) in the producer-GEMM statistics layout: part 0 = full sums, others 0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+row_stats_kernel(const T *__restrict__ x, long long ldx, float *__restrict__ stats, int parts, int M, int C) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const T *xr = x + (long long)row * ldx;
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int c = lane; c < C; c += 32) {
+    const float v = to_f(xr[c]);
+    s1 += v;
+    s2 = fmaf(v, v, s2);
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  float *o = stats + (long long)row * parts * 2;
+  for (int p = lane; p < parts; p += 32) {
+    o[2 * p] = p == 0 ? s1 : 0.0f;
+    o[2 * p + 1] = p == 0 ? s2 : 0.0f;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void fill_registers_kernel(T *act, const float *__restrict__ table, int B, int S, int R, int C) {
@@ -304,6 +327,17 @@ extern "C" int sdp_layernorm_rows(const void *x, int64_t ldx, const float *w, co
   if (dtype == SDP_BF16) return launch_ln_rows<bf16>(x, ldx, w, b, out, ldo, M, C, eps, st);
   SDP_CHECK(dtype == SDP_F32, "sdp_layernorm_rows: unknown dtype %d", dtype);
   return launch_ln_rows<float>(x, ldx, w, b, out, ldo, M, C, eps, st);
+}
+
+extern "C" int sdp_row_stats(const void *x, int64_t ldx, float *stats, int parts, int M, int C, int dtype,
+                             void *stream) {
+  SDP_CHECK(x && stats && parts > 0 && M > 0 && C > 0, "sdp_row_stats: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const dim3 grid((M + 7) / 8), block(256);
+  if (dtype == SDP_BF16) row_stats_kernel<bf16><<<grid, block, 0, st>>>((const bf16 *)x, ldx, stats, parts, M, C);
+  else row_stats_kernel<float><<<grid, block, 0, st>>>((const float *)x, ldx, stats, parts, M, C);
+  SDP_LAUNCH_OK();
+  return 0;
 }
 
 extern "C" int sdp_fill_registers(void *act, int dtype, const float *table, int B, int S, int R, int C,

@@ -78,7 +78,8 @@ class Packer:
     """Moves parameters to the device in kernel layout: GEMM weights [N, K] in the compute dtype,
     everything else fp32.  Owns the packed tensors (`keep`)."""
 
-    def __init__(self, device, precision: str, C_: int, n_head: int = 1, act: str = "none"):
+    def __init__(self, device, precision: str, C_: int, n_head: int = 1, act: str = "none", ln_fold: bool = False):
+        self.ln_fold = bool(ln_fold) and precision == "bf16"
         if precision not in _TORCH_DT:
             raise ValueError("precision must be 'bf16' or 'fp32'")
         self.precision = precision
@@ -107,6 +108,20 @@ class Packer:
         self.keep.append(t)
         return t
 
+    def _fold(self, W: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor]):
+        """LN(x) @ W^T + b  ==  rstd * (x @ W'^T - mean * s) + t  with  W' = W diag(gamma) (bf16),
+        s = rowsum(W') of the ROUNDED weights (what the tensor cores multiply), t = W beta + b."""
+        W = W.detach().to(self.device, torch.float32).reshape(W.shape[0], -1)
+        gamma, beta = gamma.detach().to(self.device, torch.float32), beta.detach().to(self.device, torch.float32)
+        Wf = (W * gamma[None, :]).to(self.dtype).contiguous()
+        s_vec = Wf.float().sum(1).contiguous()
+        t_vec = (W @ beta)
+        if bias is not None:
+            t_vec = t_vec + bias.detach().to(self.device, torch.float32)
+        t_vec = t_vec.contiguous()
+        self.keep += [Wf, s_vec, t_vec]
+        return Wf, s_vec, t_vec
+
     def _pack_encoder(self, sd, pre: str) -> dict:
         g = lambda k: sd.get(pre + k)
         w = dict(
@@ -118,13 +133,19 @@ class Packer:
             w_o=self._w(g("o_proj.weight")),
             w_ff1=self._w(g("ff_linear1.weight")), b_ff1=self._f(g("ff_linear1.bias")),
             w_ff2=self._w(g("ff_linear2.weight")), b_ff2=self._f(g("ff_linear2.bias")),
+            s_qkv=None, t_qkv=None, s_ff1=None, t_ff1=None,
         )
+        if self.ln_fold:    # norm1 -> QKV and norm2 -> ff_linear1 folded (layers.py:280-284, 307-308)
+            wqkv = torch.cat([g("q_proj.weight"), g("k_proj.weight"), g("v_proj.weight")], 0)
+            w["w_qkv"], w["s_qkv"], w["t_qkv"] = self._fold(wqkv, g("norm1.weight"), g("norm1.bias"), None)
+            w["w_ff1"], w["s_ff1"], w["t_ff1"] = self._fold(g("ff_linear1.weight"), g("norm2.weight"), g("norm2.bias"),
+                                                            g("ff_linear1.bias"))
         return w
 
     def _pack_mixer(self, sd, pre: str) -> dict:
         g = lambda k: sd.get(pre + k)
         wd = g("conv2d.0.weight")
-        return dict(
+        w = dict(
             ln1_g=self._f(g("layer_norm_1.gamma")), ln1_b=self._f(g("layer_norm_1.beta")),
             ln2_g=self._f(g("layer_norm_2.gamma")), ln2_b=self._f(g("layer_norm_2.beta")),
             w_dw=self._f(wd.reshape(wd.shape[0], -1).t()),   # tap-major [k*k, C]
@@ -132,13 +153,18 @@ class Packer:
             w_pw=self._w(g("conv2d.1.weight")), b_pw=self._f(g("conv2d.1.bias")),
             w_mlp1=self._w(g("conv1d.0.weight")), b_mlp1=self._f(g("conv1d.0.bias")),
             w_mlp2=self._w(g("conv1d.2.weight")), b_mlp2=self._f(g("conv1d.2.bias")),
+            s_mlp1=None, t_mlp1=None,
         )
+        if self.ln_fold:    # layer_norm_2 -> conv1d[0] folded (layers.py:103)
+            w["w_mlp1"], w["s_mlp1"], w["t_mlp1"] = self._fold(g("conv1d.0.weight"), g("layer_norm_2.gamma"),
+                                                               g("layer_norm_2.beta"), g("conv1d.0.bias"))
+        return w
 
 
 class PackedWeights(Packer):
     """The whole model's parameters, packed (see Packer)."""
 
-    def __init__(self, cfg: dict, sd: Dict[str, torch.Tensor], device, precision: str = "bf16"):
+    def __init__(self, cfg: dict, sd: Dict[str, torch.Tensor], device, precision: str = "bf16", ln_fold: bool = True):
         full = dict(MODEL_DEFAULTS)
         full.update(cfg)
         self.cfg = full
@@ -146,7 +172,9 @@ class PackedWeights(Packer):
         n_head = int(full["n_head"])
         if C_ % n_head != 0:   # layers.py:229
             raise ValueError("Number of embedding_dim must be divisible by n_head")
-        super().__init__(device, precision, C_, n_head, _act_name(full["activation"]))
+        # folding needs whole 32-column chunks in the consumer GEMMs (N = 3C, mC, 4C) and k in {3,5,7}
+        ln_fold = ln_fold and precision == "bf16" and C_ % 32 == 0 and int(full["conv_kernel_size"]) in (3, 5, 7)
+        super().__init__(device, precision, C_, n_head, _act_name(full["activation"]), ln_fold)
         self.embed_act = _act_name(full["embedding_activation"])
         self._pos_cache: Dict[tuple, torch.Tensor] = {}
         self._reg_cache: Dict[int, torch.Tensor] = {}
@@ -229,6 +257,8 @@ class Buffers:
         self.im2col = e(B * T, Kp)
         self.pooled = e(B, C_)
         self.head_h = torch.zeros(B, Kc, dtype=dt, device=dev)
+        parts = ops.gemm_stats_parts(C_, dt) if getattr(pw, "ln_fold", False) else 0
+        self.stats = torch.zeros(B * S, parts, 2, dtype=torch.float32, device=dev) if parts else None
         self.logits = torch.empty(B, classes, dtype=torch.float32, device=dev)
 
     def nbytes(self) -> int:
@@ -243,20 +273,28 @@ def run_encoder(pw: Packer, w: dict, bufs: Buffers, act_name: Optional[str] = No
     mult = w["w_ff1"].shape[0]
     a2, n2 = bufs.act.view(M, C_), bufs.norm.view(M, C_)
     hid = bufs.hidden.view(-1)[: M * mult].view(M, mult)
-    ops.layernorm_rows(a2, w["norm1_w"], w["norm1_b"], n2, 1e-5)
+    fold = w["s_qkv"] is not None and bufs.stats is not None
+    st = bufs.stats if fold else None
     d = C_ // pw.n_head
+    hn = None
     if w["qn_w"] is not None and ops.gemm_headnorm_ok(d, 3 * C_, pw.dtype):
-        # q/k LayerNorm fused into the QKV epilogue; attention receives normalised q, k
-        ops.gemm(n2, w["w_qkv"], bufs.qkv.view(M, 3 * C_),
-                 headnorm=(d, C_, 1e-5, w["qn_w"], w["qn_b"], w["kn_w"], w["kn_b"]))
+        hn = (d, C_, 1e-5, w["qn_w"], w["qn_b"], w["kn_w"], w["kn_b"])   # q/k LayerNorm in the QKV epilogue
+    xin = a2
+    if not fold:
+        ops.layernorm_rows(a2, w["norm1_w"], w["norm1_b"], n2, 1e-5)
+        xin = n2
+    ops.gemm(xin, w["w_qkv"], bufs.qkv.view(M, 3 * C_), headnorm=hn,
+             ln_fold=(st, 1e-5, w["s_qkv"], w["t_qkv"]) if fold else None)
+    if hn is not None:
         ops.attention(bufs.qkv, bufs.attn, pw.n_head, None, None, None, None, 1e-5)
     else:
-        ops.gemm(n2, w["w_qkv"], bufs.qkv.view(M, 3 * C_))
         ops.attention(bufs.qkv, bufs.attn, pw.n_head, w["qn_w"], w["qn_b"], w["kn_w"], w["kn_b"], 1e-5)
-    ops.gemm(bufs.attn.view(M, C_), w["w_o"], a2, residual=a2)
-    ops.layernorm_rows(a2, w["norm2_w"], w["norm2_b"], n2, 1e-5)
-    ops.gemm(n2, w["w_ff1"], hid, bias=w["b_ff1"], act=act_name or pw.act)
-    ops.gemm(hid, w["w_ff2"], a2, bias=w["b_ff2"], residual=a2)
+    ops.gemm(bufs.attn.view(M, C_), w["w_o"], a2, residual=a2, stats_out=st)
+    if not fold:
+        ops.layernorm_rows(a2, w["norm2_w"], w["norm2_b"], n2, 1e-5)
+    ops.gemm(xin, w["w_ff1"], hid, bias=None if fold else w["b_ff1"], act=act_name or pw.act,
+             ln_fold=(st, 1e-5, w["s_ff1"], w["t_ff1"]) if fold else None)
+    ops.gemm(hid, w["w_ff2"], a2, bias=w["b_ff2"], residual=a2, stats_out=st)
 
 
 def run_mixer(pw: Packer, w: dict, bufs: Buffers, Gh: int, Gw: int, act_name: Optional[str] = None) -> None:
@@ -267,19 +305,26 @@ def run_mixer(pw: Packer, w: dict, bufs: Buffers, Gh: int, Gw: int, act_name: Op
     a2, n2 = bufs.act.view(M, C_), bufs.norm.view(M, C_)
     hid = bufs.hidden.view(-1)[: M * 4 * C_].view(M, 4 * C_)
     pr = (S, R) if R > 0 else (0, 0)
-    ops.ln_dwconv(bufs.act, w["ln1_g"], w["ln1_b"], w["w_dw"], w["b_dw"], bufs.norm, Gh, Gw, R, 1e-6)
-    ops.gemm(n2, w["w_pw"], a2, bias=w["b_pw"], act=act_name, residual=a2, pass_rows=pr)
-    ops.layernorm_rows(a2, w["ln2_g"], w["ln2_b"], n2, 1e-6)
-    ops.gemm(n2, w["w_mlp1"], hid, bias=w["b_mlp1"], act=act_name)
-    ops.gemm(hid, w["w_mlp2"], a2, bias=w["b_mlp2"], residual=a2, pass_rows=pr)
+    fold = w["s_mlp1"] is not None and bufs.stats is not None
+    st = bufs.stats if fold else None
+    ops.ln_dwconv(bufs.act, w["ln1_g"], w["ln1_b"], w["w_dw"], w["b_dw"], bufs.norm, Gh, Gw, R, 1e-6, stats=st)
+    ops.gemm(n2, w["w_pw"], a2, bias=w["b_pw"], act=act_name, residual=a2, pass_rows=pr, stats_out=st)
+    xin = a2
+    if not fold:
+        ops.layernorm_rows(a2, w["ln2_g"], w["ln2_b"], n2, 1e-6)
+        xin = n2
+    ops.gemm(xin, w["w_mlp1"], hid, bias=None if fold else w["b_mlp1"], act=act_name,
+             ln_fold=(st, 1e-6, w["s_mlp1"], w["t_mlp1"]) if fold else None)
+    ops.gemm(hid, w["w_mlp2"], a2, bias=w["b_mlp2"], residual=a2, pass_rows=pr, stats_out=st)
 
 
 class Engine:
-    def __init__(self, cfg: dict, state_dict: Dict[str, torch.Tensor], device="cuda", precision: str = "bf16"):
+    def __init__(self, cfg: dict, state_dict: Dict[str, torch.Tensor], device="cuda", precision: str = "bf16",
+                 ln_fold: bool = True):
         if precision not in _TORCH_DT:
             raise ValueError("precision must be 'bf16' or 'fp32'")
         L.lib()   # fail loudly before anything else if the CUDA library is missing
-        self.pw = PackedWeights(cfg, state_dict, device, precision)
+        self.pw = PackedWeights(cfg, state_dict, device, precision, ln_fold)
         self.cfg = self.pw.cfg
         self._bufs: Dict[tuple, Buffers] = {}
         self._desc_keep = None
@@ -305,6 +350,7 @@ class Engine:
         d.conv_first = int(bool(cfg["conv_first"]))
         d.head_from_register, d.head_simple = int(pw.head_from_register), int(pw.head_simple)
         d.Kp, d.Kc = pw.Kp, pw.Kc
+        d.ln_fold = int(pw.ln_fold)
         d.w_patch = p(pw.w_patch)
         d.pos_table, d.reg_table = p(pw.pos_table(Gh, Gw)), p(pw.reg_table(R))
         d.enc, d.mix = enc, mix
@@ -353,7 +399,8 @@ class Engine:
             d = self._desc(Gh, Gw, R)
             ws = L.Workspace()
             for name, _ in L.Workspace._fields_:
-                setattr(ws, name, getattr(bufs, name).data_ptr())
+                t = getattr(bufs, name)
+                setattr(ws, name, None if t is None else t.data_ptr())
             rc = L.lib().sdp_forward(C.byref(d), C.byref(ws), x.data_ptr(), ops._dt(x), B, x.shape[2], x.shape[3], R,
                                      bufs.logits.data_ptr(), torch.cuda.current_stream().cuda_stream)
             L.check(rc, "sdp_forward")
@@ -378,6 +425,8 @@ class Engine:
         ops.gemm(bufs.im2col, pw.w_patch, bufs.act.view(B * S, C_), residual=pw.pos_table(Gh, Gw), res_first=True,
                  res_mod=T, act=pw.embed_act, seq_remap=(T, S, R), K=3 * p * p)
         ops.fill_registers(bufs.act, pw.reg_table(R))
+        if bufs.stats is not None:
+            ops.row_stats(bufs.act, bufs.stats)
         note("embed")
         cbn = int(cfg["conv_block_num"])
         for i in range(int(cfg["num_blocks"])):

@@ -55,7 +55,7 @@ def act_id(name) -> int:
 def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, act="none", res_first: bool = False, res_mod: int = 0,
          seq_remap=(0, 0, 0), pass_rows=(0, 0), M: Optional[int] = None, N: Optional[int] = None,
-         K: Optional[int] = None, headnorm=None) -> torch.Tensor:
+         K: Optional[int] = None, headnorm=None, ln_fold=None, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epi(A[M,K] @ W[N,K]^T); see sdp_gemm in the header for the epilogue definition."""
     if A.dim() != 2 or W.dim() != 2 or out.dim() != 2:
         raise ValueError("gemm operands must be 2-D (views with a row pitch are fine)")
@@ -84,12 +84,30 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, bias: Optional[
         a.headnorm_d, a.headnorm_C, a.headnorm_eps = int(d), int(Cm), float(eps)
         a.hn_q_w, a.hn_q_b = _p(_f32(qw, "q_norm.weight")), _p(_f32(qb, "q_norm.bias"))
         a.hn_k_w, a.hn_k_b = _p(_f32(kw, "k_norm.weight")), _p(_f32(kb, "k_norm.bias"))
+    if ln_fold is not None:       # (stats [M, parts, 2], eps, s [N], t [N]): LayerNorm folded into this GEMM
+        st, eps, ls, lt = ln_fold
+        a.ln_stats, a.ln_parts, a.ln_eps = _p(_f32(st, "ln stats")), int(st.shape[-2]), float(eps)
+        a.ln_s, a.ln_t = _p(_f32(ls, "ln_s")), _p(_f32(lt, "ln_t"))
+    if stats_out is not None:     # [M_out, parts, 2]: the producer emits row statistics of what it stores
+        a.stats_out, a.stats_parts = _p(_f32(stats_out, "stats_out")), int(stats_out.shape[-2])
     L.check(L.lib().sdp_gemm(C.byref(a), _stream()), "sdp_gemm")
     return out
 
 
 def gemm_headnorm_ok(head_dim: int, N: int, dtype: torch.dtype) -> bool:
     return bool(L.lib().sdp_gemm_headnorm_ok(int(head_dim), int(N), _DT[dtype]))
+
+
+def gemm_stats_parts(N: int, dtype: torch.dtype) -> int:
+    return int(L.lib().sdp_gemm_stats_parts(int(N), _DT[dtype]))
+
+
+def row_stats(x: torch.Tensor, stats: torch.Tensor) -> torch.Tensor:
+    """stats [M, parts, 2] fp32 <- per-row (sum, sum of squares) of x [M, C] in the producer-GEMM layout."""
+    x2 = x.reshape(-1, x.shape[-1])
+    L.check(L.lib().sdp_row_stats(_p(x2), x2.stride(0), _p(_f32(stats, "stats")), int(stats.shape[-2]), x2.shape[0],
+                                  x2.shape[1], _dt(x2), _stream()), "sdp_row_stats")
+    return stats
 
 
 def im2col_patches(x: torch.Tensor, A: torch.Tensor, patch: int) -> torch.Tensor:
@@ -121,16 +139,18 @@ def layernorm_rows(x: torch.Tensor, w: Optional[torch.Tensor], b: Optional[torch
 
 
 def ln_dwconv(act: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, wdw: torch.Tensor,
-              bdw: Optional[torch.Tensor], out: torch.Tensor, Gh: int, Gw: int, R: int, eps: float = 1e-6):
+              bdw: Optional[torch.Tensor], out: torch.Tensor, Gh: int, Gw: int, R: int, eps: float = 1e-6,
+              stats: Optional[torch.Tensor] = None):
     B, S, Cc = act.shape
     if S != R + Gh * Gw or not act.is_contiguous() or not out.is_contiguous():
         raise ValueError("ln_dwconv: act must be contiguous [B, R + Gh*Gw, C]")
     k = int(round(wdw.shape[0] ** 0.5))      # wdw is tap-major [k*k, C]
     if wdw.dim() != 2 or k * k != wdw.shape[0] or wdw.shape[1] != Cc:
         raise ValueError("ln_dwconv: wdw must be tap-major [k*k, C]")
-    L.check(L.lib().sdp_ln_dwconv(_p(act), _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")),
-                                  _p(_f32(wdw, "wdw")), _p(_f32(bdw, "bdw")), _p(out), B, Gh, Gw, Cc, k, R,
-                                  float(eps), _dt(act), _stream()), "sdp_ln_dwconv")
+    L.check(L.lib().sdp_ln_dwconv_stats(_p(act), _p(_f32(stats, "stats")), 0 if stats is None else int(stats.shape[-2]),
+                                        _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")), _p(_f32(wdw, "wdw")),
+                                        _p(_f32(bdw, "bdw")), _p(out), B, Gh, Gw, Cc, k, R, float(eps), _dt(act),
+                                        _stream()), "sdp_ln_dwconv")
     return out
 
 

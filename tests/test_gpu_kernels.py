@@ -140,6 +140,65 @@ def test_gemm_bf16_headnorm_epilogue(sdp, C, h):
     assert not sdp.ops.gemm_headnorm_ok(96, 2304, torch.float32)
 
 
+@pytest.mark.parametrize("M,C,K,R", [(1305, 768, 768, 5), (603, 512, 2048, 4), (300, 128, 128, 0), (77, 32, 64, 2)])
+def test_gemm_bf16_emits_row_statistics(sdp, M, C, K, R):
+    """Producer side of the LayerNorm folding: per-row column-part (sum, sumsq) of the stored bf16 values;
+    pass-through (register) rows keep their previous statistics."""
+    S = 9 if R else 0
+    A = rnd(M, K, seed=70, dtype=torch.bfloat16)
+    W = rnd(C, K, seed=71, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    x = (rnd(M, C, seed=72) * 2 + 0.7).to(torch.bfloat16)
+    parts = sdp.ops.gemm_stats_parts(C, torch.bfloat16)
+    assert parts >= 2 and parts % 2 == 0
+    stats = torch.full((M, parts, 2), -7.0, device="cuda")
+    out = x.clone()
+    sdp.ops.gemm(A, W, out, residual=out, act="gelu", pass_rows=(S, R) if R else (0, 0), stats_out=stats)
+    live = torch.ones(M, dtype=torch.bool, device="cuda") if not R else (torch.arange(M, device="cuda") % S >= R)
+    got = stats.sum(1)
+    o = out.float()
+    assert (got[live, 0] - o[live].sum(1)).abs().max() < 2e-3 * (1 + o[live].abs().sum(1).max())
+    assert (got[live, 1] - (o[live] ** 2).sum(1)).abs().max() < 2e-3 * (1 + (o[live] ** 2).sum(1).max())
+    assert (stats[~live] == -7.0).all()
+    # stand-alone producer agrees
+    st2 = torch.empty_like(stats)
+    sdp.ops.row_stats(out, st2)
+    assert (st2.sum(1)[live] - got[live]).abs().max() < 2e-3 * (1 + got[live].abs().max())
+    assert (st2[:, 1:] == 0).all()
+
+
+@pytest.mark.parametrize("C,N,act,hn", [(768, 3072, "gelu", False), (768, 2304, "none", True), (512, 1536, "none", True),
+                                        (128, 512, "relu", False), (32, 96, "none", False)])
+def test_gemm_bf16_layernorm_fold(sdp, C, N, act, hn):
+    """Consumer side: LN(x) @ W^T + b computed as rstd * (x @ W'^T - mean * s) + t from the row statistics."""
+    M, eps = 777, 1e-5
+    x = (rnd(M, C, seed=73) * 1.7 + 0.9).to(torch.bfloat16)
+    W = rnd(N, C, seed=74, scale=1 / math.sqrt(C))
+    gamma, beta, bias = rnd(C, seed=75) * 0.3 + 1, rnd(C, seed=76) * 0.3, rnd(N, seed=77) * 0.2
+    Wf = (W * gamma[None, :]).to(torch.bfloat16)
+    s_vec, t_vec = Wf.float().sum(1).contiguous(), (W @ beta + bias).contiguous()
+    parts = sdp.ops.gemm_stats_parts(C, torch.bfloat16)
+    stats = torch.empty(M, parts, 2, device="cuda")
+    sdp.ops.row_stats(x, stats)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    kw = {}
+    h = 0
+    if hn:
+        h = 8
+        d = (N // 3) // h
+        qw, qb, kw_, kb = rnd(d, seed=78) * 0.3 + 1, rnd(d, seed=79) * 0.3, rnd(d, seed=80) * 0.3 + 1, rnd(d, seed=81) * 0.3
+        kw["headnorm"] = (d, N // 3, 1e-5, qw, qb, kw_, kb)
+    sdp.ops.gemm(x, Wf, out, act=act, ln_fold=(stats, eps, s_vec, t_vec), **kw)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, eps) @ W.t() + bias
+    if hn:
+        Cq = N // 3
+        q, k, v = ref.split(Cq, dim=-1)
+        q = F.layer_norm(q.view(M, h, d), (d,), qw, qb, 1e-5).view(M, Cq)
+        k = F.layer_norm(k.view(M, h, d), (d,), kw_, kb, 1e-5).view(M, Cq)
+        ref = torch.cat([q, k, v], -1)
+    ref = O.ACTIVATIONS[act](ref)
+    assert relerr(out, ref) < 1.5e-2
+
+
 @pytest.mark.parametrize("M,N,K", [(70, 50, 33), (129, 65, 100), (300, 128, 64)])
 def test_gemm_fp32(sdp, M, N, K):
     A, W = rnd(M, K, seed=13), rnd(N, K, seed=14, scale=1 / math.sqrt(K))
@@ -277,6 +336,13 @@ def test_ln_dwconv(sdp, dtype, Gh, Gw, C, k, R, bias):
     assert (out[:, :R] == 0).all()
     tol = 4e-2 if dtype == torch.bfloat16 else 5e-5
     assert (out.float() - ref).abs().max() < tol
+    if dtype == torch.bfloat16 and k in (3, 5, 7) and C % 8 == 0:
+        # token statistics supplied by a producer instead of recomputed in the kernel
+        stats = torch.empty(B * (R + Gh * Gw), 4, 2, device="cuda")
+        sdp.ops.row_stats(act, stats)
+        out2 = torch.full_like(act, float("nan"))
+        sdp.ops.ln_dwconv(act, gamma, beta, wdw.reshape(C, k * k).t().contiguous(), bdw, out2, Gh, Gw, R, stats=stats)
+        assert (out2.float() - ref).abs().max() < tol
 
 
 # --------------------------------------------------------------------------------------------
