@@ -61,4 +61,20 @@ timed("gemm ff1 gelu 3072x768", lambda: ops.gemm(n2, w1, hid.view(M, 4 * C), bia
 timed("gemm ff1 none 3072x768", lambda: ops.gemm(n2, w1, hid.view(M, 4 * C), bias=b1), flops=2 * M * 4 * C * C)
 timed("gemm ff2 +res 768x3072", lambda: ops.gemm(hid.view(M, 4 * C), w2, a2, bias=b2, residual=a2), flops=2 * M * 4 * C * C)
 timed("gemm pw gelu+res mask 768", lambda: ops.gemm(n2, w_o, a2, act="gelu", residual=a2, pass_rows=(S, R)), flops=2 * M * C * C)
+parts = ops.gemm_stats_parts(C, bf)
+stats = torch.zeros(M, parts, 2, device=dev)
+ops.row_stats(a2, stats)
+sv3, tv3 = rn(3 * C, dt=torch.float32), rn(3 * C, dt=torch.float32)
+sv4, tv4 = rn(4 * C, dt=torch.float32), rn(4 * C, dt=torch.float32)
+timed("row_stats", lambda: ops.row_stats(a2, stats), nbytes=2 * M * C)
+timed("ln_dwconv k7 (stats in)", lambda: ops.ln_dwconv(act, lw, lb, wdw, None, norm, G, G, R, stats=stats), flops=2 * B * T * C * k * k)
+timed("gemm qkv fold+headnorm", lambda: ops.gemm(a2, w_qkv, qkv.view(M, 3 * C), headnorm=(d, C, 1e-5, qw, qb, qw, qb),
+                                                ln_fold=(stats, 1e-5, sv3, tv3)), flops=2 * M * 3 * C * C)
+timed("gemm ff1 fold gelu", lambda: ops.gemm(a2, w1, hid.view(M, 4 * C), act="gelu", ln_fold=(stats, 1e-5, sv4, tv4)),
+      flops=2 * M * 4 * C * C)
+timed("gemm o +res +stats", lambda: ops.gemm(attn.view(M, C), w_o, a2, residual=a2, stats_out=stats), flops=2 * M * C * C)
+timed("gemm ff2 +res +stats", lambda: ops.gemm(hid.view(M, 4 * C), w2, a2, bias=b2, residual=a2, stats_out=stats),
+      flops=2 * M * 4 * C * C)
+timed("gemm pw gelu+res mask +stats", lambda: ops.gemm(n2, w_o, a2, act="gelu", residual=a2, pass_rows=(S, R), stats_out=stats),
+      flops=2 * M * C * C)
 print("done", time.strftime("%H:%M:%S"))
