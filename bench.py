@@ -236,6 +236,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SDP_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg, default_batch = CONFIGS[args.config]
     B = args.batch or default_batch
@@ -362,7 +363,7 @@ def main():
             line["layernorm_gbs"] = nbytes / (fam["layernorm_rows"]["ms_per_step"] / 1e3) / 1e9
         line["hbm_peak_gbs"] = peaks["hbm"]
 
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (host cores are shared by the ranks)
         v, cores, dt = cpu_forward_rate(cfg, args.cpu_batch)
         line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_batch} images, one fp32 forward of the oracle port "

@@ -1,0 +1,52 @@
+"""BASELINE.json configs[4]: isolated layer sweep at embed 768 -- one ConvMixer (DW 7x7 + pointwise + MLP)
+and one EncoderLayer with 5 register tokens on a 14x14 grid, batch 1..2048, bf16.  Times the engine's
+kernel sequence for the layer (token-major buffers, CUDA events, median of 7) and prints a markdown table."""
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import torch  # noqa: E402
+import sdpnet_b200 as sdp  # noqa: E402
+import sdpnet_oracle as O  # noqa: E402
+from sdpnet_b200.engine import Buffers, Packer, run_encoder, run_mixer  # noqa: E402
+
+C, h, G, R, k = 768, 8, 14, 5, 7
+T, S = G * G, G * G + R
+cfg = dict(embedding_dim=C, n_head=h, num_blocks=1, conv_kernel_size=k, patch_size=16, conv_block_num=1,
+           max_image_size=[16, 16], head_output_from_register=True)
+sd = O.synth_state_dict(cfg, seed=0, stress=True)
+pk = Packer("cuda", "bf16", C, h, "gelu")
+wm = pk._pack_mixer(sd, "blocks.0.conv_blocks.0.")
+we = pk._pack_encoder(sd, "blocks.0.t_block.")
+mix_flops = 2 * T * C * k * k + 2 * S * C * C + 16 * S * C * C
+enc_flops = 6 * S * C * C + 4 * S * S * C + 2 * S * C * C + 16 * S * C * C
+
+
+def med_ms(fn, reps=7):
+    ts = []
+    for _ in range(reps + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts = sorted(ts[2:])
+    return ts[len(ts) // 2]
+
+
+print("| batch | ConvMixer ms | img/s | TFLOP/s | EncoderLayer ms | img/s | TFLOP/s |")
+print("|---:|---:|---:|---:|---:|---:|---:|")
+B = 1
+while B <= 2048:
+    bufs = Buffers(pk, B, T, R)
+    bufs.act.copy_(torch.randn(B, S, C, device="cuda"))
+    tm = med_ms(lambda: run_mixer(pk, wm, bufs, G, G))
+    te = med_ms(lambda: run_encoder(pk, we, bufs))
+    print(f"| {B} | {tm:.3f} | {B / tm * 1e3:.0f} | {B * mix_flops / tm / 1e9:.1f} | {te:.3f} | {B / te * 1e3:.0f} | "
+          f"{B * enc_flops / te / 1e9:.1f} |", flush=True)
+    del bufs
+    B *= 2
