@@ -179,6 +179,14 @@ int sdp_embed_tokens(void *act, int dtype, const float *pos, int B, int T, int R
 /* Elementwise activation (embedding activation on a [n] buffer; test hook for epilogues). */
 int sdp_activation(const void *x, void *y, int64_t n, int act, int dtype, void *stream);
 
+/* Evaluation metrics right behind the forward, without per-batch host syncs (model_test.py:76-85,
+ * training_utilities.py:50-88, 95-107): for logits [B, K] (fp32) and integer labels [B], ADD into acc[4]
+ * (device doubles): sum over rows of cross-entropy, sum over all B*K elements of
+ * binary_cross_entropy_with_logits against the smoothed one-hot target
+ * (one_hot*(1-ls) + ls/K), number of rows whose argmax equals the label, number of rows. */
+int sdp_eval_metrics(const float *logits, int64_t ldl, const int64_t *labels, int B, int K, float label_smoothing,
+                     double *acc, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Whole-model forward (model.py:129-149) sequenced on the device side of the ABI: one call
  * enqueues every kernel of the forward on `stream`.

@@ -163,6 +163,21 @@ def kelu_layer_case():
     np.savez_compressed(os.path.join(OUT, "act_kelu_grid.npz"), x=t.numpy(), y=KeLu(t).numpy())
 
 
+def metrics_case():
+    """Reference losses / accuracy (model_test.py:70-83) on seeded logits."""
+    from training_utilities import BCEWithLogitsLoss
+    g = torch.Generator().manual_seed(99)
+    logits = 3.0 * torch.randn(37, 100, generator=g)
+    labels = torch.randint(0, 100, (37,), generator=g)
+    logits[torch.arange(0, 37, 3), labels[::3]] += 8.0        # make a third of the rows correct
+    out = dict(logits=logits.numpy(), labels=labels.numpy())
+    out["ce"] = np.array(float(torch.nn.CrossEntropyLoss()(logits, labels)))
+    out["acc"] = np.array(float((logits.argmax(1) == labels).float().mean()))
+    for ls in (0.0, 0.1):
+        out[f"bce_ls{ls}"] = np.array(float(BCEWithLogitsLoss(num_classes=100, label_smoothing=ls)(logits, labels)))
+    np.savez_compressed(os.path.join(OUT, "act_eval_metrics.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     for name, (cfg, H, W, B, nr, seed, stress, embed) in CASES.items():
@@ -191,6 +206,7 @@ def main():
         print(f"{name:24s} oracle-vs-reference max|d|={err:.2e}  stages={len(keep)} "
               f"size={os.path.getsize(path) / 1024:.0f} KiB")
     kelu_layer_case()
+    metrics_case()
     print("done ->", OUT)
 
 

@@ -351,6 +351,19 @@ def synth_state_dict(cfg: dict, seed: int = 0, stress: bool = False) -> Dict[str
     return sd
 
 
+def eval_metrics(logits: Tensor, labels: Tensor, label_smoothing: float = 0.0) -> dict:
+    """model_test.py:70-83 -- nn.CrossEntropyLoss() (mean over rows), the reference's BCEWithLogitsLoss
+    (training_utilities.py:95-107: one-hot, smooth to t*(1-ls)+ls/K, mean over all elements) and top-1."""
+    x = logits.double()
+    K = x.shape[1]
+    lse = torch.logsumexp(x, dim=1)
+    ce = (lse - x.gather(1, labels.view(-1, 1)).squeeze(1)).mean()
+    t = F.one_hot(labels, K).double() * (1.0 - label_smoothing) + label_smoothing / K
+    bce = (torch.clamp(x, min=0) - x * t + torch.log1p(torch.exp(-x.abs()))).mean()
+    acc = (x.argmax(1) == labels).double().mean()
+    return {"cross_entropy": float(ce), "bce_with_logits": float(bce), "accuracy": float(acc)}
+
+
 def flops_per_image(cfg: dict, H: int, W: int, R: int) -> float:
     """Algorithmic FLOPs (2*MAC) of one forward, SURVEY.md §8(d) formula."""
     cfg = full_config(cfg)

@@ -7,7 +7,7 @@
 
 Compute happens only in `lib/libsdpnet_b200.so` (hand-written CUDA, C-ABI in include/sdpnet_b200.h).
 """
-from . import _lib, engine, ops
+from . import _lib, checkpoint, engine, evaluate, ops, shard
 from .engine import Engine
 from .layers import (Block, ClassificationHead, ConvEmbedding, ConvMixer, ConvPatcher, EmbeddingLayer,
                      EncoderLayer, FinalBlock, LayerNorm, StochasticDepth)
@@ -15,4 +15,4 @@ from .model import MainModel, SdPModel, activations
 
 __all__ = ["MainModel", "SdPModel", "Engine", "Block", "ClassificationHead", "ConvEmbedding", "ConvMixer",
            "ConvPatcher", "EmbeddingLayer", "EncoderLayer", "FinalBlock", "LayerNorm", "StochasticDepth",
-           "activations", "ops", "engine"]
+           "activations", "ops", "engine", "checkpoint", "evaluate", "shard"]

@@ -292,6 +292,46 @@ __global__ void im2col_kernel(const TI *__restrict__ x, TO *__restrict__ A, long
   }
 }
 
+// one warp per row: log-sum-exp cross-entropy, smoothed-target BCE-with-logits, first-max argmax
+__global__ void __launch_bounds__(256)
+eval_metrics_kernel(const float *__restrict__ logits, long long ldl, const long long *__restrict__ labels, int B, int K,
+                    float ls, double *__restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float *x = logits + (long long)row * ldl;
+  const int label = (int)labels[row];
+  float mx = -INFINITY;
+  int arg = K;
+  for (int c = lane; c < K; c += 32) {
+    const float v = x[c];
+    if (v > mx) { mx = v; arg = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  const float t_on = 1.0f - ls + ls / (float)K, t_off = ls / (float)K;
+  float se = 0.0f, bce = 0.0f;
+  for (int c = lane; c < K; c += 32) {
+    const float v = x[c];
+    se += expf(v - mx);
+    const float t = c == label ? t_on : t_off;
+    bce += fmaxf(v, 0.0f) - v * t + log1pf(expf(-fabsf(v)));
+  }
+  se = warp_sum(se);
+  bce = warp_sum(bce);
+  if (lane == 0) {
+    const float ce = logf(se) + mx - x[label];
+    atomicAdd(acc + 0, (double)ce);
+    atomicAdd(acc + 1, (double)bce);
+    atomicAdd(acc + 2, arg == label ? 1.0 : 0.0);
+    atomicAdd(acc + 3, 1.0);
+  }
+}
+
 template <typename T, bool EXACT>
 __global__ void embed_tokens_kernel(T *__restrict__ act, const float *__restrict__ pos, int B, int T_, int R, int C,
                                     int act_id) {
@@ -425,6 +465,16 @@ extern "C" int sdp_im2col_patches(const void *x, int x_dtype, void *A, int a_dty
   else if (a_dtype == SDP_BF16) I2C(bf16, bf16);
   else I2C(bf16, float);
 #undef I2C
+  SDP_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sdp_eval_metrics(const float *logits, int64_t ldl, const int64_t *labels, int B, int K,
+                                float label_smoothing, double *acc, void *stream) {
+  SDP_CHECK(logits && labels && acc && B > 0 && K > 0 && ldl >= K, "sdp_eval_metrics: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  eval_metrics_kernel<<<(B + 7) / 8, 256, 0, st>>>(logits, ldl, reinterpret_cast<const long long *>(labels), B, K,
+                                                   label_smoothing, acc);
   SDP_LAUNCH_OK();
   return 0;
 }

@@ -198,6 +198,19 @@ def embed_tokens(act: torch.Tensor, pos: torch.Tensor, R: int, act_name="none") 
     return act
 
 
+def eval_metrics(logits: torch.Tensor, labels: torch.Tensor, acc: torch.Tensor, label_smoothing: float = 0.0):
+    """acc [4] float64 (device) += (sum CE, sum BCE-with-logits vs smoothed one-hot, #correct, #rows)."""
+    if logits.dtype != torch.float32 or logits.dim() != 2 or logits.stride(1) != 1:
+        raise TypeError("eval_metrics: logits must be float32 [B, K]")
+    if labels.dtype != torch.int64 or not labels.is_contiguous() or labels.shape[0] != logits.shape[0]:
+        raise TypeError("eval_metrics: labels must be contiguous int64 [B]")
+    if acc.dtype != torch.float64 or acc.numel() != 4 or not acc.is_contiguous():
+        raise TypeError("eval_metrics: acc must be 4 contiguous float64 values")
+    L.check(L.lib().sdp_eval_metrics(_p(logits), logits.stride(0), _p(labels), logits.shape[0], logits.shape[1],
+                                     float(label_smoothing), _p(acc), _stream()), "sdp_eval_metrics")
+    return acc
+
+
 def activation(x: torch.Tensor, act, force_fast: bool = False) -> torch.Tensor:
     x = x.contiguous()
     y = torch.empty_like(x)

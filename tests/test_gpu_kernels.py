@@ -382,6 +382,24 @@ def test_attention(sdp, dtype, S, h, d, norm):
     assert (out.float() - ref).abs().max() < tol
 
 
+@pytest.mark.parametrize("B,K,ls", [(37, 100, 0.0), (512, 1000, 0.1), (3, 7, 0.0)])
+def test_eval_metrics_kernel(sdp, B, K, ls):
+    """On-device CE / BCE / top-1 accumulation (model_test.py:76-85) against the oracle's definition."""
+    logits = rnd(B, K, seed=90, scale=3.0)
+    labels = torch.randint(0, K, (B,), generator=_g(91), device="cuda")
+    logits[torch.arange(0, B, 3, device="cuda"), labels[::3]] += 8.0
+    logits[1, :] = 0.25                                      # all-equal row: argmax must be index 0 like torch
+    meter = sdp.evaluate.EvalMeter("cuda", ls)
+    meter.update(logits[: B // 2], labels[: B // 2])         # two batches accumulate
+    meter.update(logits[B // 2:], labels[B // 2:])
+    got = meter.result()
+    ref = O.eval_metrics(logits.cpu(), labels.cpu(), ls)
+    assert got["samples"] == B
+    assert abs(got["cross_entropy"] - ref["cross_entropy"]) < 1e-4
+    assert abs(got["bce_with_logits"] - ref["bce_with_logits"]) < 1e-5
+    assert abs(got["accuracy"] - ref["accuracy"]) < 1e-9
+
+
 def test_launch_counter(sdp):
     sdp.ops.launch_count(reset=True)
     x = rnd(4, 64)

@@ -34,6 +34,10 @@ def _worker(rank, world, port, n_total, out_dir):
     lo, hi = shard.shard_range(n_total, rank, world)
     local = O.forward(sd, cfg, x[lo:hi], 3)
     full = shard.gather_logits(local, n_total)
+    # EvalMeter's cross-rank reduction is a SUM all_reduce of its 4 accumulators (CPU tensor here)
+    acc4 = torch.tensor([float(rank + 1), 2.0, 3.0, float(hi - lo)], dtype=torch.float64)
+    dist.all_reduce(acc4, op=dist.ReduceOp.SUM)
+    assert acc4.tolist() == [3.0, 4.0, 6.0, float(n_total)]
     correct, total = shard.reduce_counts(float((local.argmax(-1) == labels[lo:hi]).sum()), hi - lo)
     torch.save({"full": full, "correct": correct, "total": total, "lo": lo, "hi": hi}, f"{out_dir}/r{rank}.pt")
     dist.barrier()
