@@ -144,6 +144,9 @@ int sdp_ln_dwconv(const void *act, const float *gamma, const float *beta, const 
                   float eps, int dtype, void *stream);
 /* Same, with the token statistics supplied by the producer GEMM (stats layout as above; row index =
  * b * S + R + t) instead of being recomputed from `act`.  stats == NULL behaves like sdp_ln_dwconv. */
+/* 1 if supplying row statistics to sdp_ln_dwconv_stats selects the tensor-core kernel for this shape (the
+ * caller then runs sdp_row_stats first when no producer GEMM emitted them). */
+int sdp_ln_dwconv_wants_stats(int Gh, int Gw, int C, int k, int R, int dtype);
 int sdp_ln_dwconv_stats(const void *act, const float *stats, int parts, const float *gamma, const float *beta,
                         const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int k,
                         int R, float eps, int dtype, void *stream);
@@ -237,7 +240,7 @@ typedef struct {                 /* caller-allocated device workspaces */
   void *im2col;   /* [B*T, Kp] */
   void *pooled;   /* [B, C] */
   void *head_h;   /* [B, Kc] */
-  float *stats;   /* [B*S, sdp_gemm_stats_parts(C), 2] fp32 (ln_fold only) */
+  float *stats;   /* [B*S, max(1, sdp_gemm_stats_parts(C)), 2] fp32 row statistics (mixers; LN folding) */
 } sdp_workspace;
 
 /* x: NCHW [B,3,H,W] in x_dtype; logits: fp32 [B, classes]. */

@@ -82,6 +82,7 @@ SYMBOLS = {
     "sdp_gemm_headnorm_ok": (c_int, [c_int, c_int, c_int]),
     "sdp_gemm_stats_parts": (c_int, [c_int, c_int]),
     "sdp_row_stats": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "sdp_ln_dwconv_wants_stats": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "sdp_ln_dwconv_stats": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "sdp_im2col_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_fill_registers": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -357,6 +357,204 @@ static int launch_dw_bf16(const void *act, const float *stats, int parts, const 
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tensor-core depthwise conv (bf16, grids up to 16 x 16, k in {3,5,7}).
+//
+// For one channel the k x k 'same' conv of the zero-haloed G x G plane P is a sum over tap rows of small
+// matrix products:   Out[y, xo] = sum_dy  P[y + dy, :] . Toe_dy[:, xo],   Toe_dy[xi, xo] = w[dy][xi - xo]
+// (a banded Toeplitz matrix of the row's taps).  With M = y (<= 16), N = xo (two n8 tiles), K = xi (two k16
+// steps, of which only three (k-step, n-tile) bands are non-zero) that is 3 mma.sync.m16n8k16 per tap row,
+// 21 per channel and image for k = 7, against 12544 scalar FMAs: the kernel becomes bandwidth-bound.
+//
+// A CTA owns a 16-channel slab (32 B of every token row) for a strided set of images.  Each of its 16 warps
+// owns one channel and keeps that channel's Toeplitz B fragments in registers for all its images.  Per image:
+// thread-per-token staging (two 128-bit loads, LayerNorm with the supplied row statistics, scatter into 16
+// channel planes), one ldmatrix + MMA pass per warp, and a thread-per-token gather of the 16 results into two
+// 128-bit stores.  Statistics come as (sum, sumsq) column parts (sdp_row_stats or a producer GEMM).
+// ---------------------------------------------------------------------------------------
+constexpr int DWT_THREADS = 512;
+constexpr int DWT_CH = 16;                // channels per CTA = warps per CTA
+constexpr int DWT_PITCH = 40;             // bf16 per plane row: 32 used + 8 pad (80 B: conflict-free ldmatrix)
+
+__device__ __forceinline__ void dwt_mma(float *c, const uint32_t *a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void dwt_ldmatrix_x4(uint32_t addr, uint32_t *r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+template <int KS>
+__global__ void __launch_bounds__(DWT_THREADS, 1)
+ln_dwconv_tc_kernel(const bf16 *__restrict__ act, const float *__restrict__ stats, int parts,
+                    const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ wdw,
+                    const float *__restrict__ bdw, bf16 *__restrict__ out, int B, int Gh, int Gw, int C, int R,
+                    float eps) {
+  constexpr int lo = (KS - 1) / 2;
+  constexpr int ROWS = 16 + KS - 1;                  // plane rows an m16 tile can touch
+  constexpr int PLANE = ROWS * DWT_PITCH;            // bf16 elements per channel plane
+  extern __shared__ __align__(16) uint8_t dwt_smem[];
+  bf16 *planes = reinterpret_cast<bf16 *>(dwt_smem);                       // [16][ROWS][PITCH], zero halo
+  const int Tn = Gh * Gw, S = R + Tn;
+  const int OPL = (Tn + 7) & ~7;                                           // out-plane pitch (bf16)
+  bf16 *oplanes = planes + DWT_CH * PLANE;                                 // [16][OPL]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = blockIdx.x * DWT_CH;
+  const int g = lane >> 2, q = lane & 3;
+
+  for (int i = tid; i < DWT_CH * PLANE / 2; i += DWT_THREADS) reinterpret_cast<uint32_t *>(planes)[i] = 0u;
+
+  // ---- this warp's channel: Toeplitz B fragments of every tap row, kept in registers ----
+  // bands (k-step, n-tile) = (0,0) (0,1) (1,1); B[k][n] = w[dy][base + k - n], base = 16*ks - 8*nt
+  uint32_t bf[KS][3][2];
+  float bias = 0.0f;
+  {
+    const int c = c0 + warp;
+    const int delta = 2 * q - g;
+    auto tap = [&](int dy, int i) { return (i >= 0 && i < KS) ? __ldg(wdw + (long long)(dy * KS + i) * C + c) : 0.0f; };
+#pragma unroll
+    for (int dy = 0; dy < KS; ++dy) {
+#pragma unroll
+      for (int band = 0; band < 3; ++band) {
+        const int base = (band == 0 ? 0 : band == 1 ? -8 : 8) + delta;
+        bf[dy][band][0] = pack_bf16x2(tap(dy, base), tap(dy, base + 1));
+        bf[dy][band][1] = pack_bf16x2(tap(dy, base + 8), tap(dy, base + 9));
+      }
+    }
+    if (bdw) bias = __ldg(bdw + c);
+  }
+  // ---- staging threads (one per token): LayerNorm affine of the slab's 16 channels ----
+  float gm[DWT_CH], bt[DWT_CH];
+#pragma unroll
+  for (int j = 0; j < DWT_CH; ++j) { gm[j] = __ldg(gamma + c0 + j); bt[j] = __ldg(beta + c0 + j); }
+  const bool tok = tid < Tn;
+  const int ty = tok ? tid / Gw : 0, tx = tok ? tid % Gw : 0;
+  bf16 *my_cell = planes + (ty + lo) * DWT_PITCH + (tx + lo);              // + j * PLANE per channel
+  const uint32_t plane_addr = static_cast<uint32_t>(__cvta_generic_to_shared(planes)) + (uint32_t)warp * PLANE * 2;
+  // ldmatrix row addresses of the 16 x 16 A tile: lanes 0-7 rows 0-7 / cols 0-7, 8-15 rows 8-15, 16-31 cols 8-15
+  const uint32_t a_lane = plane_addr + (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * DWT_PITCH + (lane >> 4) * 8) * 2);
+  __syncthreads();
+
+  uint4 raw[2] = {};
+  int img = blockIdx.y;
+  auto load_raw = [&](int im) {
+    if (tok && im < B) {
+      const uint4 *p = reinterpret_cast<const uint4 *>(act + ((long long)im * S + R + tid) * C + c0);
+      raw[0] = __ldg(p);
+      raw[1] = __ldg(p + 1);
+    }
+  };
+  load_raw(img);
+  for (; img < B; img += gridDim.y) {
+    // ---- stage: normalise this token's 16 channels and scatter them into the channel planes ----
+    if (tok) {
+      const float *sp = stats + ((long long)img * S + R + tid) * parts * 2;
+      float s1 = 0.0f, s2 = 0.0f;
+      for (int p = 0; p < parts; ++p) {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(sp + 2 * p));
+        s1 += v.x;
+        s2 += v.y;
+      }
+      const float mean = s1 / (float)C;
+      const float rstd = rsqrtf(fmaxf(s2 / (float)C - mean * mean, 0.0f) + eps);
+      const uint32_t w8[8] = {raw[0].x, raw[0].y, raw[0].z, raw[0].w, raw[1].x, raw[1].y, raw[1].z, raw[1].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = (__uint_as_float(w8[j] << 16) - mean) * rstd, b2 = (__uint_as_float(w8[j] & 0xffff0000u) - mean) * rstd;
+        my_cell[(2 * j) * PLANE] = __float2bfloat16_rn(fmaf(a, gm[2 * j], bt[2 * j]));
+        my_cell[(2 * j + 1) * PLANE] = __float2bfloat16_rn(fmaf(b2, gm[2 * j + 1], bt[2 * j + 1]));
+      }
+    }
+    load_raw(img + gridDim.y);                       // next image's rows fly while this one is computed
+    __syncthreads();
+    // ---- this warp's channel: 3 MMAs per tap row ----
+    float acc[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[n][j] = bias;
+#pragma unroll
+    for (int dy = 0; dy < KS; ++dy) {
+      uint32_t a0[4], a1[4];
+      dwt_ldmatrix_x4(a_lane + dy * DWT_PITCH * 2, a0);            // plane cols 0..15
+      dwt_ldmatrix_x4(a_lane + dy * DWT_PITCH * 2 + 32, a1);       // plane cols 16..31
+      dwt_mma(acc[0], a0, bf[dy][0][0], bf[dy][0][1]);
+      dwt_mma(acc[1], a0, bf[dy][1][0], bf[dy][1][1]);
+      dwt_mma(acc[1], a1, bf[dy][2][0], bf[dy][2][1]);
+    }
+    // C fragment: (y = g, xo = 8n + 2q, +1) and (y = g + 8, same xo) -> this channel's out plane
+    {
+      bf16 *op = oplanes + warp * OPL;
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int xo = 8 * n + 2 * q;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int y = g + 8 * hh;
+          if (y < Gh) {
+            if (xo < Gw) op[y * Gw + xo] = __float2bfloat16_rn(acc[n][2 * hh]);
+            if (xo + 1 < Gw) op[y * Gw + xo + 1] = __float2bfloat16_rn(acc[n][2 * hh + 1]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- gather the 16 channels of this token and store 32 contiguous bytes ----
+    if (tok) {
+      uint32_t o8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t lo16 = *reinterpret_cast<const uint16_t *>(oplanes + (2 * j) * OPL + tid);
+        const uint32_t hi16 = *reinterpret_cast<const uint16_t *>(oplanes + (2 * j + 1) * OPL + tid);
+        o8[j] = lo16 | (hi16 << 16);
+      }
+      uint4 *dst = reinterpret_cast<uint4 *>(out + ((long long)img * S + R + tid) * C + c0);
+      dst[0] = make_uint4(o8[0], o8[1], o8[2], o8[3]);
+      dst[1] = make_uint4(o8[4], o8[5], o8[6], o8[7]);
+    }
+    // register rows of the output: zeros (written by the slab's first 16 * R / 8 threads)
+    if (tid < R * 2) {
+      uint4 *dst = reinterpret_cast<uint4 *>(out + ((long long)img * S + (tid >> 1)) * C + c0) + (tid & 1);
+      *dst = make_uint4(0, 0, 0, 0);
+    }
+    // no barrier needed here: the next iteration's staging only writes `planes`, whose readers finished
+    // before the barrier above, and its MMA phase (which rewrites `oplanes`) sits behind the next barrier
+  }
+}
+
+template <int KS>
+static int launch_dw_tc(const void *act, const float *stats, int parts, const float *gamma, const float *beta,
+                        const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int R, float eps,
+                        cudaStream_t st) {
+  const int Tn = Gh * Gw;
+  const size_t smem = (size_t)(DWT_CH * (16 + KS - 1) * DWT_PITCH + DWT_CH * ((Tn + 7) & ~7)) * sizeof(bf16);
+  auto kern = ln_dwconv_tc_kernel<KS>;
+  static bool configured = false;
+  if (!configured) {
+    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int slabs = C / DWT_CH;
+  int groups = sms / slabs;                         // one resident CTA per SM (128 registers x 512 threads)
+  groups = groups < 1 ? 1 : (groups > B ? B : groups);
+  dim3 grid(slabs, groups);
+  kern<<<grid, DWT_THREADS, smem, st>>>((const bf16 *)act, stats, parts, gamma, beta, wdw, bdw, (bf16 *)out, B, Gh, Gw, C,
+                                        R, eps);
+  SDP_LAUNCH_OK();
+  return 0;
+}
+
 template <typename T, int KS>
 static int launch_dw(const void *act, const float *gamma, const float *beta, const float *wdw, const float *bdw,
                      void *out, int B, int Gh, int Gw, int C, int k, int R, float eps, cudaStream_t st) {
@@ -392,6 +590,12 @@ static int dispatch_dw(const void *act, const float *gamma, const float *beta, c
 
 using namespace sdp;
 
+extern "C" int sdp_ln_dwconv_wants_stats(int Gh, int Gw, int C, int k, int R, int dtype) {
+  return dtype == SDP_BF16 && (k == 3 || k == 5 || k == 7) && Gh <= 16 && Gw <= 16 && Gh * Gw <= DWT_THREADS &&
+                 C % DWT_CH == 0 && 2 * R <= DWT_THREADS
+             ? 1 : 0;
+}
+
 extern "C" int sdp_ln_dwconv(const void *act, const float *gamma, const float *beta, const float *wdw,
                              const float *bdw, void *out, int B, int Gh, int Gw, int C, int k, int R, float eps,
                              int dtype, void *stream) {
@@ -412,6 +616,11 @@ extern "C" int sdp_ln_dwconv_stats(const void *act, const float *stats, int part
                       (reinterpret_cast<uintptr_t>(out) & 3) == 0 && (reinterpret_cast<uintptr_t>(wdw) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(gamma) & 7) == 0 && (reinterpret_cast<uintptr_t>(beta) & 7) == 0 &&
                       (bdw == nullptr || (reinterpret_cast<uintptr_t>(bdw) & 7) == 0);
+    const bool tc = fast && stats != nullptr && sdp_ln_dwconv_wants_stats(Gh, Gw, C, k, R, dtype) &&
+                    (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (tc && k == 7) return launch_dw_tc<7>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+    if (tc && k == 5) return launch_dw_tc<5>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+    if (tc && k == 3) return launch_dw_tc<3>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
     int rc = -1;
     if (fast && k == 7) rc = launch_dw_bf16<7>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
     if (fast && k == 5) rc = launch_dw_bf16<5>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);

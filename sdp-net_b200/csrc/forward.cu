@@ -110,8 +110,16 @@ int mixer(const Ctx &c, const sdp_mixer_weights &w) {
   const sdp_model_desc &m = *c.m;
   const int C = m.C, M = c.B * c.S, dt = m.dtype;
   const bool fold = m.ln_fold != 0;
-  if (int rc = sdp_ln_dwconv_stats(c.ws->act, fold ? c.ws->stats : nullptr, c.parts, w.ln1_g, w.ln1_b, w.w_dw, w.b_dw,
-                                   c.ws->norm, c.B, c.Gh, c.Gw, C, m.conv_k, c.R, 1e-6f, dt, c.st)) return rc;
+  const float *dw_stats = fold ? c.ws->stats : nullptr;
+  int dw_parts = c.parts;
+  if (!fold && c.ws->stats != nullptr && sdp_ln_dwconv_wants_stats(c.Gh, c.Gw, C, m.conv_k, c.R, dt)) {
+    // token (sum, sumsq) for the tensor-core depthwise kernel
+    if (int rc = sdp_row_stats(c.ws->act, C, c.ws->stats, 1, M, C, dt, c.st)) return rc;
+    dw_stats = c.ws->stats;
+    dw_parts = 1;
+  }
+  if (int rc = sdp_ln_dwconv_stats(c.ws->act, dw_stats, dw_parts, w.ln1_g, w.ln1_b, w.w_dw, w.b_dw, c.ws->norm, c.B, c.Gh,
+                                   c.Gw, C, m.conv_k, c.R, 1e-6f, dt, c.st)) return rc;
   if (int rc = gemm(c, c.ws->norm, C, w.w_pw, C, w.b_pw, M, C, C, m.act, c.ws->act, c.ws->act, C, dt, true, nullptr, fold)) return rc;
   const void *xin = c.ws->act;
   if (!fold) {

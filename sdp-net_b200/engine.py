@@ -257,8 +257,11 @@ class Buffers:
         self.im2col = e(B * T, Kp)
         self.pooled = e(B, C_)
         self.head_h = torch.zeros(B, Kc, dtype=dt, device=dev)
-        parts = ops.gemm_stats_parts(C_, dt) if getattr(pw, "ln_fold", False) else 0
-        self.stats = torch.zeros(B * S, parts, 2, dtype=torch.float32, device=dev) if parts else None
+        # row statistics (sum, sumsq): one part from sdp_row_stats for the tensor-core depthwise conv, or the
+        # producer GEMMs' column parts when the LayerNorms are folded
+        self.fold = bool(getattr(pw, "ln_fold", False))
+        parts = ops.gemm_stats_parts(C_, dt) if self.fold else 1
+        self.stats = torch.zeros(B * S, parts, 2, dtype=torch.float32, device=dev) if dt == torch.bfloat16 else None
         self.logits = torch.empty(B, classes, dtype=torch.float32, device=dev)
 
     def nbytes(self) -> int:
@@ -273,7 +276,7 @@ def run_encoder(pw: Packer, w: dict, bufs: Buffers, act_name: Optional[str] = No
     mult = w["w_ff1"].shape[0]
     a2, n2 = bufs.act.view(M, C_), bufs.norm.view(M, C_)
     hid = bufs.hidden.view(-1)[: M * mult].view(M, mult)
-    fold = w["s_qkv"] is not None and bufs.stats is not None
+    fold = w["s_qkv"] is not None and bufs.fold
     st = bufs.stats if fold else None
     d = C_ // pw.n_head
     hn = None
@@ -305,9 +308,13 @@ def run_mixer(pw: Packer, w: dict, bufs: Buffers, Gh: int, Gw: int, act_name: Op
     a2, n2 = bufs.act.view(M, C_), bufs.norm.view(M, C_)
     hid = bufs.hidden.view(-1)[: M * 4 * C_].view(M, 4 * C_)
     pr = (S, R) if R > 0 else (0, 0)
-    fold = w["s_mlp1"] is not None and bufs.stats is not None
+    fold = w["s_mlp1"] is not None and bufs.fold
     st = bufs.stats if fold else None
-    ops.ln_dwconv(bufs.act, w["ln1_g"], w["ln1_b"], w["w_dw"], w["b_dw"], bufs.norm, Gh, Gw, R, 1e-6, stats=st)
+    dw_stats = st
+    if not fold and bufs.stats is not None and ops.ln_dwconv_wants_stats(Gh, Gw, C_, w["conv_k"], R, pw.dtype):
+        ops.row_stats(a2, bufs.stats)        # token (sum, sumsq) for the tensor-core depthwise kernel
+        dw_stats = bufs.stats
+    ops.ln_dwconv(bufs.act, w["ln1_g"], w["ln1_b"], w["w_dw"], w["b_dw"], bufs.norm, Gh, Gw, R, 1e-6, stats=dw_stats)
     ops.gemm(n2, w["w_pw"], a2, bias=w["b_pw"], act=act_name, residual=a2, pass_rows=pr, stats_out=st)
     xin = a2
     if not fold:
@@ -429,7 +436,7 @@ class Engine:
         ops.gemm(bufs.im2col, pw.w_patch, bufs.act.view(B * S, C_), residual=pw.pos_table(Gh, Gw), res_first=True,
                  res_mod=T, act=pw.embed_act, seq_remap=(T, S, R), K=3 * p * p)
         ops.fill_registers(bufs.act, pw.reg_table(R))
-        if bufs.stats is not None:
+        if bufs.fold:
             ops.row_stats(bufs.act, bufs.stats)
         note("embed")
         cbn = int(cfg["conv_block_num"])

@@ -154,6 +154,10 @@ def ln_dwconv(act: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, wdw: t
     return out
 
 
+def ln_dwconv_wants_stats(Gh: int, Gw: int, Cc: int, k: int, R: int, dtype: torch.dtype) -> bool:
+    return bool(L.lib().sdp_ln_dwconv_wants_stats(Gh, Gw, Cc, k, R, _DT[dtype]))
+
+
 def attention(qkv: torch.Tensor, out: torch.Tensor, n_head: int, qn_w=None, qn_b=None, kn_w=None, kn_b=None,
               eps: float = 1e-5) -> torch.Tensor:
     B, S, C3 = qkv.shape
