@@ -144,8 +144,8 @@ int sdp_ln_dwconv(const void *act, const float *gamma, const float *beta, const 
                   float eps, int dtype, void *stream);
 /* Same, with the token statistics supplied by the producer GEMM (stats layout as above; row index =
  * b * S + R + t) instead of being recomputed from `act`.  stats == NULL behaves like sdp_ln_dwconv. */
-/* 1 if supplying row statistics to sdp_ln_dwconv_stats selects the tensor-core kernel for this shape (the
- * caller then runs sdp_row_stats first when no producer GEMM emitted them). */
+/* 1 if the kernel chosen for this shape REQUIRES caller-supplied row statistics (currently never: every
+ * kernel computes them itself when stats == NULL). */
 int sdp_ln_dwconv_wants_stats(int Gh, int Gw, int C, int k, int R, int dtype);
 int sdp_ln_dwconv_stats(const void *act, const float *stats, int parts, const float *gamma, const float *beta,
                         const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int k,

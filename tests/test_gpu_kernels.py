@@ -324,7 +324,7 @@ def dw_ref(act, R, Gh, Gw, gamma, beta, wdw, bdw, eps=1e-6):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("Gh,Gw,C,k,R,bias", [(16, 16, 768, 7, 5, False), (14, 14, 96, 7, 4, True), (8, 8, 32, 5, 1, True),
                                               (4, 6, 40, 3, 2, False), (5, 3, 16, 9, 3, True), (2, 2, 128, 7, 5, False)])
-def test_ln_dwconv(sdp, dtype, Gh, Gw, C, k, R, bias):
+def test_ln_dwconv(sdp, dtype, Gh, Gw, C, k, R, bias, monkeypatch):
     B = 3
     act = (rnd(B, R + Gh * Gw, C, seed=40) * 2 + 0.3).to(dtype)
     gamma, beta = rnd(C, seed=41) * 0.3 + 1, rnd(C, seed=42) * 0.3
@@ -343,6 +343,13 @@ def test_ln_dwconv(sdp, dtype, Gh, Gw, C, k, R, bias):
         out2 = torch.full_like(act, float("nan"))
         sdp.ops.ln_dwconv(act, gamma, beta, wdw.reshape(C, k * k).t().contiguous(), bdw, out2, Gh, Gw, R, stats=stats)
         assert (out2.float() - ref).abs().max() < tol
+        # the experimental tensor-core (Toeplitz mma.sync) kernel, with and without supplied statistics
+        monkeypatch.setenv("SDP_DWCONV_TC", "1")
+        for st in (None, stats):
+            out3 = torch.full_like(act, float("nan"))
+            sdp.ops.ln_dwconv(act, gamma, beta, wdw.reshape(C, k * k).t().contiguous(), bdw, out3, Gh, Gw, R, stats=st)
+            assert (out3[:, :R] == 0).all()
+            assert (out3.float() - ref).abs().max() < tol
 
 
 # --------------------------------------------------------------------------------------------
