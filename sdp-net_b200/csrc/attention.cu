@@ -687,6 +687,16 @@ static int launch_attn_simt(const void *qkv, const float *qn_w, const float *qn_
   return 0;
 }
 
+int attention_tc5(const void *qkv, void *out, int B, int S, int h, int d, cudaStream_t st);   // attention_tc.cu
+
+static bool attn_tc5_enabled() {     // SDP_ATTN_TC=0 keeps the mma.sync kernels (A/B comparisons)
+  static const bool on = [] {
+    const char *e = getenv("SDP_ATTN_TC");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 }  // namespace sdp
 
 using namespace sdp;
@@ -702,6 +712,10 @@ extern "C" int sdp_attention(const void *qkv, const float *qn_w, const float *qn
   if (dtype == SDP_BF16) {
     const bool aligned = (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && ((long long)h * d) % 8 == 0;
     int rc = -1;
+    if (aligned && qn_w == nullptr && attn_tc5_enabled()) {
+      rc = attention_tc5(qkv, out, B, S, h, d, st);      // tcgen05 path: d in {64, 96, 128}, S <= 288
+      if (rc >= 0) return rc;
+    }
     if (aligned && qn_w == nullptr) {
       switch (d) {
         case 16: rc = launch_attn_mma2<16, 1, 16>(qkv, out, B, S, h, st); break;

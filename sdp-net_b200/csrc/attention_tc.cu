@@ -1,0 +1,520 @@
+// Attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA) for the short SdP-Net sequence.
+// Reference: F.scaled_dot_product_attention at layers.py:289-291 (q, k already LayerNorm-ed by the QKV
+// GEMM epilogue, layers.py:286).
+//
+// One CTA per (image, head).  The whole K and V of the sequence (<= 288 keys) sit in shared memory as
+// 64B-swizzled 32-column tiles loaded by TMA straight out of the [B*S, 3C] QKV buffer.  Per 128-query tile:
+//   S = Q K^T   tcgen05.mma, K-major A (Q) and B (K), fp32 scores in TMEM columns [0, KEYS)
+//   softmax     four warps, one thread per query row: tcgen05.ld the row, max, exp2, row sum; P (bf16) goes
+//               back to shared memory in the 64B-swizzled K-major layout the next MMA reads
+//   O = P V     tcgen05.mma, A = P (K-major), B = V read as an MN-major operand (V is [keys, d] in memory,
+//               i.e. d-contiguous: no transpose anywhere), fp32 O in TMEM columns [384, 384 + d)
+//   epilogue    tcgen05.ld O, scale by 1 / row sum, bf16, 16-byte stores into the token-major output
+// Warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2..9 = softmax / epilogue.
+// No online rescaling is needed: a full score row fits in TMEM.
+#include "tc5.cuh"
+
+namespace sdp {
+
+#ifdef AT_TRACE
+#define AT_T(tag) do { if (trace_on && lane == 0 && ntr < 56) { tr_tag[ntr] = tag; tr_t[ntr++] = clock64() - t_begin; } } while (0)
+#define AT_DUMP(who) do { if (trace_on && lane == 0) for (int i_ = 0; i_ < ntr; ++i_) printf("%s w%d %3d %lld\n", who, warp, tr_tag[i_], tr_t[i_]); } while (0)
+#else
+#define AT_T(tag)
+#define AT_DUMP(who)
+#endif
+
+constexpr int AT_MT = 128;          // query rows per tile
+constexpr int AT_THREADS = 320;        // TMA warp, MMA warp, 8 softmax warps
+constexpr int AT_O_COL = 288;       // first TMEM column of the O accumulator(s); scores use [0, 288)
+
+// 64B-swizzled tiles: rows of 64 bytes (32 bf16), groups of 8 rows = 512 bytes.
+// K-major operand descriptor (A, and B = K): layout type 4 (SWIZZLE_64B), SBO = 512.
+__device__ __forceinline__ uint64_t at_desc_kmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+// MN-major B operand (V): 32 d-columns contiguous per 64-byte row, 8 key rows per 512-byte group (SBO), the
+// next 32 d-columns `lbo` bytes further (LBO).
+__device__ __forceinline__ uint64_t at_desc_mnmajor(uint32_t saddr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+
+// Descriptor words.  Low: [0,14) address >> 4, [16,30) leading byte offset >> 4.  High: [0,14) stride byte offset >> 4
+// (one 8-row group), bit 14 = descriptor version 1, [29,32) swizzle mode (2 = 128B, 4 = 64B).
+constexpr uint32_t AT_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t AT_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint32_t at_lo(uint32_t saddr, uint32_t lbo) {
+  return ((saddr & 0x3FFFF) >> 4) | (((lbo >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ void at_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t at_idesc(int m, int n, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// One chunk of scores: 32 columns (16 for a tail) of this thread's TMEM lane.
+__device__ __forceinline__ void at_ld_chunk(uint32_t taddr, int n, float (&v)[32]) {
+  if (n >= 32) tmem_ld32(taddr, v);
+  else tmem_ld16(taddr, v);
+}
+// Columns that were not loaded (a 16-wide tail) or lie past the end of the sequence become -inf: they lose the
+// maximum and exponentiate to 0.  Only the last chunk of a row needs it; the empty asm keeps the block a real
+// (warp-uniform) branch instead of 32 predicated selects on every chunk.
+__device__ __forceinline__ void at_mask_chunk(float (&v)[32], int lim) {
+  if (lim < 32) {
+    asm volatile("" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = j < lim ? v[j] : -INFINITY;
+  }
+}
+__device__ __forceinline__ void at_max_chunk(float (&v)[32], int lim, float (&mx)[4]) {
+  at_mask_chunk(v, lim);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], v[j]);
+}
+__device__ __forceinline__ void at_exp_chunk(float (&v)[32], int lim, float scale_log2, float nm, float (&sum)[4],
+                                             uint32_t prow, uint32_t ch0, uint32_t sw) {
+  at_mask_chunk(v, lim);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    v[j] = fast_ex2(fmaf(v[j], scale_log2, nm));
+    sum[j & 3] += v[j];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {                               // 64 B of the row's P atom at swizzled 16-byte chunks
+    const uint32_t p0 = pack_bf16x2(v[8 * c], v[8 * c + 1]), p1 = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+    const uint32_t p2 = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), p3 = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (((ch0 + c) ^ sw) << 4)), "r"(p0), "r"(p1), "r"(p2),
+                 "r"(p3)
+                 : "memory");
+  }
+}
+
+// Score columns are split in two key halves X = [0, KA) and Y = [KA, KEYS) that the tensor core and the
+// softmax warps hand back and forth (a full second score tile does not fit next to O in the 512 TMEM columns):
+//   MMA    : S.X(t+1) is issued as soon as pass 2 has drained X(t), S.Y(t+1) after Y(t); P V(t) runs in the
+//            same two instalments, so the tensor core works underneath the exponentials
+//   softmax: max over X, [O(t-1) -> global], max over Y, exp/sum/P over X, exp/sum/P over Y
+struct AtBars {
+  uint32_t kv_full, q_full, q_free, sx_full, sy_full, px_full, py_full, o_full, o_free, v_full;   // o_*: two barriers each
+};
+
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ32,
+                     const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmKV,
+                     const __grid_constant__ CUtensorMap tmO,
+                     bf16 *__restrict__ out, int S, int h, int KEYS, int kv_box_rows, float scale_log2) {
+  constexpr int NA = D / 32;                   // 32-column (64B-swizzled) atoms of V along the head dim
+  // Q, K and P are K-major MMA operands read in 32-byte k-slices: only the 128B swizzle spreads the eight rows of
+  // a slice over all banks (64B-swizzled rows collide two by two), so they use 64-column atoms wherever 64
+  // columns are left and a 32-column atom for the rest (d = 96: one of each).
+  constexpr int N128 = D / 64, N64 = (D % 64) / 32;
+  constexpr int OB = (AT_O_COL + 2 * D <= 512) ? 2 : 1;       // O accumulators in TMEM
+  extern __shared__ uint8_t at_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const int NP128 = KEYS / 64, NP64 = (KEYS % 64 + 31) / 32;  // P: 64-key atoms, then 32-key atoms
+  int KA = (KEYS / 2) & ~63;                   // keys in the X half: whole P atoms (64 keys, else 32, else all)
+  if (KA == 0) KA = (KEYS / 2) & ~31;
+  if (KA == 0) KA = KEYS;
+  const int KB = KEYS - KA;                    // keys in the Y half (may be 0)
+  const uint32_t q_off = 0;                                   // [N128][128 rows][128 B] [N64][128 rows][64 B]
+  const uint32_t q64_off = q_off + N128 * AT_MT * 128;
+  const uint32_t k_off = q_off + NA * AT_MT * 64;             // [N128][KEYS][128 B] [N64][KEYS][64 B]
+  const uint32_t k64_off = k_off + N128 * KEYS * 128;
+  const uint32_t v_off = k_off + NA * KEYS * 64;              // [NA][KEYS][64 B]
+  const uint32_t p_off = v_off + NA * KEYS * 64;              // [NP128][128 rows][128 B] [NP64][128 rows][64 B]
+  const uint32_t p64_off = p_off + NP128 * AT_MT * 128;
+  const uint32_t bar_off = p64_off + NP64 * AT_MT * 64;
+  const uint32_t bar = sbase + bar_off;
+  AtBars B;
+  B.kv_full = bar; B.q_full = bar + 8; B.q_free = bar + 16; B.sx_full = bar + 24; B.sy_full = bar + 32;
+  B.px_full = bar + 40; B.py_full = bar + 48; B.o_full = bar + 56; B.o_free = bar + 72; B.v_full = bar + 88;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + bar_off + 96);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = h * D;
+  const int b = blockIdx.x / h, head = blockIdx.x % h;
+  const int tiles = (S + AT_MT - 1) / AT_MT;
+#ifdef AT_TRACE
+  const bool trace_on = blockIdx.x == 4000;
+  const long long t_begin = clock64();
+  int ntr = 0, tr_tag[56];
+  long long tr_t[56];
+#endif
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+    mbar_init(B.kv_full, 1);
+    mbar_init(B.v_full, 1);
+    mbar_init(B.q_full, 1);
+    mbar_init(B.q_free, 1);
+    mbar_init(B.sx_full, 1);
+    mbar_init(B.sy_full, 1);
+    mbar_init(B.px_full, 8);
+    mbar_init(B.py_full, 8);
+    mbar_init(B.o_full, 1);
+    mbar_init(B.o_full + 8, 1);
+    mbar_init(B.o_free, 8);
+    mbar_init(B.o_free + 8, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t *>(tmem_slot))),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int row0 = b * S;
+      mbar_expect_tx(B.kv_full, NA * KEYS * 64);
+      for (int r = 0; r < KEYS; r += kv_box_rows) {
+        for (int a = 0; a < N128; ++a)
+          tma_load_2d(sbase + k_off + (a * KEYS + r) * 128, &tmK, B.kv_full, C + head * D + 64 * a, row0 + r);
+        if (N64) tma_load_2d(sbase + k64_off + r * 64, &tmKV, B.kv_full, C + head * D + 64 * N128, row0 + r);
+      }
+      mbar_expect_tx(B.q_full, NA * AT_MT * 64);
+      auto load_q = [&](int row) {
+        for (int a = 0; a < N128; ++a) tma_load_2d(sbase + q_off + a * AT_MT * 128, &tmQ, B.q_full, head * D + 64 * a, row);
+        if (N64) tma_load_2d(sbase + q64_off, &tmQ32, B.q_full, head * D + 64 * N128, row);
+      };
+      load_q(row0);
+      mbar_expect_tx(B.v_full, NA * KEYS * 64);
+      for (int a = 0; a < NA; ++a)
+        for (int r = 0; r < KEYS; r += kv_box_rows)
+          tma_load_2d(sbase + v_off + (a * KEYS + r) * 64, &tmKV, B.v_full, 2 * C + head * D + 32 * a, row0 + r);
+      AT_T(1);
+      for (int t = 1; t < tiles; ++t) {
+        mbar_wait(B.q_free, (t - 1) & 1);
+        AT_T(2);                     // both score halves of tile t-1 are in TMEM
+        mbar_expect_tx(B.q_full, NA * AT_MT * 64);
+        load_q(row0 + t * AT_MT);
+      }
+      AT_DUMP("tma");
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc_x = at_idesc(AT_MT, KA, 0), idesc_y = at_idesc(AT_MT, KB > 0 ? KB : 16, 0);
+      const uint32_t idesc_o = at_idesc(AT_MT, D, 1);
+      // The MMAs here are short (48-72 tensor-core cycles), so the issue path is kept to a couple of integer adds
+      // per instruction: descriptor low words (address >> 4 | LBO) are prepared once, high words are constants.
+      const uint32_t q128_lo = at_lo(sbase + q_off, 16), q64_lo = at_lo(sbase + q64_off, 16);
+      const uint32_t k128_lo = at_lo(sbase + k_off, 16), k64_lo = at_lo(sbase + k64_off, 16);
+      const uint32_t p128_lo = at_lo(sbase + p_off, 16), p64_lo = at_lo(sbase + p64_off, 16);
+      const uint32_t v_lo = at_lo(sbase + v_off, KEYS * 64);
+      auto issue_qk = [&](int key0, uint32_t idesc) {         // scores of keys [key0, key0 + N) -> TMEM column key0
+        const uint32_t kl128 = k128_lo + key0 * (128 >> 4), kl64 = k64_lo + key0 * (64 >> 4);
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          if (ks < 4 * N128)                                    // 16 columns of a 64-column atom
+            at_mma(tmem + key0, q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
+                   kl128 + (ks >> 2) * (KEYS * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc, ks != 0);
+          else                                                  // ... of the 32-column atom
+            at_mma(tmem + key0, q64_lo + (ks & 1) * 2, AT_HI_SW64, kl64 + (ks & 1) * 2, AT_HI_SW64, idesc, ks != 0);
+        }
+      };
+      auto issue_pv = [&](int j0, int j1, uint32_t o_col) {   // 16-key steps [j0, j1) of O += P V
+        const int jm = j1 < 4 * NP128 ? j1 : 4 * NP128;         // steps below jm read P from 64-key atoms
+#pragma unroll 4
+        for (int j = j0; j < jm; ++j)
+          at_mma(tmem + o_col, p128_lo + ((j >> 2) << 10) + ((j & 3) << 1), AT_HI_SW128, v_lo + j * (16 * 64 >> 4),
+                 AT_HI_SW64, idesc_o, j != 0);
+        for (int j = j0 > jm ? j0 : jm; j < j1; ++j) {
+          const int j2 = j - 4 * NP128;
+          at_mma(tmem + o_col, p64_lo + ((j2 >> 1) << 9) + ((j2 & 1) << 1), AT_HI_SW64, v_lo + j * (16 * 64 >> 4),
+                 AT_HI_SW64, idesc_o, j != 0);
+        }
+      };
+      AT_T(10);
+      mbar_wait(B.kv_full, 0);
+      AT_T(11);
+      mbar_wait(B.q_full, 0);
+      AT_T(12);
+      tc_fence_after();
+      issue_qk(0, idesc_x);
+      tc_commit(B.sx_full);
+      if (KB > 0) {
+        issue_qk(KA, idesc_y);
+        tc_commit(B.sy_full);
+      }
+      tc_commit(B.q_free);
+      for (int t = 0; t < tiles; ++t) {
+        const int ob = t % OB;
+        const uint32_t o_col = AT_O_COL + ob * D;
+        if (t >= OB) mbar_wait(B.o_free + 8 * ob, ((t / OB) - 1) & 1);    // O(t - OB) has been read out
+        if (t == 0) mbar_wait(B.v_full, 0);
+        AT_T(13);
+        mbar_wait(B.px_full, t & 1);                          // P.X(t) in shared memory, S.X(t) consumed
+        AT_T(14);
+        tc_fence_after();
+        issue_pv(0, KA / 16, o_col);
+        AT_T(17);
+        if (KB == 0) tc_commit(B.o_full + 8 * ob);
+        if (t + 1 < tiles) {
+          mbar_wait(B.q_full, (t + 1) & 1);
+          tc_fence_after();
+          issue_qk(0, idesc_x);
+          tc_commit(B.sx_full);
+          if (KB == 0) tc_commit(B.q_free);
+        }
+        if (KB > 0) {
+          AT_T(15);
+          mbar_wait(B.py_full, t & 1);
+          AT_T(16);
+          tc_fence_after();
+          issue_pv(KA / 16, KEYS / 16, o_col);
+          tc_commit(B.o_full + 8 * ob);
+          if (t + 1 < tiles) {
+            issue_qk(KA, idesc_y);
+            tc_commit(B.sy_full);
+            tc_commit(B.q_free);
+          }
+        }
+      }
+      AT_T(19);
+      AT_DUMP("mma");
+    }
+    __syncwarp();
+  } else {
+    // ================= softmax + epilogue =================
+    // Eight warps: TMEM lane quadrant = warp % 4 (a warp only reaches its own 32 lanes), so two warps share every
+    // query row; warp group g = 0/1 takes the first / second part of each key half and of the O columns.  The
+    // two partial maxima and sums of a row meet in shared memory across a 64-thread named barrier.
+    const int quad = warp & 3;
+    const int g = (warp - 2) >> 2;
+    const int r = quad * 32 + lane;                           // row inside the tile = TMEM lane
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    // P row of a 32-key chunk at key kk: address of the row in its atom, first 16-byte chunk, swizzle XOR
+    auto p_place = [&](int kk, uint32_t &prow, uint32_t &ch0, uint32_t &sw) {
+      if (kk < 64 * NP128) {
+        prow = sbase + p_off + (kk >> 6) * AT_MT * 128 + r * 128;
+        ch0 = (kk & 63) >> 3;
+        sw = r & 7;                                           // 128B swizzle: chunk ^ address bits [7:9]
+      } else {
+        prow = sbase + p64_off + ((kk - 64 * NP128) >> 5) * AT_MT * 64 + r * 64;
+        ch0 = 0;
+        sw = (r >> 1) & 3;                                    // 64B swizzle: chunk ^ address bits [7:8]
+      }
+    };
+    float *xch = reinterpret_cast<float *>(smem + bar_off + 128);     // [max|sum][tile parity][group][128 rows]
+    auto first_part = [](int n) { return n < 64 ? (n < 32 ? n : 32) : ((n / 2) & ~31); };
+    const int xa = first_part(KA), ya = first_part(KB);
+    const int xk0 = g ? xa : 0, xn = g ? KA - xa : xa;        // this group's keys of the X half
+    const int yk0 = KA + (g ? ya : 0), yn = g ? KB - ya : ya; // ... and of the Y half (up to 96 = three chunks)
+    // Output staging: when this warp's Y keys start on a 64-key P atom of their own, its 32 rows of that atom
+    // (4 KB nobody else touches) are free from the end of P V(t) until the warp's own pass 2 over Y(t + 1):
+    // O goes there and leaves as one TMA store instead of 16-byte stores to 32 different rows.
+    const bool stage_ok = (KA & 63) == 0 && ya == 64 && KB >= 128 && KA / 64 + 2 <= NP128;
+    const uint32_t stage = sbase + p_off + (KA / 64 + g) * AT_MT * 128 + quad * 32 * 128 + lane * (D / 2) * 2;
+
+    auto pass1 = [&](int key0, int nkeys, float m) {          // row maximum of this group's keys
+      float mx[4] = {m, m, m, m};
+#pragma unroll 1
+      for (int k = 0; k < nkeys; k += 32) {                   // the partner warp on this scheduler hides the latency
+        const int n = nkeys - k < 32 ? nkeys - k : 32, kk = key0 + k;
+        float v0[32];
+        at_ld_chunk(t_lane + kk, n, v0);
+        tmem_ld_wait();
+        at_max_chunk(v0, min(n, S - kk), mx);
+      }
+      return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    };
+    auto pass2 = [&](int key0, int nkeys, float nm) {         // p = 2^(s*scale - max*scale) -> P (bf16), row sum
+      float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      for (int k = 0; k < nkeys; k += 64) {
+        const int n = nkeys - k < 64 ? nkeys - k : 64, kk = key0 + k;
+        float v0[32], v1[32];
+        at_ld_chunk(t_lane + kk, n, v0);
+        if (n > 32) at_ld_chunk(t_lane + kk + 32, n - 32, v1);
+        tmem_ld_wait();
+        uint32_t prow, ch0, sw;
+        p_place(kk, prow, ch0, sw);
+        at_exp_chunk(v0, min(n, S - kk), scale_log2, nm, sum, prow, ch0, sw);
+        if (n > 32) {
+          p_place(kk + 32, prow, ch0, sw);
+          at_exp_chunk(v1, min(n, S - kk) - 32, scale_log2, nm, sum, prow, ch0, sw);
+        }
+      }
+      return (sum[0] + sum[1]) + (sum[2] + sum[3]);
+    };
+    auto publish = [&](uint32_t barrier) {                    // P part visible to the tensor core, S part free
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(barrier);
+    };
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
+    auto epilogue = [&](int t) {                              // this group's half of O(t) / row sum -> bf16 -> global
+      constexpr int HALF = D / 2;
+      const int ob = t % OB;
+      const float *xs = xch + 512 + (t & 1) * 256;
+      const float inv = 1.0f / (xs[r] + xs[128 + r]);
+      const int row = t * AT_MT + r;
+      bf16 *orow = out + ((long long)b * S + row) * C + head * D + g * HALF;
+      const bool warp_live = t * AT_MT + quad * 32 < S;
+      if (warp_live) {
+        mbar_wait(B.o_full + 8 * ob, (t / OB) & 1);
+        tc_fence_after();
+        AT_T(40);
+      }
+      auto store8 = [&](const float *w, int c) {              // 8 columns -> 16 bytes
+        const uint32_t p0 = pack_bf16x2(w[0] * inv, w[1] * inv), p1 = pack_bf16x2(w[2] * inv, w[3] * inv);
+        const uint32_t p2 = pack_bf16x2(w[4] * inv, w[5] * inv), p3 = pack_bf16x2(w[6] * inv, w[7] * inv);
+        if (stage_ok) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + 2 * c), "r"(p0), "r"(p1), "r"(p2), "r"(p3)
+                       : "memory");
+        } else if (row < S) {
+          *reinterpret_cast<uint4 *>(orow + c) = make_uint4(p0, p1, p2, p3);
+        }
+      };
+      constexpr int REST = HALF - 32;                         // 0, 16 or 32 columns after the first 32
+      if (warp_live) {
+        float v[32];
+        tmem_ld32(t_lane + AT_O_COL + ob * D + g * HALF, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) store8(&v[8 * c], 8 * c);
+        if constexpr (REST > 0) {
+          if constexpr (REST == 32) tmem_ld32(t_lane + AT_O_COL + ob * D + g * HALF + 32, v);
+          else tmem_ld16(t_lane + AT_O_COL + ob * D + g * HALF + 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < REST / 8; ++c) store8(&v[8 * c], 32 + 8 * c);
+        }
+        tc_fence_before();
+        if (stage_ok) fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(B.o_free + 8 * ob);
+        if (warp_live && stage_ok) {                          // rows past the end of the image are clipped by the map
+          tma_store_3d(&tmO, stage, head * D + g * HALF, t * AT_MT + quad * 32, b);
+          bulk_commit();
+        }
+      }
+    };
+
+#pragma unroll 1
+    for (int t = 0; t <= tiles; ++t) {                        // iteration t: scores of tile t, output of tile t - 1
+      const bool live = t < tiles && t * AT_MT + quad * 32 < S;   // warps whose rows are all past the sequence idle
+      float *xm = xch + (t & 1) * 256, *xs = xch + 512 + (t & 1) * 256;
+      float m = -INFINITY;
+      if (t < tiles) {
+#pragma unroll 1
+        for (int hf = 0; hf < (KB > 0 ? 2 : 1); ++hf) {       // X then Y: the Y scores land while X is scanned
+          AT_T(20 + hf);
+          mbar_wait(hf ? B.sy_full : B.sx_full, t & 1);
+          tc_fence_after();
+          AT_T(22 + hf);
+          if (live) m = pass1(hf ? yk0 : xk0, hf ? yn : xn, m);
+          AT_T(24 + hf);
+        }
+        xm[g * 128 + r] = m;
+      }
+      pair_sync();                                            // partial maxima of tile t, partial sums of tile t - 1
+      AT_T(26);
+      if (t > 0) epilogue(t - 1);
+      AT_T(27);
+      if (t < tiles) {
+        m = fmaxf(m, xm[(g ^ 1) * 128 + r]);
+        const float nm = -m * scale_log2;
+        float sum = 0.0f;
+#pragma unroll 1
+        for (int hf = 0; hf < (KB > 0 ? 2 : 1); ++hf) {
+          if (hf && stage_ok) {                               // the staged O(t - 1) must have left shared memory
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+          }
+          if (live) sum += pass2(hf ? yk0 : xk0, hf ? yn : xn, nm);
+          publish(hf ? B.py_full : B.px_full);
+          AT_T(28 + hf);
+        }
+        xs[g * 128 + r] = sum;
+      }
+    }
+    if (stage_ok && lane == 0) bulk_wait_read<0>();          // shared memory outlives the last output store
+    if (warp == 4 || warp == 8) AT_DUMP("smx");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+template <int D>
+static int launch_attn_tc5(const void *qkv, void *out, int B, int S, int h, cudaStream_t st) {
+  const int C = h * D;
+  const int KEYS = (S + 15) & ~15;
+  const int nbox = (KEYS + 255) / 256;
+  if (KEYS > 288 || KEYS % nbox != 0 || (KEYS / nbox) % 8 != 0) return -1;
+  const int NA = D / 32, NKA = (KEYS + 31) / 32;
+  const size_t smem = (size_t)NA * AT_MT * 64 + 2 * (size_t)NA * KEYS * 64 + (size_t)NKA * AT_MT * 64 + 128 + 4096 + 1024;
+  if (smem > 227 * 1024) return -1;
+  CUtensorMap tq, tq32, tk, tkv;          // 64-column boxes are 128B-swizzled, 32-column boxes 64B-swizzled
+  if (int rc = make_tensor_map_bf16(qkv, (uint64_t)B * S, 3 * C, 3 * C, AT_MT, 64, &tq)) return rc;
+  if (int rc = make_tensor_map_bf16(qkv, (uint64_t)B * S, 3 * C, 3 * C, AT_MT, 32, &tq32)) return rc;
+  if (int rc = make_tensor_map_bf16(qkv, (uint64_t)B * S, 3 * C, 3 * C, KEYS / nbox, 64, &tk)) return rc;
+  if (int rc = make_tensor_map_bf16(qkv, (uint64_t)B * S, 3 * C, 3 * C, KEYS / nbox, 32, &tkv)) return rc;
+  CUtensorMap to;                          // [B][S][C] output, 32-row x D/2-column boxes
+  if (int rc = make_tensor_map_bf16_3d(out, B, S, C, 32, D / 2, &to)) return rc;
+  auto kern = attention_tc5_kernel<D>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
+  kern<<<B * h, AT_THREADS, smem, st>>>(tq, tq32, tk, tkv, to, (bf16 *)out, S, h, KEYS, KEYS / nbox, scale_log2);
+  SDP_LAUNCH_OK();
+  return 0;
+}
+
+// -1: shape not covered (the caller falls back to the mma.sync kernel)
+int attention_tc5(const void *qkv, void *out, int B, int S, int h, int d, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (h * d) % 8) return -1;
+  switch (d) {
+    case 64: return launch_attn_tc5<64>(qkv, out, B, S, h, st);
+    case 96: return launch_attn_tc5<96>(qkv, out, B, S, h, st);
+    case 128: return launch_attn_tc5<128>(qkv, out, B, S, h, st);
+    default: return -1;
+  }
+}
+
+}  // namespace sdp
