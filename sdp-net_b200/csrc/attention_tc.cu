@@ -118,7 +118,7 @@ __device__ __forceinline__ void at_exp_chunk(float (&v)[32], int lim, float scal
 //            same two instalments, so the tensor core works underneath the exponentials
 //   softmax: max over X, [O(t-1) -> global], max over Y, exp/sum/P over X, exp/sum/P over Y
 struct AtBars {
-  uint32_t kv_full, q_full, q_free, sx_full, sy_full, px_full, py_full, o_full, o_free, v_full;   // o_*: two barriers each
+  uint32_t kv_full, q_full, q_free, sx_full, sy_full, px_full, py_full, o_full, o_free, v_full, k1_full;   // o_*: two barriers each
 };
 
 template <int D>
@@ -152,8 +152,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t bar = sbase + bar_off;
   AtBars B;
   B.kv_full = bar; B.q_full = bar + 8; B.q_free = bar + 16; B.sx_full = bar + 24; B.sy_full = bar + 32;
-  B.px_full = bar + 40; B.py_full = bar + 48; B.o_full = bar + 56; B.o_free = bar + 72; B.v_full = bar + 88;
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + bar_off + 96);
+  B.px_full = bar + 40; B.py_full = bar + 48; B.o_full = bar + 56; B.o_free = bar + 72; B.v_full = bar + 88; B.k1_full = bar + 96;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + bar_off + 104);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = h * D;
@@ -172,6 +172,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
     mbar_init(B.kv_full, 1);
     mbar_init(B.v_full, 1);
+    mbar_init(B.k1_full, 1);
     mbar_init(B.q_full, 1);
     mbar_init(B.q_free, 1);
     mbar_init(B.sx_full, 1);
@@ -183,6 +184,23 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(B.o_free, 8);
     mbar_init(B.o_free + 8, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // The loads of this (image, head) start before the rest of the CTA is set up: Q and the first box of K rows
+    // (all the X scores need), then the remaining K rows, then V.
+    const int row0 = b * S;
+    mbar_expect_tx(B.q_full, NA * AT_MT * 64);
+    for (int a = 0; a < N128; ++a) tma_load_2d(sbase + q_off + a * AT_MT * 128, &tmQ, B.q_full, head * D + 64 * a, row0);
+    if (N64) tma_load_2d(sbase + q64_off, &tmQ32, B.q_full, head * D + 64 * N128, row0);
+    for (int r = 0; r < KEYS; r += kv_box_rows) {
+      const uint32_t kbar = r == 0 ? B.kv_full : B.k1_full;
+      mbar_expect_tx(kbar, NA * kv_box_rows * 64);
+      for (int a = 0; a < N128; ++a)
+        tma_load_2d(sbase + k_off + (a * KEYS + r) * 128, &tmK, kbar, C + head * D + 64 * a, row0 + r);
+      if (N64) tma_load_2d(sbase + k64_off + r * 64, &tmKV, kbar, C + head * D + 64 * N128, row0 + r);
+    }
+    mbar_expect_tx(B.v_full, NA * KEYS * 64);
+    for (int a = 0; a < NA; ++a)
+      for (int r = 0; r < KEYS; r += kv_box_rows)
+        tma_load_2d(sbase + v_off + (a * KEYS + r) * 64, &tmKV, B.v_full, 2 * C + head * D + 32 * a, row0 + r);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -200,28 +218,14 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ================= TMA producer =================
     if (lane == 0) {
       const int row0 = b * S;
-      mbar_expect_tx(B.kv_full, NA * KEYS * 64);
-      for (int r = 0; r < KEYS; r += kv_box_rows) {
-        for (int a = 0; a < N128; ++a)
-          tma_load_2d(sbase + k_off + (a * KEYS + r) * 128, &tmK, B.kv_full, C + head * D + 64 * a, row0 + r);
-        if (N64) tma_load_2d(sbase + k64_off + r * 64, &tmKV, B.kv_full, C + head * D + 64 * N128, row0 + r);
-      }
-      mbar_expect_tx(B.q_full, NA * AT_MT * 64);
-      auto load_q = [&](int row) {
-        for (int a = 0; a < N128; ++a) tma_load_2d(sbase + q_off + a * AT_MT * 128, &tmQ, B.q_full, head * D + 64 * a, row);
-        if (N64) tma_load_2d(sbase + q64_off, &tmQ32, B.q_full, head * D + 64 * N128, row);
-      };
-      load_q(row0);
-      mbar_expect_tx(B.v_full, NA * KEYS * 64);
-      for (int a = 0; a < NA; ++a)
-        for (int r = 0; r < KEYS; r += kv_box_rows)
-          tma_load_2d(sbase + v_off + (a * KEYS + r) * 64, &tmKV, B.v_full, 2 * C + head * D + 32 * a, row0 + r);
       AT_T(1);
       for (int t = 1; t < tiles; ++t) {
         mbar_wait(B.q_free, (t - 1) & 1);
         AT_T(2);                     // both score halves of tile t-1 are in TMEM
         mbar_expect_tx(B.q_full, NA * AT_MT * 64);
-        load_q(row0 + t * AT_MT);
+        for (int a = 0; a < N128; ++a)
+          tma_load_2d(sbase + q_off + a * AT_MT * 128, &tmQ, B.q_full, head * D + 64 * a, row0 + t * AT_MT);
+        if (N64) tma_load_2d(sbase + q64_off, &tmQ32, B.q_full, head * D + 64 * N128, row0 + t * AT_MT);
       }
       AT_DUMP("tma");
     }
@@ -268,6 +272,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       issue_qk(0, idesc_x);
       tc_commit(B.sx_full);
       if (KB > 0) {
+        if (kv_box_rows < KEYS) mbar_wait(B.k1_full, 0);      // the K rows past the first box
+        tc_fence_after();
         issue_qk(KA, idesc_y);
         tc_commit(B.sy_full);
       }
@@ -296,13 +302,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mbar_wait(B.py_full, t & 1);
           AT_T(16);
           tc_fence_after();
-          issue_pv(KA / 16, KEYS / 16, o_col);
-          tc_commit(B.o_full + 8 * ob);
-          if (t + 1 < tiles) {
+          if (t + 1 < tiles) {                                  // the softmax warps wait on these scores next
             issue_qk(KA, idesc_y);
             tc_commit(B.sy_full);
             tc_commit(B.q_free);
           }
+          issue_pv(KA / 16, KEYS / 16, o_col);
+          tc_commit(B.o_full + 8 * ob);
         }
       }
       AT_T(19);
