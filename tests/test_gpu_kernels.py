@@ -372,7 +372,12 @@ def attn_ref(qkv, h, qn_w, qn_b, kn_w, kn_b, eps=1e-5):
                                         (68, 2, 16, True), (20, 4, 8, True), (33, 3, 24, False), (300, 2, 128, True),
                                         (17, 4, 32, True), (32, 2, 64, True), (261, 8, 96, False), (201, 8, 64, False),
                                         (513, 2, 96, False), (400, 2, 64, False), (256, 4, 32, False),
-                                        (16, 2, 16, False), (300, 1, 128, False), (1, 2, 32, False)])
+                                        (16, 2, 16, False), (300, 1, 128, False), (1, 2, 32, False),
+                                        # shapes of the tcgen05 kernel: one / two / three query tiles, 16-key tails,
+                                        # one and two TMA boxes of keys, all three head sizes
+                                        (128, 2, 64, False), (5, 2, 64, False), (16, 1, 64, False), (257, 2, 96, False),
+                                        (288, 2, 64, False), (272, 1, 128, False), (256, 2, 128, False),
+                                        (144, 3, 96, False), (208, 2, 128, False)])
 def test_attention(sdp, dtype, S, h, d, norm):
     B, C = 2, h * d
     qkv = rnd(B, S, 3 * C, seed=50, scale=1.5).to(dtype)
