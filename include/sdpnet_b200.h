@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SDPNET_B200_ABI_VERSION 3
+#define SDPNET_B200_ABI_VERSION 4
 
 typedef enum { SDP_F32 = 0, SDP_BF16 = 1 } sdp_dtype;
 
@@ -150,6 +150,16 @@ int sdp_ln_dwconv_wants_stats(int Gh, int Gw, int C, int k, int R, int dtype);
 int sdp_ln_dwconv_stats(const void *act, const float *stats, int parts, const float *gamma, const float *beta,
                         const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int k,
                         int R, float eps, int dtype, void *stream);
+
+/* The same operator as a channel-stationary tensor-core kernel (dwconv_slab.cu): a CTA keeps the Toeplitz
+ * fragments of 32 channels' taps in registers and streams images past them (14 mma.sync per channel and image
+ * for k = 7 instead of 12544 FMAs).  Needs `token_stats`: caller-owned scratch of 2 * B * Gh * Gw floats that
+ * the call fills with (mean, rstd) of every spatial token and then consumes.  bf16 only;
+ * sdp_ln_dwconv_slab_ok says whether the shape is covered (Gh <= 16, Gw in {8, 16}, C % 32 == 0, k in {3,5,7}). */
+int sdp_ln_dwconv_slab_ok(int Gh, int Gw, int C, int k, int dtype);
+int sdp_ln_dwconv_slab(const void *act, float *token_stats, const float *gamma, const float *beta,
+                       const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int k,
+                       int R, float eps, void *stream);
 
 /* Fused QK-LayerNorm + softmax attention (layers.py:282-300): qkv [B, S, 3C] with column
  * blocks q | k | v, each [h, d]; q/k get a per-head LayerNorm(d) (eps, affine) when

@@ -1,0 +1,315 @@
+// Channel-stationary tensor-core depthwise conv + channel LayerNorm (bf16, grids G x 8 / G x 16 with G <= 16,
+// k in {3,5,7}).  Reference: layer_norm_1 + conv2d[0] of ConvMixer, layers.py:102 (:12-24 + :73-78).
+//
+// For one channel the k x k 'same' conv of the zero-haloed plane P is, per tap row dy and per block of eight
+// output columns x0..x0+7, one 16 x 8 x 16 matrix product
+//      Out[y, x0 + n] += sum_k P[y + dy, x0 + k] * T_dy[k, n],     T_dy[k, n] = w[dy][k - n - 1]  (k = 7)
+// (a banded Toeplitz block of the row's taps; shift-invariant, so ONE block serves every x0).  That makes the
+// whole weight operand of a channel 2 registers per tap row and lane -- 14 for k = 7 -- small enough to stay in
+// registers for the lifetime of the CTA.  So the kernel is organised around the weights, not around the image:
+//   * a CTA owns 32 channels (each of its 8 warps owns 4, B fragments loaded once) and loops over images;
+//   * per image it streams the [tokens, 32 channels] slice in with cp.async (64 B per token = two full sectors),
+//     normalises and transposes it into per-channel planes with ldmatrix.trans (80-byte token rows and 48-byte
+//     plane rows: conflict-free both ways), runs 14 mma.sync.m16n8k16 per channel on ldmatrix'ed plane rows, and
+//     writes the [tokens, 32] result back through a token-major tile with 128-bit stores;
+//   * the token statistics (over all C channels) come from a separate warp-per-row pass, because a slab CTA never
+//     sees the whole row.
+// Two CTAs per SM overlap one's transposes with the other's MMAs.  12544 scalar FMAs per channel and image
+// become 14 MMAs.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace sdp {
+
+constexpr int DS_THREADS = 256;
+constexpr int DS_CH = 32;                 // channels per CTA
+constexpr int DS_HL = 4;                  // left halo columns (keeps 8-column blocks 16-byte aligned)
+constexpr int DS_PROW = 48;               // bytes per plane row: 24 bf16 = 4 halo + 16 + 4 halo
+constexpr int DS_RAWP = 80;               // bytes per token in the raw / out tiles: 64 used + 16 pad
+
+__device__ __forceinline__ void ds_mma(float *c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ds_ldmatrix_x4(uint32_t addr, uint32_t *r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ds_ldmatrix_x2(uint32_t addr, uint32_t *r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void ds_ldmatrix_x4_trans(uint32_t addr, uint32_t *r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ds_cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// (mean, rstd) of every spatial token row over all C channels, compact [B][Tn]: warp per row, the row held in
+// registers (exact two-pass).
+__global__ void __launch_bounds__(256)
+token_stats_kernel(const bf16 *__restrict__ act, float2 *__restrict__ stats, long long rows, int Tn, int R, int C,
+                   float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long src_row = (row / Tn) * (R + Tn) + R + row % Tn;
+  const uint4 *rv = reinterpret_cast<const uint4 *>(act + src_row * C);
+  const int nv = C >> 3;
+  float v[8][8];                                            // up to C = 2048
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) {
+      const uint4 u = __ldg(rv + idx);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[i][2 * j] = __uint_as_float(w[j] << 16);
+        v[i][2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+        s += v[i][2 * j] + v[i][2 * j + 1];
+      }
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (lane + 32 * i < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  q = warp_sum(q);
+  if (lane == 0) stats[row] = make_float2(mean, 1.0f / sqrtf(q / (float)C + eps));
+}
+
+template <int KS>
+struct DsLayout {
+  static constexpr int ROWS = 16 + KS - 1;
+  int raw, stat, planes, otile, total;
+  int plane_bytes;
+  __host__ __device__ explicit DsLayout(int Tn) {
+    // plane stride: a multiple of 16 bytes whose word count is 12 (mod 32): the eight channels a transposing
+    // store touches at once then land in eight different bank quads
+    int pb = (ROWS * DS_PROW + 15) / 16 * 16;
+    while ((pb / 4) % 32 != 12) pb += 16;
+    plane_bytes = pb;
+    raw = 0;                                                // [2][Tn][80 B]
+    stat = raw + 2 * Tn * DS_RAWP;                          // [2][Tn] float2 (mean, rstd)
+    planes = stat + 2 * Tn * 8;                             // [32][plane_bytes], zero halo
+    planes = (planes + 15) / 16 * 16;
+    otile = planes + DS_CH * pb;                            // [Tn][80 B]
+    total = otile + Tn * DS_RAWP;
+  }
+};
+
+template <int KS>
+__global__ void __launch_bounds__(DS_THREADS, 2)
+ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ stats, const float *__restrict__ gamma,
+                      const float *__restrict__ beta, const float *__restrict__ wdw, const float *__restrict__ bdw,
+                      bf16 *__restrict__ out, int B, int Gh, int Gw, int C, int R, int img_per_cta) {
+  constexpr int lo = (KS - 1) / 2;
+  extern __shared__ __align__(16) uint8_t ds_smem[];
+  const int Tn = Gh * Gw, S = R + Tn;
+  const DsLayout<KS> L(Tn);
+  const int PB = L.plane_bytes;
+  const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(ds_smem));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int c0 = blockIdx.x * DS_CH;
+  const int b_begin = blockIdx.y * img_per_cta, b_end = min(B, b_begin + img_per_cta);
+  if (b_begin >= b_end) return;
+
+  auto prefetch = [&](int b, int buf) {    // the [Tn, 32-channel] slice of image b (64 B per token) + its statistics
+    const bf16 *src = act + ((long long)b * S + R) * C + c0;
+    for (int i = tid; i < Tn * 4; i += DS_THREADS)
+      ds_cp_async16(sbase + L.raw + buf * Tn * DS_RAWP + (i >> 2) * DS_RAWP + (i & 3) * 16, src + (long long)(i >> 2) * C + (i & 3) * 8);
+    const float2 *ss = stats + (long long)b * Tn;
+    for (int i = tid; i < Tn / 2; i += DS_THREADS)
+      ds_cp_async16(sbase + L.stat + buf * Tn * 8 + i * 16, ss + 2 * i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(b_begin, 0);
+
+  // zero the planes once: halo cells are never written again
+  for (int i = tid; i < DS_CH * PB / 16; i += DS_THREADS)
+    reinterpret_cast<uint4 *>(ds_smem + L.planes)[i] = make_uint4(0, 0, 0, 0);
+
+  // ---- the weights of this warp's four channels as Toeplitz B fragments, for the lifetime of the CTA ----
+  // lane (g, q) holds (k = 2q, 2q+1 | n = g) and (k = 2q+8, 2q+9 | n = g); tap column kx = k - n + lo - HL
+  uint32_t bfr[4][KS][2];
+  float bias[4];
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const int ch = c0 + warp * 4 + cc;
+    bias[cc] = bdw ? __ldg(bdw + ch) : 0.0f;
+#pragma unroll
+    for (int dy = 0; dy < KS; ++dy) {
+      auto tap = [&](int k) {
+        const int kx = k - g + lo - DS_HL;
+        return (kx >= 0 && kx < KS) ? __ldg(wdw + (long long)(dy * KS + kx) * C + ch) : 0.0f;
+      };
+      bfr[cc][dy][0] = pack_bf16x2(tap(2 * q), tap(2 * q + 1));
+      bfr[cc][dy][1] = pack_bf16x2(tap(2 * q + 8), tap(2 * q + 9));
+    }
+  }
+  // transform constants: after ldmatrix.trans matrix m hands this lane channel 8m + g of tokens 2q, 2q + 1
+  float gm[4], bt[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    gm[m] = __ldg(gamma + c0 + 8 * m + g);
+    bt[m] = __ldg(beta + c0 + 8 * m + g);
+  }
+  // ldmatrix lane addressing inside a plane: matrices (rows 0-7 | 8-15) x (cols 0-7 | 8-15), then cols 16-23
+  const uint32_t a_lane = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * DS_PROW + (lane >> 4) * 16);
+  const uint32_t a_lane2 = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * DS_PROW + 32);
+  const uint32_t planes_addr = sbase + L.planes;
+
+  for (int b = b_begin; b < b_end; ++b) {
+    const int buf = (b - b_begin) & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                       // slice b has landed; everybody is past the previous image's stores
+    if (b + 1 < b_end) prefetch(b + 1, buf ^ 1);
+
+    // ---- normalise + transpose: [token][channel] rows -> per-channel planes (two tokens per 32-bit store) ----
+    const uint32_t raw_addr = sbase + L.raw + buf * Tn * DS_RAWP;
+    const float2 *s_stat = reinterpret_cast<const float2 *>(ds_smem + L.stat + buf * Tn * 8);
+    for (int t0 = warp * 8; t0 < Tn; t0 += 8 * (DS_THREADS / 32)) {
+      uint32_t r4[4];
+      ds_ldmatrix_x4_trans(raw_addr + (t0 + (lane & 7)) * DS_RAWP + (lane >> 3) * 16, r4);
+      const float2 st0 = s_stat[t0 + 2 * q], st1 = s_stat[t0 + 2 * q + 1];
+      const int y = t0 / Gw, x = t0 % Gw + 2 * q;
+      const uint32_t cell = planes_addr + (y + lo) * DS_PROW + (DS_HL + x) * 2;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const float v0 = (__uint_as_float(r4[m] << 16) - st0.x) * st0.y;
+        const float v1 = (__uint_as_float(r4[m] & 0xffff0000u) - st1.x) * st1.y;
+        const uint32_t pk = pack_bf16x2(fmaf(v0, gm[m], bt[m]), fmaf(v1, gm[m], bt[m]));
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(cell + (8 * m + g) * PB), "r"(pk) : "memory");
+      }
+    }
+    __syncthreads();                       // planes of image b complete
+
+    // ---- MMA: four channels per warp, 2 * KS MMAs each ----
+    float acc[4][2][4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[cc][n][j] = bias[cc];
+      const uint32_t pbase = planes_addr + (warp * 4 + cc) * PB;
+#pragma unroll
+      for (int dy = 0; dy < KS; ++dy) {
+        uint32_t a[4], a2[2];
+        ds_ldmatrix_x4(pbase + dy * DS_PROW + a_lane, a);        // (r0-7,c0-7) (r8-15,c0-7) (r0-7,c8-15) (r8-15,c8-15)
+        ds_ldmatrix_x2(pbase + dy * DS_PROW + a_lane2, a2);      // (r0-7,c16-23) (r8-15,c16-23)
+        ds_mma(acc[cc][0], a[0], a[1], a[2], a[3], bfr[cc][dy][0], bfr[cc][dy][1]);
+        ds_mma(acc[cc][1], a[2], a[3], a2[0], a2[1], bfr[cc][dy][0], bfr[cc][dy][1]);
+      }
+    }
+    // C fragments: (y = g | g + 8, x = 8n + 2q, +1); the warp's four channels of a token go out as one 8-byte store
+    const uint32_t otile_addr = sbase + L.otile + warp * 8;
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int y = g + 8 * hh, x = 8 * n + 2 * q;
+        if (y < Gh && x < Gw) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const uint32_t lo2 = pack_bf16x2(acc[0][n][2 * hh + e], acc[1][n][2 * hh + e]);
+            const uint32_t hi2 = pack_bf16x2(acc[2][n][2 * hh + e], acc[3][n][2 * hh + e]);
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(otile_addr + (y * Gw + x + e) * DS_RAWP), "r"(lo2), "r"(hi2)
+                         : "memory");
+          }
+        }
+      }
+    __syncthreads();                       // out tile complete, planes free
+
+    // ---- 128-bit stores of the [Tn, 32] result; the R register rows of the slab are zero (passed through later) ----
+    bf16 *dst = out + (long long)b * S * C + c0;
+    for (int i = tid; i < R * 4; i += DS_THREADS)
+      *reinterpret_cast<uint4 *>(dst + (long long)(i >> 2) * C + (i & 3) * 8) = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < Tn * 4; i += DS_THREADS) {
+      const uint4 u = *reinterpret_cast<const uint4 *>(ds_smem + L.otile + (i >> 2) * DS_RAWP + (i & 3) * 16);
+      *reinterpret_cast<uint4 *>(dst + (long long)(R + (i >> 2)) * C + (i & 3) * 8) = u;
+    }
+  }
+}
+
+static int num_sms_ds() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int KS>
+static int launch_slab(const void *act, float *token_stats, const float *gamma, const float *beta, const float *wdw,
+                       const float *bdw, void *out, int B, int Gh, int Gw, int C, int R, float eps, cudaStream_t st) {
+  const int Tn = Gh * Gw, S = R + Tn;
+  const long long rows = (long long)B * Tn;
+  (void)S;
+  token_stats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16 *)act, reinterpret_cast<float2 *>(token_stats),
+                                                                rows, Tn, R, C, eps);
+  SDP_LAUNCH_OK();
+  const DsLayout<KS> L(Tn);
+  auto kern = ln_dwconv_slab_kernel<KS>;
+  static int configured = 0;
+  if (L.total > configured) {
+    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    configured = L.total;
+  }
+  const int slabs = C / DS_CH;
+  // two CTAs per SM; image groups sized so that the grid is (just under) one wave
+  int groups = (2 * num_sms_ds()) / slabs;
+  if (groups < 1) groups = 1;
+  if (groups > B) groups = B;
+  const int per = (B + groups - 1) / groups;
+  groups = (B + per - 1) / per;
+  kern<<<dim3(slabs, groups), DS_THREADS, L.total, st>>>((const bf16 *)act, reinterpret_cast<const float2 *>(token_stats),
+                                                         gamma, beta, wdw, bdw, (bf16 *)out, B, Gh, Gw, C, R, per);
+  SDP_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace sdp
+
+using namespace sdp;
+
+extern "C" int sdp_ln_dwconv_slab_ok(int Gh, int Gw, int C, int k, int dtype) {
+  return dtype == SDP_BF16 && (k == 3 || k == 5 || k == 7) && Gh >= 1 && Gh <= 16 && (Gw == 8 || Gw == 16) &&
+         C % DS_CH == 0 && C <= 2048;
+}
+
+extern "C" int sdp_ln_dwconv_slab(const void *act, float *token_stats, const float *gamma, const float *beta,
+                                  const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int k,
+                                  int R, float eps, void *stream) {
+  SDP_CHECK(act && token_stats && gamma && beta && wdw && out, "sdp_ln_dwconv_slab: null pointer");
+  SDP_CHECK(sdp_ln_dwconv_slab_ok(Gh, Gw, C, k, SDP_BF16), "sdp_ln_dwconv_slab: shape not covered (ask sdp_ln_dwconv_slab_ok)");
+  SDP_CHECK(B > 0 && R >= 0, "sdp_ln_dwconv_slab: bad sizes");
+  SDP_CHECK(act != out, "sdp_ln_dwconv_slab: must not run in place (spatial neighbours are read)");
+  SDP_CHECK((reinterpret_cast<uintptr_t>(act) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(token_stats) & 15) == 0,
+            "sdp_ln_dwconv_slab: act, out and token_stats must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (k == 7) return launch_slab<7>(act, token_stats, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+  if (k == 5) return launch_slab<5>(act, token_stats, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+  return launch_slab<3>(act, token_stats, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+}

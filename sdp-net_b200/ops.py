@@ -154,6 +154,28 @@ def ln_dwconv(act: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, wdw: t
     return out
 
 
+def ln_dwconv_slab_ok(Gh: int, Gw: int, Cc: int, k: int, dtype: torch.dtype) -> bool:
+    return bool(L.lib().sdp_ln_dwconv_slab_ok(Gh, Gw, Cc, k, _DT[dtype]))
+
+
+def ln_dwconv_slab(act: torch.Tensor, token_stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                   wdw: torch.Tensor, bdw: Optional[torch.Tensor], out: torch.Tensor, Gh: int, Gw: int, R: int,
+                   eps: float = 1e-6):
+    """Channel-stationary tensor-core variant of ln_dwconv; `token_stats` is fp32 scratch of >= 2*B*Gh*Gw elements."""
+    B, S, Cc = act.shape
+    if S != R + Gh * Gw or not act.is_contiguous() or not out.is_contiguous():
+        raise ValueError("ln_dwconv_slab: act must be contiguous [B, R + Gh*Gw, C]")
+    k = int(round(wdw.shape[0] ** 0.5))
+    if wdw.dim() != 2 or k * k != wdw.shape[0] or wdw.shape[1] != Cc:
+        raise ValueError("ln_dwconv_slab: wdw must be tap-major [k*k, C]")
+    if token_stats.dtype != torch.float32 or token_stats.numel() < 2 * B * Gh * Gw or not token_stats.is_contiguous():
+        raise ValueError("ln_dwconv_slab: token_stats must be contiguous fp32 with >= 2*B*Gh*Gw elements")
+    L.check(L.lib().sdp_ln_dwconv_slab(_p(act), _p(token_stats), _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")),
+                                       _p(_f32(wdw, "wdw")), _p(_f32(bdw, "bdw")), _p(out), B, Gh, Gw, Cc, k, R,
+                                       float(eps), _stream()), "sdp_ln_dwconv_slab")
+    return out
+
+
 def ln_dwconv_wants_stats(Gh: int, Gw: int, Cc: int, k: int, R: int, dtype: torch.dtype) -> bool:
     return bool(L.lib().sdp_ln_dwconv_wants_stats(Gh, Gw, Cc, k, R, _DT[dtype]))
 

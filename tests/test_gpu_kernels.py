@@ -352,6 +352,25 @@ def test_ln_dwconv(sdp, dtype, Gh, Gw, C, k, R, bias, monkeypatch):
             assert (out3.float() - ref).abs().max() < tol
 
 
+@pytest.mark.parametrize("B,Gh,Gw,C,k,R,bias", [(3, 16, 16, 768, 7, 5, False), (5, 16, 16, 64, 7, 4, True), (2, 8, 8, 32, 5, 1, True),
+                                                (7, 12, 16, 96, 3, 0, False), (40, 5, 8, 32, 7, 2, True), (1, 16, 8, 128, 5, 5, False)])
+def test_ln_dwconv_slab(sdp, B, Gh, Gw, C, k, R, bias):
+    """Channel-stationary tensor-core kernel (dwconv_slab.cu) against the same torch reference (layers.py:102)."""
+    assert sdp.ops.ln_dwconv_slab_ok(Gh, Gw, C, k, torch.bfloat16)
+    assert not sdp.ops.ln_dwconv_slab_ok(14, 14, C, k, torch.bfloat16)
+    act = (rnd(B, R + Gh * Gw, C, seed=45) * 2 + 0.3).bfloat16()
+    gamma, beta = rnd(C, seed=41) * 0.3 + 1, rnd(C, seed=42) * 0.3
+    wdw = rnd(C, k, k, seed=43, scale=1 / k)
+    bdw = rnd(C, seed=44) if bias else None
+    out = torch.full_like(act, float("nan"))
+    scratch = torch.full((2 * B * Gh * Gw,), float("nan"), device="cuda")
+    sdp.ops.ln_dwconv_slab(act, scratch, gamma, beta, wdw.reshape(C, k * k).t().contiguous(), bdw, out, Gh, Gw, R)
+    ref = dw_ref(act, R, Gh, Gw, gamma, beta, wdw, bdw)
+    assert (out[:, :R] == 0).all()
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max() < 4e-2
+
+
 # --------------------------------------------------------------------------------------------
 # attention with fused QK LayerNorm
 # --------------------------------------------------------------------------------------------

@@ -52,6 +52,9 @@ def timed(name, fn, flops=0, nbytes=0):
 timed("layernorm_rows", lambda: ops.layernorm_rows(a2, lw, lb, n2, 1e-5), nbytes=4 * M * C)
 timed("ln_dwconv k7", lambda: ops.ln_dwconv(act, lw, lb, wdw, None, norm, G, G, R), flops=2 * B * T * C * k * k,
       nbytes=4 * B * T * C)
+scratch = torch.empty(2 * B * T, device=dev)
+timed("ln_dwconv_slab k7", lambda: ops.ln_dwconv_slab(act, scratch, lw, lb, wdw, None, norm, G, G, R), flops=2 * B * T * C * k * k,
+      nbytes=4 * B * T * C)
 timed("gemm qkv+headnorm 2304x768", lambda: ops.gemm(n2, w_qkv, qkv.view(M, 3 * C), headnorm=(d, C, 1e-5, qw, qb, qw, qb)),
       flops=2 * M * 3 * C * C)
 timed("gemm qkv plain 2304x768", lambda: ops.gemm(n2, w_qkv, qkv.view(M, 3 * C)), flops=2 * M * 3 * C * C)
