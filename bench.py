@@ -191,7 +191,7 @@ def profile_families(eng, x, R, steps):
             return r
         setattr(ops, name, timed)
 
-    for name, family in [("gemm", "gemm_bf16_tc"), ("layernorm_rows", "layernorm_rows"), ("ln_dwconv", "ln_dwconv"),
+    for name, family in [("gemm", "gemm_bf16_tc"), ("layernorm_rows", "layernorm_rows"), ("ln_dwconv", "ln_dwconv"), ("ln_dwconv_slab", "ln_dwconv"),
                          ("attention", "attention"), ("im2col_patches", "other"), ("fill_registers", "other"),
                          ("pool_ln", "other"), ("row_stats", "other")]:
         wrap(name, family)

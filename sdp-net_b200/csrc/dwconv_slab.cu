@@ -27,7 +27,9 @@ constexpr int DS_THREADS = 256;
 constexpr int DS_CH = 32;                 // channels per CTA
 constexpr int DS_HL = 4;                  // left halo columns (keeps 8-column blocks 16-byte aligned)
 constexpr int DS_PROW = 48;               // bytes per plane row: 24 bf16 = 4 halo + 16 + 4 halo
-constexpr int DS_RAWP = 80;               // bytes per token in the raw / out tiles: 64 used + 16 pad
+constexpr int DS_RAWP = 64;               // bytes per token in the raw tile; 16-byte chunk c of token t sits at c ^ ((t >> 1) & 3):
+                                          // conflict-free for the cp.async writes (whole rows) and the ldmatrix reads (8 tokens x 16 B)
+constexpr int DS_OUTP = 80;               // bytes per token in the out tile: 64 used + 16 pad
 
 __device__ __forceinline__ void ds_mma(float *c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                        uint32_t b1) {
@@ -55,6 +57,7 @@ __device__ __forceinline__ void ds_cp_async16(uint32_t dst, const void *src) {
 
 // (mean, rstd) of every spatial token row over all C channels, compact [B][Tn]: warp per row, the row held in
 // registers (exact two-pass).
+template <int NI>                          // 16-byte chunks per lane: C <= 256 * NI
 __global__ void __launch_bounds__(256)
 token_stats_kernel(const bf16 *__restrict__ act, float2 *__restrict__ stats, long long rows, int Tn, int R, int C,
                    float eps) {
@@ -64,10 +67,10 @@ token_stats_kernel(const bf16 *__restrict__ act, float2 *__restrict__ stats, lon
   const long long src_row = (row / Tn) * (R + Tn) + R + row % Tn;
   const uint4 *rv = reinterpret_cast<const uint4 *>(act + src_row * C);
   const int nv = C >> 3;
-  float v[8][8];                                            // up to C = 2048
+  float v[NI][8];
   float s = 0.0f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < NI; ++i) {
     const int idx = lane + 32 * i;
     if (idx < nv) {
       const uint4 u = __ldg(rv + idx);
@@ -83,7 +86,7 @@ token_stats_kernel(const bf16 *__restrict__ act, float2 *__restrict__ stats, lon
   const float mean = warp_sum(s) / (float)C;
   float q = 0.0f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < NI; ++i)
     if (lane + 32 * i < nv) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -106,12 +109,12 @@ struct DsLayout {
     int pb = (ROWS * DS_PROW + 15) / 16 * 16;
     while ((pb / 4) % 32 != 12) pb += 16;
     plane_bytes = pb;
-    raw = 0;                                                // [2][Tn][80 B]
+    raw = 0;                                                // [2][Tn][64 B]
     stat = raw + 2 * Tn * DS_RAWP;                          // [2][Tn] float2 (mean, rstd)
     planes = stat + 2 * Tn * 8;                             // [32][plane_bytes], zero halo
     planes = (planes + 15) / 16 * 16;
     otile = planes + DS_CH * pb;                            // [Tn][80 B]
-    total = otile + Tn * DS_RAWP;
+    total = otile + Tn * DS_OUTP;
   }
 };
 
@@ -135,7 +138,8 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
   auto prefetch = [&](int b, int buf) {    // the [Tn, 32-channel] slice of image b (64 B per token) + its statistics
     const bf16 *src = act + ((long long)b * S + R) * C + c0;
     for (int i = tid; i < Tn * 4; i += DS_THREADS)
-      ds_cp_async16(sbase + L.raw + buf * Tn * DS_RAWP + (i >> 2) * DS_RAWP + (i & 3) * 16, src + (long long)(i >> 2) * C + (i & 3) * 8);
+      ds_cp_async16(sbase + L.raw + buf * Tn * DS_RAWP + (i >> 2) * DS_RAWP + (((i & 3) ^ ((i >> 3) & 3)) << 4),
+                    src + (long long)(i >> 2) * C + (i & 3) * 8);
     const float2 *ss = stats + (long long)b * Tn;
     for (int i = tid; i < Tn / 2; i += DS_THREADS)
       ds_cp_async16(sbase + L.stat + buf * Tn * 8 + i * 16, ss + 2 * i);
@@ -188,7 +192,7 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
     const float2 *s_stat = reinterpret_cast<const float2 *>(ds_smem + L.stat + buf * Tn * 8);
     for (int t0 = warp * 8; t0 < Tn; t0 += 8 * (DS_THREADS / 32)) {
       uint32_t r4[4];
-      ds_ldmatrix_x4_trans(raw_addr + (t0 + (lane & 7)) * DS_RAWP + (lane >> 3) * 16, r4);
+      ds_ldmatrix_x4_trans(raw_addr + (t0 + (lane & 7)) * DS_RAWP + (((lane >> 3) ^ ((lane >> 1) & 3)) << 4), r4);
       const float2 st0 = s_stat[t0 + 2 * q], st1 = s_stat[t0 + 2 * q + 1];
       const int y = t0 / Gw, x = t0 % Gw + 2 * q;
       const uint32_t cell = planes_addr + (y + lo) * DS_PROW + (DS_HL + x) * 2;
@@ -221,7 +225,9 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
       }
     }
     // C fragments: (y = g | g + 8, x = 8n + 2q, +1); the warp's four channels of a token go out as one 8-byte store
-    const uint32_t otile_addr = sbase + L.otile + warp * 8;
+    // 8-byte slot w of token (y, x) sits at w ^ (y & 3): the 16 lanes of a half-warp (4 rows x 4 column pairs) then
+    // cover all 32 banks
+    const uint32_t otile_addr = sbase + L.otile;
 #pragma unroll
     for (int n = 0; n < 2; ++n)
 #pragma unroll
@@ -232,7 +238,8 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
           for (int e = 0; e < 2; ++e) {
             const uint32_t lo2 = pack_bf16x2(acc[0][n][2 * hh + e], acc[1][n][2 * hh + e]);
             const uint32_t hi2 = pack_bf16x2(acc[2][n][2 * hh + e], acc[3][n][2 * hh + e]);
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(otile_addr + (y * Gw + x + e) * DS_RAWP), "r"(lo2), "r"(hi2)
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(otile_addr + (y * Gw + x + e) * DS_OUTP + ((warp ^ (g & 3)) << 3)),
+                         "r"(lo2), "r"(hi2)
                          : "memory");
           }
         }
@@ -244,8 +251,11 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
     for (int i = tid; i < R * 4; i += DS_THREADS)
       *reinterpret_cast<uint4 *>(dst + (long long)(i >> 2) * C + (i & 3) * 8) = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < Tn * 4; i += DS_THREADS) {
-      const uint4 u = *reinterpret_cast<const uint4 *>(ds_smem + L.otile + (i >> 2) * DS_RAWP + (i & 3) * 16);
-      *reinterpret_cast<uint4 *>(dst + (long long)(R + (i >> 2)) * C + (i & 3) * 8) = u;
+      const int t = i >> 2, sw = (t / Gw) & 3;
+      const uint8_t *row = ds_smem + L.otile + t * DS_OUTP;
+      const uint2 u0 = *reinterpret_cast<const uint2 *>(row + (((2 * (i & 3)) ^ sw) << 3));
+      const uint2 u1 = *reinterpret_cast<const uint2 *>(row + (((2 * (i & 3) + 1) ^ sw) << 3));
+      *reinterpret_cast<uint4 *>(dst + (long long)(R + t) * C + (i & 3) * 8) = make_uint4(u0.x, u0.y, u1.x, u1.y);
     }
   }
 }
@@ -266,8 +276,13 @@ static int launch_slab(const void *act, float *token_stats, const float *gamma, 
   const int Tn = Gh * Gw, S = R + Tn;
   const long long rows = (long long)B * Tn;
   (void)S;
-  token_stats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16 *)act, reinterpret_cast<float2 *>(token_stats),
-                                                                rows, Tn, R, C, eps);
+  const unsigned sblocks = (unsigned)((rows + 7) / 8);
+  float2 *ts = reinterpret_cast<float2 *>(token_stats);
+  if (C <= 256) token_stats_kernel<1><<<sblocks, 256, 0, st>>>((const bf16 *)act, ts, rows, Tn, R, C, eps);
+  else if (C <= 512) token_stats_kernel<2><<<sblocks, 256, 0, st>>>((const bf16 *)act, ts, rows, Tn, R, C, eps);
+  else if (C <= 768) token_stats_kernel<3><<<sblocks, 256, 0, st>>>((const bf16 *)act, ts, rows, Tn, R, C, eps);
+  else if (C <= 1024) token_stats_kernel<4><<<sblocks, 256, 0, st>>>((const bf16 *)act, ts, rows, Tn, R, C, eps);
+  else token_stats_kernel<8><<<sblocks, 256, 0, st>>>((const bf16 *)act, ts, rows, Tn, R, C, eps);
   SDP_LAUNCH_OK();
   const DsLayout<KS> L(Tn);
   auto kern = ln_dwconv_slab_kernel<KS>;

@@ -1,6 +1,7 @@
 // ABI housekeeping + the whole-model forward (reference model.py:129-149) sequenced behind the
 // C-ABI: one call enqueues every kernel of the forward on the caller's stream.  No allocation,
 // no synchronisation, no host<->device copies happen here.
+#include <cstdlib>
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
@@ -118,8 +119,15 @@ int mixer(const Ctx &c, const sdp_mixer_weights &w) {
     dw_stats = c.ws->stats;
     dw_parts = 1;
   }
-  if (int rc = sdp_ln_dwconv_stats(c.ws->act, dw_stats, dw_parts, w.ln1_g, w.ln1_b, w.w_dw, w.b_dw, c.ws->norm, c.B, c.Gh,
-                                   c.Gw, C, m.conv_k, c.R, 1e-6f, dt, c.st)) return rc;
+  static const bool slab_on = [] { const char *e = getenv("SDP_DWCONV_SLAB"); return !(e && e[0] == '0'); }();
+  if (!fold && slab_on && c.ws->stats != nullptr && sdp_ln_dwconv_slab_ok(c.Gh, c.Gw, C, m.conv_k, dt)) {
+    // channel-stationary tensor-core kernel; the statistics workspace doubles as its (mean, rstd) scratch
+    if (int rc = sdp_ln_dwconv_slab(c.ws->act, c.ws->stats, w.ln1_g, w.ln1_b, w.w_dw, w.b_dw, c.ws->norm, c.B, c.Gh, c.Gw, C,
+                                    m.conv_k, c.R, 1e-6f, c.st)) return rc;
+  } else if (int rc = sdp_ln_dwconv_stats(c.ws->act, dw_stats, dw_parts, w.ln1_g, w.ln1_b, w.w_dw, w.b_dw, c.ws->norm, c.B,
+                                          c.Gh, c.Gw, C, m.conv_k, c.R, 1e-6f, dt, c.st)) {
+    return rc;
+  }
   if (int rc = gemm(c, c.ws->norm, C, w.w_pw, C, w.b_pw, M, C, C, m.act, c.ws->act, c.ws->act, C, dt, true, nullptr, fold)) return rc;
   const void *xin = c.ws->act;
   if (!fold) {

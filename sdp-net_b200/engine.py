@@ -15,6 +15,7 @@ Activation layout everywhere: token-major `[B, S = R + T, C]`, registers first
 """
 from __future__ import annotations
 
+import os
 import ctypes as C
 from typing import Dict, Optional
 
@@ -314,7 +315,13 @@ def run_mixer(pw: Packer, w: dict, bufs: Buffers, Gh: int, Gw: int, act_name: Op
     if not fold and bufs.stats is not None and ops.ln_dwconv_wants_stats(Gh, Gw, C_, w["conv_k"], R, pw.dtype):
         ops.row_stats(a2, bufs.stats)        # token (sum, sumsq) for the tensor-core depthwise kernel
         dw_stats = bufs.stats
-    ops.ln_dwconv(bufs.act, w["ln1_g"], w["ln1_b"], w["w_dw"], w["b_dw"], bufs.norm, Gh, Gw, R, 1e-6, stats=dw_stats)
+    k_dw = int(round(w["w_dw"].shape[0] ** 0.5))
+    if (not fold and bufs.stats is not None and os.environ.get("SDP_DWCONV_SLAB", "1") != "0"
+            and ops.ln_dwconv_slab_ok(Gh, Gw, C_, k_dw, pw.dtype)):
+        # channel-stationary tensor-core kernel (same choice as sdp_forward); the statistics buffer is its scratch
+        ops.ln_dwconv_slab(bufs.act, bufs.stats.view(-1), w["ln1_g"], w["ln1_b"], w["w_dw"], w["b_dw"], bufs.norm, Gh, Gw, R, 1e-6)
+    else:
+        ops.ln_dwconv(bufs.act, w["ln1_g"], w["ln1_b"], w["w_dw"], w["b_dw"], bufs.norm, Gh, Gw, R, 1e-6, stats=dw_stats)
     ops.gemm(n2, w["w_pw"], a2, bias=w["b_pw"], act=act_name, residual=a2, pass_rows=pr, stats_out=st)
     xin = a2
     if not fold:
