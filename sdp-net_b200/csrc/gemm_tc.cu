@@ -43,7 +43,9 @@ __host__ __device__ constexpr uint32_t tmem_cols_for(int bn) {
 template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ CUtensorMap tmO, const Epilogue epi, const int K, const int vec_ok) {
+                    const __grid_constant__ CUtensorMap tmO, const Epilogue epi, const int K, const int flags) {
+  const int vec_ok = flags & 1;
+  const bool nofeed = (flags & 2) != 0;   // SDP_GEMM_NOFEED=1 (diagnostic): no TMA loads, MMAs run on stale shared memory
   using L = SmemLayout<BN, STAGES, CG>;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
@@ -104,7 +106,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    // (the whole warp walks the loop so that the stage / phase counters stay warp-uniform; lane 0 issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
@@ -113,56 +116,66 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
-          if constexpr (CG == 1) {
-            mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
-            tma_load_2d(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
-            tma_load_2d(sa + L::A_BYTES, &tmW, full_bar(stage), kb * BLOCK_K, n0);
-          } else {
-            // both CTAs' bytes complete on the LEADER's full barrier; only the leader arms it
-            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
-            tma_load_2d_2sm(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
-            tma_load_2d_2sm(sa + L::A_BYTES, &tmW, full_bar(stage), kb * BLOCK_K, n0);
+          if (lane == 0) {
+            if (nofeed) {
+              if (rank == 0) mbar_arrive(full_bar(stage));
+            } else if constexpr (CG == 1) {
+              mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+              tma_load_2d(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
+              tma_load_2d(sa + L::A_BYTES, &tmW, full_bar(stage), kb * BLOCK_K, n0);
+            } else {
+              // both CTAs' bytes complete on the LEADER's full barrier; only the leader arms it
+              if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+              tma_load_2d_2sm(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
+              tma_load_2d_2sm(sa + L::A_BYTES, &tmW, full_bar(stage), kb * BLOCK_K, n0);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
+    // The whole warp walks the loops (stage / phase / tile counters stay warp-uniform, so descriptors are built on
+    // the uniform datapath); one lane issues.  Descriptor low words carry the address, high words are constant.
     constexpr uint32_t idesc = make_idesc(TILE_M, BN);
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      if (lane == 0 && rank == 0) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);       // epilogue has drained this accumulator
+    if (rank == 0) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);         // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);             // TMA bytes have landed
+          mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
           tc_fence_after();
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
-          const uint64_t adesc = make_smem_desc(sa);
-          const uint64_t bdesc = make_smem_desc(sa + L::A_BYTES);
+          const uint32_t a_lo = ((sa & 0x3FFFF) >> 4) | (1u << 16);
+          const uint32_t b_lo = (((sa + L::A_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+          if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 32 bytes (16 bf16) inside the 128B swizzle atom: +2 in the >>4 address field
-            if constexpr (CG == 1) tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            else tc_mma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 32 bytes (16 bf16) inside the 128B swizzle atom: +2 in the >>4 address field
+              if constexpr (CG == 1) tc_mma_bf16_w(d_tmem, a_lo + 2 * k, b_lo + 2 * k, DESC_HI, idesc, (kb | k) != 0);
+              else tc_mma_bf16_2sm_w(d_tmem, a_lo + 2 * k, b_lo + 2 * k, DESC_HI, idesc, (kb | k) != 0);
+            }
+            if constexpr (CG == 1) {
+              tc_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
+              if (kb == num_kb - 1) tc_commit(tfull_bar(acc));
+            } else {                                       // same barriers in both CTAs of the pair
+              tc_commit_2sm(empty_bar(stage));
+              if (kb == num_kb - 1) tc_commit_2sm(tfull_bar(acc));
+            }
           }
-          if constexpr (CG == 1) {
-            tc_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
-            if (kb == num_kb - 1) tc_commit(tfull_bar(acc));
-          } else {                                       // same barriers in both CTAs of the pair
-            tc_commit_2sm(empty_bar(stage));
-            if (kb == num_kb - 1) tc_commit_2sm(tfull_bar(acc));
-          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      __syncwarp();
     }
   } else {
     // ================= epilogue =================
@@ -540,7 +553,8 @@ static int launch_tc2(const CUtensorMap &ta, const CUtensorMap &tw, const CUtens
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG > 1 ? 1 : 0;
-  SDP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw, to, e, K, epilogue_vec_ok(e) ? 1 : 0));
+  static const int nofeed = [] { const char *v = getenv("SDP_GEMM_NOFEED"); return (v && v[0] == '1') ? 2 : 0; }();
+  SDP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw, to, e, K, (epilogue_vec_ok(e) ? 1 : 0) | nofeed));
   SDP_LAUNCH_OK();
   return 0;
 }
