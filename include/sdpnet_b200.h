@@ -160,6 +160,13 @@ int sdp_ln_dwconv_slab_ok(int Gh, int Gw, int C, int k, int dtype);
 int sdp_ln_dwconv_slab(const void *act, float *token_stats, const float *gamma, const float *beta,
                        const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int k,
                        int R, float eps, void *stream);
+/* Same, with the statistics taken from the GEMM that produced `act` instead of a pass over `act`: producer_stats =
+ * that GEMM's stats_out buffer ((sum, sumsq) column parts, row index b * S + R + t, parts ==
+ * sdp_gemm_stats_parts(C)); a small kernel turns them into (mean, rstd) in `token_stats` (scratch as above, must
+ * not alias producer_stats).  producer_stats == NULL behaves like sdp_ln_dwconv_slab. */
+int sdp_ln_dwconv_slab_stats(const void *act, const float *producer_stats, int parts, float *token_stats,
+                             const float *gamma, const float *beta, const float *wdw, const float *bdw,
+                             void *out, int B, int Gh, int Gw, int C, int k, int R, float eps, void *stream);
 
 /* Fused QK-LayerNorm + softmax attention (layers.py:282-300): qkv [B, S, 3C] with column
  * blocks q | k | v, each [h, d]; q/k get a per-head LayerNorm(d) (eps, affine) when

@@ -129,6 +129,29 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+// NV values at once: the switch sits outside the (unrolled) element loop, so a run-time activation costs one
+// branch per chunk instead of a jump table per element.
+template <int NV, bool EXACT>
+__device__ __forceinline__ void apply_act_vec(float *v, int act) {
+  switch (act) {
+    case SDP_ACT_NONE: break;
+#define SDP_ACT_CASE(ID)                                                \
+    case ID:                                                            \
+      _Pragma("unroll") for (int j = 0; j < NV; ++j) v[j] = apply_act<EXACT>(v[j], ID); \
+      break;
+    SDP_ACT_CASE(SDP_ACT_RELU)
+    SDP_ACT_CASE(SDP_ACT_GELU)
+    SDP_ACT_CASE(SDP_ACT_GELU_TANH)
+    SDP_ACT_CASE(SDP_ACT_TANH)
+    SDP_ACT_CASE(SDP_ACT_SIGMOID)
+    SDP_ACT_CASE(SDP_ACT_LEAKY_RELU)
+    SDP_ACT_CASE(SDP_ACT_SELU)
+    SDP_ACT_CASE(SDP_ACT_KELU)
+#undef SDP_ACT_CASE
+    default: break;
+  }
+}
+
 // ---- GEMM epilogue description (shared by the tcgen05 and the CUDA-core GEMM) -----------
 struct Epilogue {
   const float *bias;
@@ -191,8 +214,7 @@ __device__ __forceinline__ void epilogue_math(const Epilogue &e, const RowMap &m
     }
   }
   if (e.residual == nullptr || !e.res_first) {
-#pragma unroll
-    for (int j = 0; j < NV; ++j) v[j] = apply_act<EXACT>(v[j], act);
+    apply_act_vec<NV, EXACT>(v, act);
   }
   if (e.residual) {
     if (e.res_dtype == SDP_BF16) {
@@ -227,8 +249,7 @@ __device__ __forceinline__ void epilogue_math(const Epilogue &e, const RowMap &m
       }
     }
     if (e.res_first) {
-#pragma unroll
-      for (int j = 0; j < NV; ++j) v[j] = apply_act<EXACT>(v[j], act);
+      apply_act_vec<NV, EXACT>(v, act);
     }
   }
 }
@@ -249,8 +270,7 @@ __device__ __forceinline__ void epilogue_math_preres(const Epilogue &e, int c0, 
         v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
     }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act<false>(v[j], act);
+    apply_act_vec<32, false>(v, act);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {

@@ -98,6 +98,24 @@ token_stats_kernel(const bf16 *__restrict__ act, float2 *__restrict__ stats, lon
   if (lane == 0) stats[row] = make_float2(mean, 1.0f / sqrtf(q / (float)C + eps));
 }
 
+// (mean, rstd) of the spatial tokens from the (sum, sumsq) column parts a producer GEMM wrote for every row of the
+// [B*S, C] activation (row b*S + R + t  ->  compact index b*Tn + t).
+__global__ void __launch_bounds__(256)
+token_stats_from_parts_kernel(const float2 *__restrict__ parts_in, float2 *__restrict__ stats, long long rows, int Tn,
+                              int R, int parts, int C, float eps) {
+  const long long row = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (row >= rows) return;
+  const float2 *p = parts_in + ((row / Tn) * (R + Tn) + R + row % Tn) * parts;
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int i = 0; i < parts; ++i) {
+    const float2 v = __ldg(p + i);
+    s1 += v.x;
+    s2 += v.y;
+  }
+  const float mean = s1 / (float)C;
+  stats[row] = make_float2(mean, 1.0f / sqrtf(fmaxf(s2 / (float)C - mean * mean, 0.0f) + eps));
+}
+
 template <int KS>
 struct DsLayout {
   static constexpr int ROWS = 16 + KS - 1;
@@ -271,14 +289,18 @@ static int num_sms_ds() {
 }
 
 template <int KS>
-static int launch_slab(const void *act, float *token_stats, const float *gamma, const float *beta, const float *wdw,
-                       const float *bdw, void *out, int B, int Gh, int Gw, int C, int R, float eps, cudaStream_t st) {
+static int launch_slab(const void *act, const float *producer, int parts, float *token_stats, const float *gamma,
+                       const float *beta, const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int R,
+                       float eps, cudaStream_t st) {
   const int Tn = Gh * Gw, S = R + Tn;
   const long long rows = (long long)B * Tn;
   (void)S;
   const unsigned sblocks = (unsigned)((rows + 7) / 8);
   float2 *ts = reinterpret_cast<float2 *>(token_stats);
-  if (C <= 256) token_stats_kernel<1><<<sblocks, 256, 0, st>>>((const bf16 *)act, ts, rows, Tn, R, C, eps);
+  if (producer != nullptr && parts > 0)
+    token_stats_from_parts_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2 *>(producer), ts, rows,
+                                                                                    Tn, R, parts, C, eps);
+  else if (C <= 256) token_stats_kernel<1><<<sblocks, 256, 0, st>>>((const bf16 *)act, ts, rows, Tn, R, C, eps);
   else if (C <= 512) token_stats_kernel<2><<<sblocks, 256, 0, st>>>((const bf16 *)act, ts, rows, Tn, R, C, eps);
   else if (C <= 768) token_stats_kernel<3><<<sblocks, 256, 0, st>>>((const bf16 *)act, ts, rows, Tn, R, C, eps);
   else if (C <= 1024) token_stats_kernel<4><<<sblocks, 256, 0, st>>>((const bf16 *)act, ts, rows, Tn, R, C, eps);
@@ -313,18 +335,26 @@ extern "C" int sdp_ln_dwconv_slab_ok(int Gh, int Gw, int C, int k, int dtype) {
          C % DS_CH == 0 && C <= 2048;
 }
 
-extern "C" int sdp_ln_dwconv_slab(const void *act, float *token_stats, const float *gamma, const float *beta,
-                                  const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int k,
-                                  int R, float eps, void *stream) {
+extern "C" int sdp_ln_dwconv_slab_stats(const void *act, const float *producer_stats, int parts, float *token_stats,
+                                        const float *gamma, const float *beta, const float *wdw, const float *bdw,
+                                        void *out, int B, int Gh, int Gw, int C, int k, int R, float eps, void *stream) {
   SDP_CHECK(act && token_stats && gamma && beta && wdw && out, "sdp_ln_dwconv_slab: null pointer");
   SDP_CHECK(sdp_ln_dwconv_slab_ok(Gh, Gw, C, k, SDP_BF16), "sdp_ln_dwconv_slab: shape not covered (ask sdp_ln_dwconv_slab_ok)");
   SDP_CHECK(B > 0 && R >= 0, "sdp_ln_dwconv_slab: bad sizes");
+  SDP_CHECK(producer_stats == nullptr || parts > 0, "sdp_ln_dwconv_slab: producer statistics need parts > 0");
+  SDP_CHECK(producer_stats != token_stats, "sdp_ln_dwconv_slab: producer_stats and token_stats must not alias");
   SDP_CHECK(act != out, "sdp_ln_dwconv_slab: must not run in place (spatial neighbours are read)");
   SDP_CHECK((reinterpret_cast<uintptr_t>(act) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                (reinterpret_cast<uintptr_t>(token_stats) & 15) == 0,
+                (reinterpret_cast<uintptr_t>(token_stats) & 15) == 0 && (reinterpret_cast<uintptr_t>(producer_stats) & 7) == 0,
             "sdp_ln_dwconv_slab: act, out and token_stats must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (k == 7) return launch_slab<7>(act, token_stats, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
-  if (k == 5) return launch_slab<5>(act, token_stats, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
-  return launch_slab<3>(act, token_stats, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+  if (k == 7) return launch_slab<7>(act, producer_stats, parts, token_stats, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+  if (k == 5) return launch_slab<5>(act, producer_stats, parts, token_stats, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+  return launch_slab<3>(act, producer_stats, parts, token_stats, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
+}
+
+extern "C" int sdp_ln_dwconv_slab(const void *act, float *token_stats, const float *gamma, const float *beta,
+                                  const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int k,
+                                  int R, float eps, void *stream) {
+  return sdp_ln_dwconv_slab_stats(act, nullptr, 0, token_stats, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, k, R, eps, stream);
 }

@@ -43,7 +43,9 @@ struct Ctx {
   const sdp_model_desc *m;
   const sdp_workspace *ws;
   int B, S, T, R, Gh, Gw;
-  int parts;       // column parts of the row-statistics buffer (ln_fold)
+  int parts;       // column parts of the row-statistics buffer (ln_fold, or producer statistics for the mixers)
+  bool emit;       // mixer-feeding GEMMs write (sum, sumsq) parts for the tensor-core depthwise kernel
+  mutable bool stats_fresh;   // ws->stats currently describes ws->act
   void *st;
 };
 
@@ -102,8 +104,9 @@ int encoder(const Ctx &c, const sdp_encoder_weights &w) {
   Fold f2; f2.s = w.s_ff1; f2.t = w.t_ff1; f2.eps = 1e-5f;
   if (int rc = gemm(c, xin, C, w.w_ff1, C, fold ? nullptr : w.b_ff1, M, F, C, m.act, nullptr, c.ws->hidden, F, dt, false,
                     fold ? &f2 : nullptr)) return rc;
+  c.stats_fresh = fold || c.emit;
   return gemm(c, c.ws->hidden, F, w.w_ff2, F, w.b_ff2, M, C, F, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, false, nullptr,
-              fold);
+              fold || c.emit);
 }
 
 // layers.py:101-104
@@ -122,13 +125,19 @@ int mixer(const Ctx &c, const sdp_mixer_weights &w) {
   static const bool slab_on = [] { const char *e = getenv("SDP_DWCONV_SLAB"); return !(e && e[0] == '0'); }();
   if (!fold && slab_on && c.ws->stats != nullptr && sdp_ln_dwconv_slab_ok(c.Gh, c.Gw, C, m.conv_k, dt)) {
     // channel-stationary tensor-core kernel; the statistics workspace doubles as its (mean, rstd) scratch
-    if (int rc = sdp_ln_dwconv_slab(c.ws->act, c.ws->stats, w.ln1_g, w.ln1_b, w.w_dw, w.b_dw, c.ws->norm, c.B, c.Gh, c.Gw, C,
-                                    m.conv_k, c.R, 1e-6f, c.st)) return rc;
+    // statistics: the producer GEMM's parts when it wrote them, else a pass over act.  The (mean, rstd) scratch is
+    // the head of the QKV buffer, which is dead between two encoders.
+    const bool have = c.emit && c.stats_fresh;
+    float *scratch = have ? reinterpret_cast<float *>(c.ws->qkv) : c.ws->stats;
+    if (int rc = sdp_ln_dwconv_slab_stats(c.ws->act, have ? c.ws->stats : nullptr, have ? c.parts : 0, scratch, w.ln1_g,
+                                          w.ln1_b, w.w_dw, w.b_dw, c.ws->norm, c.B, c.Gh, c.Gw, C, m.conv_k, c.R, 1e-6f,
+                                          c.st)) return rc;
   } else if (int rc = sdp_ln_dwconv_stats(c.ws->act, dw_stats, dw_parts, w.ln1_g, w.ln1_b, w.w_dw, w.b_dw, c.ws->norm, c.B,
                                           c.Gh, c.Gw, C, m.conv_k, c.R, 1e-6f, dt, c.st)) {
     return rc;
   }
   if (int rc = gemm(c, c.ws->norm, C, w.w_pw, C, w.b_pw, M, C, C, m.act, c.ws->act, c.ws->act, C, dt, true, nullptr, fold)) return rc;
+  c.stats_fresh = fold;
   const void *xin = c.ws->act;
   if (!fold) {
     if (int rc = sdp_layernorm_rows(c.ws->act, C, w.ln2_g, w.ln2_b, c.ws->norm, C, M, C, 1e-6f, dt, c.st)) return rc;
@@ -137,8 +146,9 @@ int mixer(const Ctx &c, const sdp_mixer_weights &w) {
   Fold f; f.s = w.s_mlp1; f.t = w.t_mlp1; f.eps = 1e-6f;
   if (int rc = gemm(c, xin, C, w.w_mlp1, C, fold ? nullptr : w.b_mlp1, M, 4 * C, C, m.act, nullptr, c.ws->hidden, 4 * C, dt,
                     false, fold ? &f : nullptr)) return rc;
+  c.stats_fresh = fold || c.emit;
   return gemm(c, c.ws->hidden, 4 * C, w.w_mlp2, 4 * C, w.b_mlp2, M, C, 4 * C, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, true,
-              nullptr, fold);
+              nullptr, fold || c.emit);
 }
 
 }  // namespace
@@ -155,7 +165,12 @@ extern "C" int sdp_forward(const sdp_model_desc *m, const sdp_workspace *ws, con
   c.Gh = H / m->patch; c.Gw = W / m->patch;
   c.T = c.Gh * c.Gw; c.S = c.T + R;
   const int C = m->C, dt = m->dtype, Kc3 = 3 * m->patch * m->patch;
-  c.parts = m->ln_fold ? sdp_gemm_stats_parts(C, dt) : 0;
+  static const bool slab_env = [] { const char *e = getenv("SDP_DWCONV_SLAB"); return !(e && e[0] == '0'); }();
+  const int sparts = ws->stats != nullptr ? sdp_gemm_stats_parts(C, dt) : 0;
+  c.emit = !m->ln_fold && slab_env && sparts > 0 && sparts % 2 == 0 && sparts <= 16 && m->conv_block_num > 0 &&
+           sdp_ln_dwconv_slab_ok(c.Gh, c.Gw, C, m->conv_k, dt);
+  c.stats_fresh = false;
+  c.parts = (m->ln_fold || c.emit) ? sparts : 0;
   SDP_CHECK(!m->ln_fold || (dt == SDP_BF16 && c.parts > 0 && ws->stats != nullptr),
             "sdp_forward: ln_fold needs bf16 and a statistics workspace");
 

@@ -261,8 +261,12 @@ class Buffers:
         # row statistics (sum, sumsq): one part from sdp_row_stats for the tensor-core depthwise conv, or the
         # producer GEMMs' column parts when the LayerNorms are folded
         self.fold = bool(getattr(pw, "ln_fold", False))
-        parts = ops.gemm_stats_parts(C_, dt) if self.fold else 1
+        parts = max(1, ops.gemm_stats_parts(C_, dt)) if dt == torch.bfloat16 else 1
         self.stats = torch.zeros(B * S, parts, 2, dtype=torch.float32, device=dev) if dt == torch.bfloat16 else None
+        # producer statistics for the tensor-core depthwise kernel: the GEMMs that feed a mixer write (sum, sumsq)
+        # parts (same choice as sdp_forward); stats_fresh says whether self.stats currently describes self.act
+        self.emit = False
+        self.stats_fresh = False
         self.logits = torch.empty(B, classes, dtype=torch.float32, device=dev)
 
     def nbytes(self) -> int:
@@ -298,7 +302,8 @@ def run_encoder(pw: Packer, w: dict, bufs: Buffers, act_name: Optional[str] = No
         ops.layernorm_rows(a2, w["norm2_w"], w["norm2_b"], n2, 1e-5)
     ops.gemm(xin, w["w_ff1"], hid, bias=None if fold else w["b_ff1"], act=act_name or pw.act,
              ln_fold=(st, 1e-5, w["s_ff1"], w["t_ff1"]) if fold else None)
-    ops.gemm(hid, w["w_ff2"], a2, bias=w["b_ff2"], residual=a2, stats_out=st)
+    ops.gemm(hid, w["w_ff2"], a2, bias=w["b_ff2"], residual=a2, stats_out=bufs.stats if (fold or bufs.emit) else None)
+    bufs.stats_fresh = bool(fold or bufs.emit)
 
 
 def run_mixer(pw: Packer, w: dict, bufs: Buffers, Gh: int, Gw: int, act_name: Optional[str] = None) -> None:
@@ -319,17 +324,23 @@ def run_mixer(pw: Packer, w: dict, bufs: Buffers, Gh: int, Gw: int, act_name: Op
     if (not fold and bufs.stats is not None and os.environ.get("SDP_DWCONV_SLAB", "1") != "0"
             and ops.ln_dwconv_slab_ok(Gh, Gw, C_, k_dw, pw.dtype)):
         # channel-stationary tensor-core kernel (same choice as sdp_forward); the statistics buffer is its scratch
-        ops.ln_dwconv_slab(bufs.act, bufs.stats.view(-1), w["ln1_g"], w["ln1_b"], w["w_dw"], w["b_dw"], bufs.norm, Gh, Gw, R, 1e-6)
+        have = bufs.emit and bufs.stats_fresh
+        scratch = bufs.qkv.view(-1).view(torch.float32) if have else bufs.stats.view(-1)   # qkv is dead between encoders
+        ops.ln_dwconv_slab(bufs.act, scratch, w["ln1_g"], w["ln1_b"], w["w_dw"], w["b_dw"], bufs.norm, Gh, Gw, R, 1e-6,
+                           producer_stats=bufs.stats if have else None)
     else:
         ops.ln_dwconv(bufs.act, w["ln1_g"], w["ln1_b"], w["w_dw"], w["b_dw"], bufs.norm, Gh, Gw, R, 1e-6, stats=dw_stats)
     ops.gemm(n2, w["w_pw"], a2, bias=w["b_pw"], act=act_name, residual=a2, pass_rows=pr, stats_out=st)
+    bufs.stats_fresh = bool(fold)
     xin = a2
     if not fold:
         ops.layernorm_rows(a2, w["ln2_g"], w["ln2_b"], n2, 1e-6)
         xin = n2
     ops.gemm(xin, w["w_mlp1"], hid, bias=None if fold else w["b_mlp1"], act=act_name,
              ln_fold=(st, 1e-6, w["s_mlp1"], w["t_mlp1"]) if fold else None)
-    ops.gemm(hid, w["w_mlp2"], a2, bias=w["b_mlp2"], residual=a2, pass_rows=pr, stats_out=st)
+    ops.gemm(hid, w["w_mlp2"], a2, bias=w["b_mlp2"], residual=a2, pass_rows=pr,
+             stats_out=bufs.stats if (fold or bufs.emit) else None)
+    bufs.stats_fresh = bool(fold or bufs.emit)
 
 
 class Engine:
@@ -443,6 +454,12 @@ class Engine:
         ops.gemm(bufs.im2col, pw.w_patch, bufs.act.view(B * S, C_), residual=pw.pos_table(Gh, Gw), res_first=True,
                  res_mod=T, act=pw.embed_act, seq_remap=(T, S, R), K=3 * p * p)
         ops.fill_registers(bufs.act, pw.reg_table(R))
+        k_dw = int(cfg["conv_kernel_size"]) if "conv_kernel_size" in cfg else 0
+        sparts = bufs.stats.shape[1] if bufs.stats is not None else 0
+        bufs.emit = bool(not bufs.fold and bufs.stats is not None and os.environ.get("SDP_DWCONV_SLAB", "1") != "0"
+                         and sparts > 1 and sparts % 2 == 0 and sparts <= 16 and int(cfg["conv_block_num"]) > 0
+                         and k_dw > 0 and ops.ln_dwconv_slab_ok(Gh, Gw, C_, k_dw, torch.bfloat16))
+        bufs.stats_fresh = False
         if bufs.fold:
             ops.row_stats(bufs.act, bufs.stats)
         note("embed")

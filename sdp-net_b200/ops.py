@@ -160,8 +160,10 @@ def ln_dwconv_slab_ok(Gh: int, Gw: int, Cc: int, k: int, dtype: torch.dtype) -> 
 
 def ln_dwconv_slab(act: torch.Tensor, token_stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
                    wdw: torch.Tensor, bdw: Optional[torch.Tensor], out: torch.Tensor, Gh: int, Gw: int, R: int,
-                   eps: float = 1e-6):
-    """Channel-stationary tensor-core variant of ln_dwconv; `token_stats` is fp32 scratch of >= 2*B*Gh*Gw elements."""
+                   eps: float = 1e-6, producer_stats: Optional[torch.Tensor] = None):
+    """Channel-stationary tensor-core variant of ln_dwconv; `token_stats` is fp32 scratch of >= 2*B*Gh*Gw elements.
+    `producer_stats` ([B*S, parts, 2] fp32, the stats_out of the GEMM that produced `act`) replaces the statistics
+    pass over `act`."""
     B, S, Cc = act.shape
     if S != R + Gh * Gw or not act.is_contiguous() or not out.is_contiguous():
         raise ValueError("ln_dwconv_slab: act must be contiguous [B, R + Gh*Gw, C]")
@@ -170,9 +172,15 @@ def ln_dwconv_slab(act: torch.Tensor, token_stats: torch.Tensor, gamma: torch.Te
         raise ValueError("ln_dwconv_slab: wdw must be tap-major [k*k, C]")
     if token_stats.dtype != torch.float32 or token_stats.numel() < 2 * B * Gh * Gw or not token_stats.is_contiguous():
         raise ValueError("ln_dwconv_slab: token_stats must be contiguous fp32 with >= 2*B*Gh*Gw elements")
-    L.check(L.lib().sdp_ln_dwconv_slab(_p(act), _p(token_stats), _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")),
-                                       _p(_f32(wdw, "wdw")), _p(_f32(bdw, "bdw")), _p(out), B, Gh, Gw, Cc, k, R,
-                                       float(eps), _stream()), "sdp_ln_dwconv_slab")
+    parts = 0
+    if producer_stats is not None:
+        if (producer_stats.dtype != torch.float32 or producer_stats.dim() != 3 or producer_stats.shape[0] != B * S
+                or producer_stats.shape[2] != 2 or not producer_stats.is_contiguous()):
+            raise ValueError("ln_dwconv_slab: producer_stats must be contiguous fp32 [B*S, parts, 2]")
+        parts = int(producer_stats.shape[1])
+    L.check(L.lib().sdp_ln_dwconv_slab_stats(_p(act), _p(producer_stats), parts, _p(token_stats), _p(_f32(gamma, "gamma")),
+                                             _p(_f32(beta, "beta")), _p(_f32(wdw, "wdw")), _p(_f32(bdw, "bdw")), _p(out),
+                                             B, Gh, Gw, Cc, k, R, float(eps), _stream()), "sdp_ln_dwconv_slab")
     return out
 
 

@@ -369,6 +369,19 @@ def test_ln_dwconv_slab(sdp, B, Gh, Gw, C, k, R, bias):
     assert (out[:, :R] == 0).all()
     assert torch.isfinite(out.float()).all()
     assert (out.float() - ref).abs().max() < 4e-2
+    # statistics in the producer-GEMM format: (sum, sumsq) column parts per row of the [B*S, C] activation
+    for parts in (2, 6):
+        stats = torch.zeros(B * (R + Gh * Gw), parts, 2, device="cuda")
+        xf = act.float().view(-1, C)
+        for p_, chunk in enumerate(xf.chunk(parts, dim=1)):
+            stats[:, p_, 0] = chunk.sum(1)
+            stats[:, p_, 1] = (chunk * chunk).sum(1)
+        out2 = torch.full_like(act, float("nan"))
+        scratch.fill_(float("nan"))
+        sdp.ops.ln_dwconv_slab(act, scratch, gamma, beta, wdw.reshape(C, k * k).t().contiguous(), bdw, out2, Gh, Gw, R,
+                               producer_stats=stats)
+        assert (out2[:, :R] == 0).all()
+        assert (out2.float() - ref).abs().max() < 4e-2
 
 
 # --------------------------------------------------------------------------------------------

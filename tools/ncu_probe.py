@@ -55,6 +55,11 @@ timed("ln_dwconv k7", lambda: ops.ln_dwconv(act, lw, lb, wdw, None, norm, G, G, 
 scratch = torch.empty(2 * B * T, device=dev)
 timed("ln_dwconv_slab k7", lambda: ops.ln_dwconv_slab(act, scratch, lw, lb, wdw, None, norm, G, G, R), flops=2 * B * T * C * k * k,
       nbytes=4 * B * T * C)
+pstats = torch.zeros(M, 6, 2, device=dev)
+pstats[:, :, 0] = (act.float().view(M, 6, C // 6).sum(-1))
+pstats[:, :, 1] = ((act.float().view(M, 6, C // 6) ** 2).sum(-1))
+timed("ln_dwconv_slab k7 (parts in)", lambda: ops.ln_dwconv_slab(act, scratch, lw, lb, wdw, None, norm, G, G, R, producer_stats=pstats),
+      flops=2 * B * T * C * k * k, nbytes=4 * B * T * C)
 timed("gemm qkv+headnorm 2304x768", lambda: ops.gemm(n2, w_qkv, qkv.view(M, 3 * C), headnorm=(d, C, 1e-5, qw, qb, qw, qb)),
       flops=2 * M * 3 * C * C)
 timed("gemm qkv plain 2304x768", lambda: ops.gemm(n2, w_qkv, qkv.view(M, 3 * C)), flops=2 * M * 3 * C * C)
