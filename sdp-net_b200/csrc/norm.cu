@@ -11,6 +11,8 @@ namespace sdp {
 template <typename T> struct Vec;
 template <> struct Vec<float> {
   static constexpr int N = 4;
+  using Raw = float4;
+  __device__ static void cvt(const float4 &u, float *v) { v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; }
   __device__ static void load(const float *p, float *v) {
     const float4 u = *reinterpret_cast<const float4 *>(p);
     v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
@@ -21,6 +23,14 @@ template <> struct Vec<float> {
 };
 template <> struct Vec<bf16> {
   static constexpr int N = 8;
+  using Raw = uint4;
+  __device__ static void cvt(const uint4 &u, float *v) {
+    float2 f;
+    f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+    f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+    f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+    f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+  }
   __device__ static void load(const bf16 *p, float *v) {
     const uint4 u = *reinterpret_cast<const uint4 *>(p);
     float2 f;
@@ -37,59 +47,77 @@ template <> struct Vec<bf16> {
   }
 };
 
+// Persistent: a warp walks rows with a grid stride and has the NEXT row's loads in flight while it reduces,
+// normalises and stores the current one (two rows of memory-level parallelism per warp, no block churn).
 template <typename T, int VPL>
 __global__ void __launch_bounds__(256)
 ln_rows_vec_kernel(const T *__restrict__ x, long long ldx, const float *__restrict__ w,
                    const float *__restrict__ b, T *__restrict__ out, long long ldo, int M, int C, float eps) {
   constexpr int EPV = Vec<T>::N;
+  using Raw = typename Vec<T>::Raw;
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int nvec = C / EPV;
-  const T *xr = x + (long long)row * ldx;
-  float v[VPL][EPV];
-  float s = 0.0f;
+  Raw cur[VPL], nxt[VPL];
+  auto load_row = [&](int r, Raw *dst) {
+    const Raw *xr = reinterpret_cast<const Raw *>(x + (long long)r * ldx);
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int iv = lane + 32 * i;
-    if (iv < nvec) {
-      Vec<T>::load(xr + iv * EPV, v[i]);
+    for (int i = 0; i < VPL; ++i)
+      if (lane + 32 * i < nvec) dst[i] = xr[lane + 32 * i];
+  };
+  load_row(row, cur);
+  while (true) {
+    const int next = row + nwarps;
+    if (next < M) load_row(next, nxt);
+    float v[VPL][EPV];
+    float s = 0.0f;
 #pragma unroll
-      for (int j = 0; j < EPV; ++j) s += v[i][j];
-    }
-  }
-  const float mean = warp_sum(s) / (float)C;
-  float q = 0.0f;
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + 32 * i < nvec) {
+        Vec<T>::cvt(cur[i], v[i]);
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    if (lane + 32 * i < nvec) {
-#pragma unroll
-      for (int j = 0; j < EPV; ++j) {
-        const float d = v[i][j] - mean;
-        q = fmaf(d, d, q);
+        for (int j = 0; j < EPV; ++j) s += v[i][j];
       }
     }
-  }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
-  T *orow = out + (long long)row * ldo;
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.0f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int iv = lane + 32 * i;
-    if (iv < nvec) {
-      float y[EPV];
-      const int c0 = iv * EPV;
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + 32 * i < nvec) {
 #pragma unroll
-      for (int j = 0; j < EPV; j += 4) {          // affine parameters as 128-bit loads (L1/L2 resident)
-        float4 wv = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (w) wv = __ldg(reinterpret_cast<const float4 *>(w + c0 + j));
-        if (b) bv = __ldg(reinterpret_cast<const float4 *>(b + c0 + j));
-        y[j] = (v[i][j] - mean) * rstd * wv.x + bv.x;
-        y[j + 1] = (v[i][j + 1] - mean) * rstd * wv.y + bv.y;
-        y[j + 2] = (v[i][j + 2] - mean) * rstd * wv.z + bv.z;
-        y[j + 3] = (v[i][j + 3] - mean) * rstd * wv.w + bv.w;
+        for (int j = 0; j < EPV; ++j) {
+          const float d = v[i][j] - mean;
+          q = fmaf(d, d, q);
+        }
       }
-      Vec<T>::store(orow + iv * EPV, y);
     }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+    T *orow = out + (long long)row * ldo;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int iv = lane + 32 * i;
+      if (iv < nvec) {
+        float y[EPV];
+        const int c0 = iv * EPV;
+#pragma unroll
+        for (int j = 0; j < EPV; j += 4) {          // affine parameters as 128-bit loads (L1/L2 resident)
+          float4 wv = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (w) wv = __ldg(reinterpret_cast<const float4 *>(w + c0 + j));
+          if (b) bv = __ldg(reinterpret_cast<const float4 *>(b + c0 + j));
+          y[j] = (v[i][j] - mean) * rstd * wv.x + bv.x;
+          y[j + 1] = (v[i][j + 1] - mean) * rstd * wv.y + bv.y;
+          y[j + 2] = (v[i][j + 2] - mean) * rstd * wv.z + bv.z;
+          y[j + 3] = (v[i][j + 3] - mean) * rstd * wv.w + bv.w;
+        }
+        Vec<T>::store(orow + iv * EPV, y);
+      }
+    }
+    if (next >= M) break;
+    row = next;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) cur[i] = nxt[i];
   }
 }
 
@@ -127,14 +155,28 @@ static int launch_ln_rows(const void *x, long long ldx, const float *w, const fl
   const T *xp = reinterpret_cast<const T *>(x);
   T *op = reinterpret_cast<T *>(out);
   const int wpb = 8;
-  const dim3 grid((M + wpb - 1) / wpb), block(32 * wpb);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int full = (M + wpb - 1) / wpb;
+  const dim3 grid(full), block(32 * wpb);
+  auto persistent_grid = [&](const void *kern) {         // one resident wave of the vector kernel
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * wpb, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    const int g = per_sm * sms;
+    return dim3(full < g ? full : g);
+  };
   const bool vec = C % EPV == 0 && (ldx * sizeof(T)) % 16 == 0 && (ldo * sizeof(T)) % 16 == 0 &&
                    (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0;
   const int need = vec ? (C / EPV + 31) / 32 : 99;
 #define LN_CASE(V)                                                                             \
   if (need <= V) {                                                                             \
-    ln_rows_vec_kernel<T, V><<<grid, block, 0, st>>>(xp, ldx, w, b, op, ldo, M, C, eps);       \
+    static const dim3 pg = persistent_grid(reinterpret_cast<const void *>(&ln_rows_vec_kernel<T, V>));   \
+    ln_rows_vec_kernel<T, V><<<full < (int)pg.x ? dim3(full) : pg, block, 0, st>>>(xp, ldx, w, b, op, ldo, M, C, eps); \
     SDP_LAUNCH_OK();                                                                           \
     return 0;                                                                                  \
   }
