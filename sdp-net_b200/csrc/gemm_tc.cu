@@ -17,8 +17,8 @@ namespace sdp {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;      // 64 bf16 = 128 bytes = one swizzle-128B atom row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 8;          // default: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (320 threads)
+constexpr int EPI_WARPS_WIDE = 16;    // heavy epilogues (GELU): four warps per TMEM lane quadrant (576 threads)
 
 template <int BN, int STAGES, int CG = 1>
 struct SmemLayout {
@@ -26,7 +26,7 @@ struct SmemLayout {
   static constexpr int B_BYTES = (BN / CG) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_OFF = STAGES * STAGE_BYTES;              // epilogue staging: 8 warps x 2 x [32 rows x 64 B]
-  static constexpr int OUT_BYTES = EPI_WARPS * 2 * 2048;
+  static constexpr int OUT_BYTES = 32768;                           // shared by 8 warps x 2 slots or 16 warps x 1 slot
   static constexpr int BAR_OFF = OUT_OFF + OUT_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
   static_assert(TOTAL <= 232448, "shared memory budget exceeded");
@@ -40,8 +40,8 @@ __host__ __device__ constexpr uint32_t tmem_cols_for(int bn) {
 // 32-column chunk, 64B-swizzled, double-buffered per warp) instead of 16-byte-per-row global stores.
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: launched as clusters of 2 (one TPC); the pair owns a
 // 256 x BN tile, B traffic from L2 halves and the smem ring gets deeper for the same capacity.
-template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1, int EW = EPI_WARPS>
+__global__ void __launch_bounds__((2 + EW) * 32, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO, const Epilogue epi, const int K, const int flags) {
   const int vec_ok = flags & 1;
@@ -73,7 +73,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), CG * EPI_WARPS);   // one arrive per epilogue warp (of both CTAs when paired)
+      mbar_init(tempty_bar(a), CG * EW);   // one arrive per epilogue warp (of both CTAs when paired)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -182,17 +182,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Two warps per TMEM lane quadrant: warps 2..5 take the low half of the tile's columns,
     // warps 6..9 the high half.  One thread = one output row.
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;          // which share of the tile's columns (EW / 4 shares)
+    constexpr int PARTS = EW / 4;
     constexpr int UNIT = HN > 0 ? HN : 32;     // columns finished together (whole heads with head-norm)
     constexpr int UNITS = BN / UNIT;
-    constexpr int U_LO = (UNITS + 1) / 2;      // units of the low half
-    const int u_begin = half == 0 ? 0 : U_LO, u_end = half == 0 ? U_LO : UNITS;
-    const uint32_t stage_base = smem_base + L::OUT_OFF + static_cast<uint32_t>(warp - 2) * 4096;
-    uint32_t cc = 0;                           // chunks this warp has staged (slot = cc & 1)
+    static_assert(PARTS == 2 || (HN == 0 && UNITS % PARTS == 0), "wide epilogue: plain 32-column units only");
+    const int u_begin = (half * UNITS + PARTS - 1) / PARTS, u_end = ((half + 1) * UNITS + PARTS - 1) / PARTS;
+    constexpr int SLOTS = 16 / EW;             // 2 KB staging slots per warp (8 warps: double-buffered)
+    const uint32_t stage_base = smem_base + L::OUT_OFF + static_cast<uint32_t>(warp - 2) * (SLOTS * 2048);
+    uint32_t cc = 0;                           // chunks this warp has staged (slot = cc % SLOTS)
     // in-place bf16 residual (the common case): each chunk's residual is fetched one chunk ahead
     const bool res_fast = STAGED && epi.residual != nullptr && epi.res_dtype == SDP_BF16 && !epi.res_first &&
                           epi.res_mod == 0 && vec_ok != 0;
-    const int col_end = (half == 0 ? U_LO : UNITS) * UNIT;   // end of this warp's column range inside the tile
+    const int col_end = u_end * UNIT;          // end of this warp's column range inside the tile
     int it = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
       const int acc = it & 1;
@@ -316,9 +318,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               } else {
                 epilogue_passthrough<32>(epi, rm, col, v, vec_ok != 0);
               }
-              const uint32_t slot = stage_base + ((cc & 1) << 11);
-              if (cc >= 2) {                     // the store issued from this slot two chunks ago has read it
-                if (lane == 0) bulk_wait_read<1>();
+              const uint32_t slot = stage_base + ((cc & (SLOTS - 1)) << 11);
+              if (cc >= SLOTS) {                 // the store last issued from this slot has read it
+                if (lane == 0) bulk_wait_read<SLOTS - 1>();
                 __syncwarp();
               }
               const uint32_t rowp = slot + lane * 64;
@@ -353,7 +355,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       if (STAGED && epi.stats_out != nullptr && rm.live) {
-        const int part = (tile % n_tiles) * 2 + half;
+        const int part = (tile % n_tiles) * PARTS + half;
         *reinterpret_cast<float2 *>(epi.stats_out + (rm.ro * epi.stats_parts + part) * 2) = make_float2(st1, st2);
       }
       tc_fence_before();
@@ -528,11 +530,11 @@ static bool staged_ok(const Epilogue &e) {
          (e.ldo * 2) % 16 == 0 && (e.pass_seq == 0 || e.residual != nullptr);
 }
 
-template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1>
+template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1, int EW = EPI_WARPS>
 static int launch_tc2(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &to, const Epilogue &e, int K,
                       cudaStream_t st) {
   using L = SmemLayout<BN, STAGES, CG>;
-  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT, HN, STAGED, CG>;
+  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT, HN, STAGED, CG, EW>;
   static bool configured = false;
   if (!configured) {
     SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -543,7 +545,7 @@ static int launch_tc2(const CUtensorMap &ta, const CUtensorMap &tw, const CUtens
   const int grid = CG * (units < slots ? units : slots);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3((2 + EW) * 32);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -580,6 +582,14 @@ static int launch_tc(const sdp_gemm_args &a, const CUtensorMap &ta, const Epilog
       if (pref != 1 && e.M > BLOCK_M && (pref == 2 || e.M >= 8 * BLOCK_M)) {
         constexpr int ST2 = (STAGES * (BLOCK_M + BN)) / (BLOCK_M + BN / 2);   // same bytes, deeper ring
         if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, BN / 2, &tw)) return rc;
+        if constexpr (ACT == SDP_ACT_GELU && HN == 0 && BN == 256) {
+          // SDP_GEMM_WIDE_EPI=1 (experiment, measured slower: 1.40 vs 1.19 ms on the XL C->4C GEMM): four epilogue
+          // warps per scheduler instead of two; they share the same 32 KB of staging, so each has a single slot
+          // and waits for its previous TMA store.  The statistics producer always keeps the 8-warp kernel.
+          static const bool wide = [] { const char *v = getenv("SDP_GEMM_WIDE_EPI"); return v && v[0] == '1'; }();
+          if (wide && e.stats_out == nullptr && e.ln_stats == nullptr)
+            return launch_tc2<BN, ST2, ACT, HN, true, 2, EPI_WARPS_WIDE>(ta, tw, to, e, a.K, st);
+        }
         return launch_tc2<BN, ST2, ACT, HN, true, 2>(ta, tw, to, e, a.K, st);
       }
     }
