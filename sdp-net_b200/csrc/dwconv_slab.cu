@@ -1,5 +1,5 @@
-// Channel-stationary tensor-core depthwise conv + channel LayerNorm (bf16, grids G x 8 / G x 16 with G <= 16,
-// k in {3,5,7}).  Reference: layer_norm_1 + conv2d[0] of ConvMixer, layers.py:102 (:12-24 + :73-78).
+// Channel-stationary tensor-core depthwise conv + channel LayerNorm (bf16, grids up to 16 x 16 with an even number
+// of tokens, k in {3,5,7}).  Reference: layer_norm_1 + conv2d[0] of ConvMixer, layers.py:102 (:12-24 + :73-78).
 //
 // For one channel the k x k 'same' conv of the zero-haloed plane P is, per tap row dy and per block of eight
 // output columns x0..x0+7, one 16 x 8 x 16 matrix product
@@ -121,18 +121,19 @@ struct DsLayout {
   static constexpr int ROWS = 16 + KS - 1;
   int raw, stat, planes, otile, total;
   int plane_bytes;
-  __host__ __device__ explicit DsLayout(int Tn) {
+  __host__ __device__ explicit DsLayout(int Gh, int Tn) {
+    const int TP = Gh * 16;                                 // token slots of the raw / out tiles: grid rows padded to 16
     // plane stride: a multiple of 16 bytes whose word count is 12 (mod 32): the eight channels a transposing
     // store touches at once then land in eight different bank quads
     int pb = (ROWS * DS_PROW + 15) / 16 * 16;
     while ((pb / 4) % 32 != 12) pb += 16;
     plane_bytes = pb;
-    raw = 0;                                                // [2][Tn][64 B]
-    stat = raw + 2 * Tn * DS_RAWP;                          // [2][Tn] float2 (mean, rstd)
-    planes = stat + 2 * Tn * 8;                             // [32][plane_bytes], zero halo
+    raw = 0;                                                // [2][TP][64 B]
+    stat = raw + 2 * TP * DS_RAWP;                          // [2][Tn] float2 (mean, rstd)
+    planes = stat + 2 * ((Tn * 8 + 15) / 16 * 16);          // [32][plane_bytes], zero halo
     planes = (planes + 15) / 16 * 16;
-    otile = planes + DS_CH * pb;                            // [Tn][80 B]
-    total = otile + Tn * DS_OUTP;
+    otile = planes + DS_CH * pb;                            // [TP][80 B]
+    total = otile + TP * DS_OUTP;
   }
 };
 
@@ -144,8 +145,9 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
   constexpr int lo = (KS - 1) / 2;
   extern __shared__ __align__(16) uint8_t ds_smem[];
   const int Tn = Gh * Gw, S = R + Tn;
-  const DsLayout<KS> L(Tn);
+  const DsLayout<KS> L(Gh, Tn);
   const int PB = L.plane_bytes;
+  const int TP = Gh * 16, SBUF = (Tn * 8 + 15) / 16 * 16;
   const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(ds_smem));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
@@ -155,12 +157,14 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
 
   auto prefetch = [&](int b, int buf) {    // the [Tn, 32-channel] slice of image b (64 B per token) + its statistics
     const bf16 *src = act + ((long long)b * S + R) * C + c0;
-    for (int i = tid; i < Tn * 4; i += DS_THREADS)
-      ds_cp_async16(sbase + L.raw + buf * Tn * DS_RAWP + (i >> 2) * DS_RAWP + (((i & 3) ^ ((i >> 3) & 3)) << 4),
-                    src + (long long)(i >> 2) * C + (i & 3) * 8);
-    const float2 *ss = stats + (long long)b * Tn;
+    for (int i = tid; i < Tn * 4; i += DS_THREADS) {
+      const int t = i >> 2, slot = (t / Gw) * 16 + t % Gw;   // token (y, x) sits in slot 16 y + x
+      ds_cp_async16(sbase + L.raw + buf * TP * DS_RAWP + slot * DS_RAWP + (((i & 3) ^ ((slot >> 1) & 3)) << 4),
+                    src + (long long)t * C + (i & 3) * 8);
+    }
+    const float2 *ss = stats + (long long)b * Tn;            // Tn is even: 16-byte aligned for every image
     for (int i = tid; i < Tn / 2; i += DS_THREADS)
-      ds_cp_async16(sbase + L.stat + buf * Tn * 8 + i * 16, ss + 2 * i);
+      ds_cp_async16(sbase + L.stat + buf * SBUF + i * 16, ss + 2 * i);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   prefetch(b_begin, 0);
@@ -206,20 +210,22 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
     if (b + 1 < b_end) prefetch(b + 1, buf ^ 1);
 
     // ---- normalise + transpose: [token][channel] rows -> per-channel planes (two tokens per 32-bit store) ----
-    const uint32_t raw_addr = sbase + L.raw + buf * Tn * DS_RAWP;
-    const float2 *s_stat = reinterpret_cast<const float2 *>(ds_smem + L.stat + buf * Tn * 8);
-    for (int t0 = warp * 8; t0 < Tn; t0 += 8 * (DS_THREADS / 32)) {
+    const uint32_t raw_addr = sbase + L.raw + buf * TP * DS_RAWP;
+    const float2 *s_stat = reinterpret_cast<const float2 *>(ds_smem + L.stat + buf * SBUF);
+    for (int t0 = warp * 8; t0 < TP; t0 += 8 * (DS_THREADS / 32)) {      // eight slots of one grid row
+      const int y = t0 >> 4, x = (t0 & 15) + 2 * q;
+      if ((t0 & 15) >= Gw) continue;                          // the padded half of a narrow row (warp-uniform)
       uint32_t r4[4];
       ds_ldmatrix_x4_trans(raw_addr + (t0 + (lane & 7)) * DS_RAWP + (((lane >> 3) ^ ((lane >> 1) & 3)) << 4), r4);
-      const float2 st0 = s_stat[t0 + 2 * q], st1 = s_stat[t0 + 2 * q + 1];
-      const int y = t0 / Gw, x = t0 % Gw + 2 * q;
+      const bool in0 = x < Gw, in1 = x + 1 < Gw;              // slots past the row end hold stale bytes
+      const float2 st0 = s_stat[in0 ? y * Gw + x : 0], st1 = s_stat[in1 ? y * Gw + x + 1 : 0];
       const uint32_t cell = planes_addr + (y + lo) * DS_PROW + (DS_HL + x) * 2;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const float v0 = (__uint_as_float(r4[m] << 16) - st0.x) * st0.y;
         const float v1 = (__uint_as_float(r4[m] & 0xffff0000u) - st1.x) * st1.y;
-        const uint32_t pk = pack_bf16x2(fmaf(v0, gm[m], bt[m]), fmaf(v1, gm[m], bt[m]));
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(cell + (8 * m + g) * PB), "r"(pk) : "memory");
+        const uint32_t pk = pack_bf16x2(in0 ? fmaf(v0, gm[m], bt[m]) : 0.0f, in1 ? fmaf(v1, gm[m], bt[m]) : 0.0f);
+        if (in0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(cell + (8 * m + g) * PB), "r"(pk) : "memory");   // halo stays 0
       }
     }
     __syncthreads();                       // planes of image b complete
@@ -251,12 +257,12 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int y = g + 8 * hh, x = 8 * n + 2 * q;
-        if (y < Gh && x < Gw) {
+        if (y < Gh && x < Gw) {                               // (a slot past a narrow row's end is never read back)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const uint32_t lo2 = pack_bf16x2(acc[0][n][2 * hh + e], acc[1][n][2 * hh + e]);
             const uint32_t hi2 = pack_bf16x2(acc[2][n][2 * hh + e], acc[3][n][2 * hh + e]);
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(otile_addr + (y * Gw + x + e) * DS_OUTP + ((warp ^ (g & 3)) << 3)),
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(otile_addr + (y * 16 + x + e) * DS_OUTP + ((warp ^ (g & 3)) << 3)),
                          "r"(lo2), "r"(hi2)
                          : "memory");
           }
@@ -269,8 +275,8 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
     for (int i = tid; i < R * 4; i += DS_THREADS)
       *reinterpret_cast<uint4 *>(dst + (long long)(i >> 2) * C + (i & 3) * 8) = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < Tn * 4; i += DS_THREADS) {
-      const int t = i >> 2, sw = (t / Gw) & 3;
-      const uint8_t *row = ds_smem + L.otile + t * DS_OUTP;
+      const int t = i >> 2, y = t / Gw, sw = y & 3;
+      const uint8_t *row = ds_smem + L.otile + (y * 16 + t % Gw) * DS_OUTP;
       const uint2 u0 = *reinterpret_cast<const uint2 *>(row + (((2 * (i & 3)) ^ sw) << 3));
       const uint2 u1 = *reinterpret_cast<const uint2 *>(row + (((2 * (i & 3) + 1) ^ sw) << 3));
       *reinterpret_cast<uint4 *>(dst + (long long)(R + t) * C + (i & 3) * 8) = make_uint4(u0.x, u0.y, u1.x, u1.y);
@@ -306,7 +312,7 @@ static int launch_slab(const void *act, const float *producer, int parts, float 
   else if (C <= 1024) token_stats_kernel<4><<<sblocks, 256, 0, st>>>((const bf16 *)act, ts, rows, Tn, R, C, eps);
   else token_stats_kernel<8><<<sblocks, 256, 0, st>>>((const bf16 *)act, ts, rows, Tn, R, C, eps);
   SDP_LAUNCH_OK();
-  const DsLayout<KS> L(Tn);
+  const DsLayout<KS> L(Gh, Tn);
   auto kern = ln_dwconv_slab_kernel<KS>;
   static int configured = 0;
   if (L.total > configured) {
@@ -331,8 +337,8 @@ static int launch_slab(const void *act, const float *producer, int parts, float 
 using namespace sdp;
 
 extern "C" int sdp_ln_dwconv_slab_ok(int Gh, int Gw, int C, int k, int dtype) {
-  return dtype == SDP_BF16 && (k == 3 || k == 5 || k == 7) && Gh >= 1 && Gh <= 16 && (Gw == 8 || Gw == 16) &&
-         C % DS_CH == 0 && C <= 2048;
+  return dtype == SDP_BF16 && (k == 3 || k == 5 || k == 7) && Gh >= 1 && Gh <= 16 && Gw >= 1 && Gw <= 16 &&
+         (Gh * Gw) % 2 == 0 && C % DS_CH == 0 && C <= 2048;
 }
 
 extern "C" int sdp_ln_dwconv_slab_stats(const void *act, const float *producer_stats, int parts, float *token_stats,

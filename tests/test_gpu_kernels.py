@@ -353,11 +353,15 @@ def test_ln_dwconv(sdp, dtype, Gh, Gw, C, k, R, bias, monkeypatch):
 
 
 @pytest.mark.parametrize("B,Gh,Gw,C,k,R,bias", [(3, 16, 16, 768, 7, 5, False), (5, 16, 16, 64, 7, 4, True), (2, 8, 8, 32, 5, 1, True),
-                                                (7, 12, 16, 96, 3, 0, False), (40, 5, 8, 32, 7, 2, True), (1, 16, 8, 128, 5, 5, False)])
+                                                (7, 12, 16, 96, 3, 0, False), (40, 5, 8, 32, 7, 2, True), (1, 16, 8, 128, 5, 5, False),
+                                                # grids narrower than the 16-slot rows of the shared-memory tiles
+                                                (3, 14, 14, 768, 7, 5, False), (4, 14, 14, 512, 7, 5, True), (3, 6, 3, 32, 3, 1, True),
+                                                (2, 4, 15, 64, 5, 2, False), (5, 2, 1, 32, 7, 3, True), (2, 10, 9, 96, 7, 0, False)])
 def test_ln_dwconv_slab(sdp, B, Gh, Gw, C, k, R, bias):
     """Channel-stationary tensor-core kernel (dwconv_slab.cu) against the same torch reference (layers.py:102)."""
     assert sdp.ops.ln_dwconv_slab_ok(Gh, Gw, C, k, torch.bfloat16)
-    assert not sdp.ops.ln_dwconv_slab_ok(14, 14, C, k, torch.bfloat16)
+    assert not sdp.ops.ln_dwconv_slab_ok(15, 15, C, k, torch.bfloat16)      # odd token count
+    assert not sdp.ops.ln_dwconv_slab_ok(17, 16, C, k, torch.bfloat16)
     act = (rnd(B, R + Gh * Gw, C, seed=45) * 2 + 0.3).bfloat16()
     gamma, beta = rnd(C, seed=41) * 0.3 + 1, rnd(C, seed=42) * 0.3
     wdw = rnd(C, k, k, seed=43, scale=1 / k)
