@@ -44,6 +44,30 @@ def workload_name(size, batch):
             f"conv 7, 8 heads, R=5) 224^2 eval forward, batch {batch} per GPU, random-init weights (seed 0)")
 
 
+def gemm_traffic(config, batch):
+    """DRAM bytes per GEMM launch (dram__bytes_read + dram__bytes_write, averaged over the step's GEMM launches) from
+    the committed `ncu --set full` capture; None when the capture was taken on another workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+            t = json.load(f)
+        if t.get("config") != config or int(t.get("batch", 0)) != int(batch):
+            return None
+        return t["avg_dram_gb_per_launch"] * 1e9
+    except (OSError, ValueError, KeyError):
+        return None
+
+
+def gemm_bytes_per_step(cfg, M):
+    """Algorithmic bytes of the step's big GEMMs: A + W + out (+ the residual read), bf16."""
+    C, F = int(cfg["embedding_dim"]), int(cfg.get("ff_multiplication_factor", 4)) * int(cfg["embedding_dim"])
+    def g(K, N, res):
+        return 2 * (M * K + N * K + M * N * (2 if res else 1))
+    nb, cb = int(cfg["num_blocks"]), int(cfg["conv_block_num"])
+    enc = g(C, 3 * C, False) + g(C, C, True) + g(C, F, False) + g(F, C, True)
+    mix = g(C, C, True) + g(C, 4 * C, False) + g(4 * C, C, True)
+    return (nb + 1) * enc + nb * cb * mix
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -369,7 +393,12 @@ def main():
         achieved = gf / (gms / 1e3) / 1e12
         line["roofline"] = {
             "kernel": "gemm_bf16_tc_kernel (tcgen05/TMEM/TMA)", "bound": "tensor", "achieved": achieved,
-            "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["sustained"], "traffic": None,
+            "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["sustained"],
+            "traffic": gemm_traffic(args.config, B),
+            "traffic_how": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the step's GEMM launches "
+                           "by shape, from the committed ncu --set full capture (profiles/r01_gemm_traffic.json); "
+                           "compare algorithmic_bytes_per_launch",
+            "algorithmic_bytes_per_launch": gemm_bytes_per_step(cfg, B * (T + R)) / nl,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
             "launches_per_step": nl, "avg_launch_ms": gms / nl, "avg_launch_gflop": gf / nl / 1e9,
             "share_of_step": gms / sum(v["ms_per_step"] for v in fam.values()),
