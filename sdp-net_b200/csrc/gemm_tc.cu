@@ -10,6 +10,8 @@
 #include <mutex>
 #include <unordered_map>
 
+// this kernel only runs on bf16 operands and (bar the tiny head GEMMs) writes bf16: the degree-3 GELU is enough
+#define SDP_GELU_FAST_FN gelu_erf_fast3
 #include "tc5.cuh"
 
 namespace sdp {
@@ -250,33 +252,30 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float mean = 0.0f, rstd = 1.0f;
         const float *hw = nullptr, *hb = nullptr;
         if constexpr (HN > 0) {
-          // per-head LayerNorm over this thread's HN accumulator columns: TMEM is re-read per pass
-          // (cheap) instead of holding HN values in registers
+          // per-head LayerNorm over this thread's HN accumulator columns: TMEM is read twice (statistics, then
+          // normalise) instead of holding HN values in registers
           if (col0 < 2 * epi.hn_C) {
-            float s = 0.0f;
+            // one pass: sums of (v - shift) and (v - shift)^2 with the head's first column as the shift (no
+            // cancellation even when |mean| >> std), four accumulators each so the adds are not one serial chain
+            float s1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, s2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            float shift = 0.0f;
 #pragma unroll 1
             for (int i = 0; i < HN; i += 32) {
               float v[32];
               tmem_ld32(taddr + c + i, v);
               tmem_ld_wait();
               if (lnf) ln_fold(v, col0 + i);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) s += v[j];
-            }
-            mean = s * (1.0f / HN);
-            float q = 0.0f;
-#pragma unroll 1
-            for (int i = 0; i < HN; i += 32) {
-              float v[32];
-              tmem_ld32(taddr + c + i, v);
-              tmem_ld_wait();
-              if (lnf) ln_fold(v, col0 + i);
+              if (i == 0) shift = v[0];
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float dlt = v[j] - mean;
-                q = fmaf(dlt, dlt, q);
+                const float dlt = v[j] - shift;
+                s1[j & 3] += dlt;
+                s2[j & 3] = fmaf(dlt, dlt, s2[j & 3]);
               }
             }
+            const float dm = ((s1[0] + s1[1]) + (s1[2] + s1[3])) * (1.0f / HN);
+            mean = shift + dm;
+            const float q = fmaxf(((s2[0] + s2[1]) + (s2[2] + s2[3])) * (1.0f / HN) - dm * dm, 0.0f) * HN;
             rstd = rsqrtf(q * (1.0f / HN) + epi.hn_eps);
             const bool is_q = col0 < epi.hn_C;
             hw = is_q ? epi.hn_qw : epi.hn_kw;
