@@ -33,7 +33,7 @@ def _stale(target: str, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "sdpnet_b200.h")]
+    headers = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")] + [os.path.join(ROOT, "include", "sdpnet_b200.h")]
     nvcc = _nvcc()
 
     def compile_one(src: str):

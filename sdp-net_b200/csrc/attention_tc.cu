@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ32,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmKV,
                      const __grid_constant__ CUtensorMap tmO,
-                     bf16 *__restrict__ out, int S, int h, int KEYS, int kv_box_rows, float scale_log2) {
+                     bf16 *__restrict__ out, int S, int h, int KEYS, int kv_box_rows, float scale_log2, int tail_mode) {
   constexpr int NA = D / 32;                   // 32-column (64B-swizzled) atoms of V along the head dim
   // Q, K and P are K-major MMA operands read in 32-byte k-slices: only the 128B swizzle spreads the eight rows of
   // a slice over all banks (64B-swizzled rows collide two by two), so they use 64-column atoms wherever 64
@@ -263,6 +263,36 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                  AT_HI_SW64, idesc_o, j != 0);
         }
       };
+      // Tail tile (tail_mode: the last query tile holds <= 8 rows, e.g. the 5 register tokens of S = 261): scores are
+      // computed TRANSPOSED, S^T = K Q_tail^T (keys on the TMEM lanes, 16 query columns per 128-key tile), so the
+      // softmax is spread over all lanes by key instead of 5 live lanes doing a 272-wide row each; the warps write
+      // P back as rows 0..15 of compact 2 KB atoms in the (now free) Q buffer and the usual P V follows.
+      const uint32_t idesc_t = at_idesc(AT_MT, 16, 0);
+      auto issue_st = [&]() {
+        for (int kt = 0; kt * 128 < KEYS; ++kt) {
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            if (ks < 4 * N128)
+              at_mma(tmem + 16 * kt, k128_lo + (ks >> 2) * (KEYS * 128 >> 4) + kt * (128 * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
+                     q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc_t, ks != 0);
+            else
+              at_mma(tmem + 16 * kt, k64_lo + kt * (128 * 64 >> 4) + (ks & 1) * 2, AT_HI_SW64, q64_lo + (ks & 1) * 2, AT_HI_SW64,
+                     idesc_t, ks != 0);
+          }
+        }
+      };
+      auto issue_pv_tail = [&](uint32_t o_col) {
+        const uint32_t pt128 = at_lo(sbase + q_off, 16), pt64 = at_lo(sbase + q_off + NP128 * 2048, 16);
+#pragma unroll 4
+        for (int j = 0; j < 4 * NP128; ++j)
+          at_mma(tmem + o_col, pt128 + (j >> 2) * (2048 >> 4) + ((j & 3) << 1), AT_HI_SW128, v_lo + j * (16 * 64 >> 4), AT_HI_SW64,
+                 idesc_o, j != 0);
+        for (int j = 4 * NP128; j < KEYS / 16; ++j) {
+          const int j2 = j - 4 * NP128;
+          at_mma(tmem + o_col, pt64 + (j2 >> 1) * (1024 >> 4) + ((j2 & 1) << 1), AT_HI_SW64, v_lo + j * (16 * 64 >> 4), AT_HI_SW64,
+                 idesc_o, j != 0);
+        }
+      };
       AT_T(10);
       mbar_wait(B.kv_full, 0);
       AT_T(11);
@@ -287,13 +317,24 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(B.px_full, t & 1);                          // P.X(t) in shared memory, S.X(t) consumed
         AT_T(14);
         tc_fence_after();
+        if (tail_mode && t == tiles - 1) {                    // the whole transposed P arrives with one barrier
+          issue_pv_tail(o_col);
+          tc_commit(B.o_full + 8 * ob);
+          break;
+        }
+        const bool next_tail = tail_mode && t + 2 == tiles;
         issue_pv(0, KA / 16, o_col);
         AT_T(17);
         if (KB == 0) tc_commit(B.o_full + 8 * ob);
         if (t + 1 < tiles) {
           mbar_wait(B.q_full, (t + 1) & 1);
           tc_fence_after();
-          issue_qk(0, idesc_x);
+          if (next_tail) {
+            if (kv_box_rows < KEYS) mbar_wait(B.k1_full, 0);
+            issue_st();
+          } else {
+            issue_qk(0, idesc_x);
+          }
           tc_commit(B.sx_full);
           if (KB == 0) tc_commit(B.q_free);
         }
@@ -302,7 +343,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mbar_wait(B.py_full, t & 1);
           AT_T(16);
           tc_fence_after();
-          if (t + 1 < tiles) {                                  // the softmax warps wait on these scores next
+          if (t + 1 < tiles && !next_tail) {                    // the softmax warps wait on these scores next
             issue_qk(KA, idesc_y);
             tc_commit(B.sy_full);
             tc_commit(B.q_free);
@@ -384,11 +425,17 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (lane == 0) mbar_arrive(barrier);
     };
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
-    auto epilogue = [&](int t) {                              // this group's half of O(t) / row sum -> bf16 -> global
+    auto epilogue = [&](int t, bool tail) {                   // this group's half of O(t) / row sum -> bf16 -> global
       constexpr int HALF = D / 2;
       const int ob = t % OB;
       const float *xs = xch + 512 + (t & 1) * 256;
-      const float inv = 1.0f / (xs[r] + xs[128 + r]);
+      float den = xs[r] + xs[128 + r];
+      if (tail) {                                             // transposed tail tile: eight per-warp partial sums per row
+        den = 0.0f;
+        if (r < 8)
+          for (int w = 0; w < 8; ++w) den += xs[w * 8 + r];
+      }
+      const float inv = 1.0f / den;
       const int row = t * AT_MT + r;
       bf16 *orow = out + ((long long)b * S + row) * C + head * D + g * HALF;
       const bool warp_live = t * AT_MT + quad * 32 < S;
@@ -434,8 +481,93 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     };
 
+    // ---- tail tile, transposed: this thread owns key 128 kt + 32 quad + lane of key tiles kt = g, g + 2 ----
+    auto tail_tile = [&](int t) {
+      // All 8 query columns are processed without branches (columns past the live rows only produce garbage in P
+      // rows and sums nobody reads), so the eight shuffle chains interleave.
+      float *tmax = xch + (t & 1) * 256;                      // [8 warps][8]
+      float *psum = xch + 512 + (t & 1) * 256;                // [8 warps][8]: partial row sums, added up by the epilogue
+      AT_T(49);
+      mbar_wait(B.sx_full, t & 1);
+      tc_fence_after();
+      AT_T(50);
+      float v[2][8];
+      bool valid[2];
+      uint32_t pbase[2], pch[2];                              // P row 0 address of this thread's key, its 16-byte chunk
+      bool sw128[2], store[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int kt = g + 2 * i, key = 128 * kt + 32 * quad + lane;
+        valid[i] = kt * 128 < KEYS && key < S;
+        store[i] = kt * 128 < KEYS && key < KEYS;
+        if (kt * 128 < KEYS) tmem_ld8(t_lane + 16 * kt, v[i]);
+        sw128[i] = key < 64 * NP128;
+        const int k2 = key - 64 * NP128;
+        pbase[i] = sw128[i] ? sbase + q_off + (key >> 6) * 2048 + (key & 7) * 2 : sbase + q_off + NP128 * 2048 + (k2 >> 5) * 1024 + (k2 & 7) * 2;
+        pch[i] = sw128[i] ? (key & 63) >> 3 : (k2 & 31) >> 3;
+      }
+      tmem_ld_wait();
+      float mq[8];
+#pragma unroll
+      for (int qi = 0; qi < 8; ++qi) mq[qi] = fmaxf(valid[0] ? v[0][qi] : -INFINITY, valid[1] ? v[1][qi] : -INFINITY);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int qi = 0; qi < 8; ++qi) mq[qi] = fmaxf(mq[qi], __shfl_xor_sync(0xffffffffu, mq[qi], o));
+      if (lane < 8) {
+        float mine = mq[0];
+#pragma unroll
+        for (int qi = 1; qi < 8; ++qi) mine = lane == qi ? mq[qi] : mine;
+        tmax[(warp - 2) * 8 + lane] = mine;
+      }
+      AT_T(51);
+      asm volatile("bar.sync 9, 256;" ::: "memory");          // all eight softmax warps
+      AT_T(52);
+      epilogue(t - 1, false);
+      AT_T(53);
+      float mrow = -INFINITY;                                 // lane qi: maximum of query qi over all keys
+      if (lane < 8) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) mrow = fmaxf(mrow, tmax[w * 8 + lane]);
+      }
+      float ps[8];
+#pragma unroll
+      for (int qi = 0; qi < 8; ++qi) {
+        const float nm = -__shfl_sync(0xffffffffu, mrow, qi) * scale_log2;
+        ps[qi] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float pv = valid[i] ? fast_ex2(fmaf(v[i][qi], scale_log2, nm)) : 0.0f;
+          ps[qi] += pv;
+          if (store[i]) {                                     // P[qi][key] into the compact atoms (zeros past the sequence)
+            const uint32_t addr = sw128[i] ? pbase[i] + qi * 128 + ((pch[i] ^ (qi & 7)) << 4)
+                                           : pbase[i] + qi * 64 + ((pch[i] ^ ((qi >> 1) & 3)) << 4);
+            const uint16_t pb = __bfloat16_as_ushort(__float2bfloat16_rn(pv));
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(pb) : "memory");
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int qi = 0; qi < 8; ++qi) ps[qi] += __shfl_xor_sync(0xffffffffu, ps[qi], o);
+      if (lane < 8) {
+        float mine = ps[0];
+#pragma unroll
+        for (int qi = 1; qi < 8; ++qi) mine = lane == qi ? ps[qi] : mine;
+        psum[(warp - 2) * 8 + lane] = mine;
+      }
+      AT_T(54);
+      publish(B.px_full);
+      AT_T(55);
+    };
+
 #pragma unroll 1
     for (int t = 0; t <= tiles; ++t) {                        // iteration t: scores of tile t, output of tile t - 1
+      if (tail_mode && t == tiles - 1) {
+        tail_tile(t);
+        continue;
+      }
       const bool live = t < tiles && t * AT_MT + quad * 32 < S;   // warps whose rows are all past the sequence idle
       float *xm = xch + (t & 1) * 256, *xs = xch + 512 + (t & 1) * 256;
       float m = -INFINITY;
@@ -453,7 +585,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       pair_sync();                                            // partial maxima of tile t, partial sums of tile t - 1
       AT_T(26);
-      if (t > 0) epilogue(t - 1);
+      if (t > 0) epilogue(t - 1, tail_mode && t == tiles);
       AT_T(27);
       if (t < tiles) {
         m = fmaxf(m, xm[(g ^ 1) * 128 + r]);
@@ -507,7 +639,11 @@ static int launch_attn_tc5(const void *qkv, void *out, int B, int S, int h, cuda
     configured = smem;
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
-  kern<<<B * h, AT_THREADS, smem, st>>>(tq, tq32, tk, tkv, to, (bf16 *)out, S, h, KEYS, KEYS / nbox, scale_log2);
+  // the last query tile is transposed when it holds at most 8 rows (SDP_ATTN_TAIL=0: treat it like the others)
+  static const bool tail_on = [] { const char *e = getenv("SDP_ATTN_TAIL"); return !(e && e[0] == '0'); }();
+  const int tiles = (S + AT_MT - 1) / AT_MT;
+  const int tail_mode = tail_on && tiles >= 2 && S - (tiles - 1) * AT_MT <= 8 ? 1 : 0;
+  kern<<<B * h, AT_THREADS, smem, st>>>(tq, tq32, tk, tkv, to, (bf16 *)out, S, h, KEYS, KEYS / nbox, scale_log2, tail_mode);
   SDP_LAUNCH_OK();
   return 0;
 }
