@@ -157,7 +157,9 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = h * D;
-  const int b = blockIdx.x / h, head = blockIdx.x % h;
+  // images from the last to the first: the QKV GEMM wrote its rows in ascending order (the tail of the batch is still in
+  // L2), and the output projection starts at image 0, which this grid then writes last
+  const int b = (int)(gridDim.x / h) - 1 - (int)(blockIdx.x / h), head = blockIdx.x % h;
   const int tiles = (S + AT_MT - 1) / AT_MT;
 #ifdef AT_TRACE
   const bool trace_on = blockIdx.x == 4000;

@@ -154,8 +154,10 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
   const int c0 = blockIdx.x * DS_CH;
   const int b_begin = blockIdx.y * img_per_cta, b_end = min(B, b_begin + img_per_cta);
   if (b_begin >= b_end) return;
-
-  auto prefetch = [&](int b, int buf) {    // the [Tn, 32-channel] slice of image b (64 B per token) + its statistics
+  // images are walked from the last to the first (loop index b -> image B - 1 - b): the producer GEMM wrote the
+  // activations in ascending order, so the tail of the batch is still in L2, and the consumer GEMM starts at image 0
+  auto prefetch = [&](int bi, int buf) {   // the [Tn, 32-channel] slice of an image (64 B per token) + its statistics
+    const int b = B - 1 - bi;
     const bf16 *src = act + ((long long)b * S + R) * C + c0;
     for (int i = tid; i < Tn * 4; i += DS_THREADS) {
       const int t = i >> 2, slot = (t / Gw) * 16 + t % Gw;   // token (y, x) sits in slot 16 y + x
@@ -271,7 +273,7 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
     __syncthreads();                       // out tile complete, planes free
 
     // ---- 128-bit stores of the [Tn, 32] result; the R register rows of the slab are zero (passed through later) ----
-    bf16 *dst = out + (long long)b * S * C + c0;
+    bf16 *dst = out + (long long)(B - 1 - b) * S * C + c0;
     for (int i = tid; i < R * 4; i += DS_THREADS)
       *reinterpret_cast<uint4 *>(dst + (long long)(i >> 2) * C + (i & 3) * 8) = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < Tn * 4; i += DS_THREADS) {

@@ -49,6 +49,8 @@ template <> struct Vec<bf16> {
 
 // Persistent: a warp walks rows with a grid stride and has the NEXT row's loads in flight while it reduces,
 // normalises and stores the current one (two rows of memory-level parallelism per warp, no block churn).
+// Rows are walked from the LAST to the first: the producer GEMM wrote them in ascending order, so its most recent
+// ~100 MB are still in L2 when this kernel starts, and the consumer GEMM starts at row 0, which this kernel wrote last.
 template <typename T, int VPL>
 __global__ void __launch_bounds__(256)
 ln_rows_vec_kernel(const T *__restrict__ x, long long ldx, const float *__restrict__ w,
@@ -62,7 +64,7 @@ ln_rows_vec_kernel(const T *__restrict__ x, long long ldx, const float *__restri
   const int nvec = C / EPV;
   Raw cur[VPL], nxt[VPL];
   auto load_row = [&](int r, Raw *dst) {
-    const Raw *xr = reinterpret_cast<const Raw *>(x + (long long)r * ldx);
+    const Raw *xr = reinterpret_cast<const Raw *>(x + (long long)(M - 1 - r) * ldx);
 #pragma unroll
     for (int i = 0; i < VPL; ++i)
       if (lane + 32 * i < nvec) dst[i] = xr[lane + 32 * i];
@@ -94,7 +96,7 @@ ln_rows_vec_kernel(const T *__restrict__ x, long long ldx, const float *__restri
       }
     }
     const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
-    T *orow = out + (long long)row * ldo;
+    T *orow = out + (long long)(M - 1 - row) * ldo;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int iv = lane + 32 * i;
