@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SDPNET_B200_ABI_VERSION 4
+#define SDPNET_B200_ABI_VERSION 5
 
 typedef enum { SDP_F32 = 0, SDP_BF16 = 1 } sdp_dtype;
 
@@ -206,6 +206,29 @@ int sdp_activation(const void *x, void *y, int64_t n, int act, int dtype, void *
  * (one_hot*(1-ls) + ls/K), number of rows whose argmax equals the label, number of rows. */
 int sdp_eval_metrics(const float *logits, int64_t ldl, const int64_t *labels, int B, int K, float label_smoothing,
                      double *acc, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Validation preprocessing right in front of the forward (val_transforms, hf_dataset_generator.py:27-41:
+ * RGB() -> Resize(resize, BICUBIC) -> CenterCrop(crop) -> ToImage() -> ToDtype(float32, scale=True) ->
+ * Normalize(mean, std), applied to PIL images).  Input: decoded 8-bit RGB images of any sizes, packed in one device
+ * buffer (3 bytes per pixel, rows contiguous); output: [B, 3, crop_h, crop_w] float32 (bit-identical to the
+ * reference transform: Pillow's fixed-point bicubic resample with its two uint8 roundings, then the float32
+ * scale / subtract / divide in torchvision's order) or the same values rounded to bf16 for the patcher.
+ * `images` is a HOST array (sizes drive the launch geometry); it is copied into the workspace on `stream`.
+ * `mean` / `std` are host arrays of 3 floats.  The workspace (device, 16-byte aligned) holds the descriptors, the
+ * per-image tap tables and the uint8 intermediate between the two passes; size it with
+ * sdp_val_preprocess_workspace_bytes (returns -1 and sets sdp_last_error on bad arguments).
+ * --------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t offset;          /* byte offset of the image's first pixel in `pixels` */
+  int32_t height, width;
+} sdp_image_desc;
+
+int64_t sdp_val_preprocess_workspace_bytes(const sdp_image_desc *images, int B, int resize_h, int resize_w,
+                                           int crop_h, int crop_w);
+int sdp_val_preprocess(const uint8_t *pixels, const sdp_image_desc *images, int B, int resize_h, int resize_w,
+                       int crop_h, int crop_w, const float *mean, const float *std, void *workspace,
+                       int64_t workspace_bytes, void *out, int out_dtype, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Whole-model forward (model.py:129-149) sequenced on the device side of the ABI: one call

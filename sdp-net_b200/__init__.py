@@ -7,12 +7,14 @@
 
 Compute happens only in `lib/libsdpnet_b200.so` (hand-written CUDA, C-ABI in include/sdpnet_b200.h).
 """
-from . import _lib, checkpoint, engine, evaluate, ops, shard
+from . import _lib, checkpoint, engine, evaluate, ops, preprocess, shard
 from .engine import Engine
 from .layers import (Block, ClassificationHead, ConvEmbedding, ConvMixer, ConvPatcher, EmbeddingLayer,
                      EncoderLayer, FinalBlock, LayerNorm, StochasticDepth)
 from .model import MainModel, SdPModel, activations
+from .preprocess import ValTransforms, val_transforms
 
 __all__ = ["MainModel", "SdPModel", "Engine", "Block", "ClassificationHead", "ConvEmbedding", "ConvMixer",
            "ConvPatcher", "EmbeddingLayer", "EncoderLayer", "FinalBlock", "LayerNorm", "StochasticDepth",
-           "activations", "ops", "engine", "checkpoint", "evaluate", "shard"]
+           "activations", "ops", "engine", "checkpoint", "evaluate", "preprocess", "shard", "ValTransforms",
+           "val_transforms"]

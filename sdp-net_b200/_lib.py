@@ -68,6 +68,10 @@ class ModelDesc(C.Structure):
     ]
 
 
+class ImageDesc(C.Structure):
+    _fields_ = [("offset", c_i64), ("height", C.c_int32), ("width", C.c_int32)]
+
+
 class Workspace(C.Structure):
     _fields_ = [(n, c_void_p) for n in (
         "act", "norm", "qkv", "attn", "hidden", "im2col", "pooled", "head_h", "stats")]
@@ -97,6 +101,8 @@ SYMBOLS = {
     "sdp_tokens_to_nchw": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_embed_tokens": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_eval_metrics": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "sdp_val_preprocess_workspace_bytes": (c_i64, [C.POINTER(ImageDesc), c_int, c_int, c_int, c_int, c_int]),
+    "sdp_val_preprocess": (c_int, [c_void_p, C.POINTER(ImageDesc), c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p, c_i64, c_void_p, c_int, c_void_p]),
     "sdp_activation": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
     "sdp_forward": (c_int, [C.POINTER(ModelDesc), C.POINTER(Workspace), c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sdp_launch_count": (c_i64, [c_int]),
@@ -122,7 +128,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)   # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if handle.sdp_abi_version() != 4:
+        if handle.sdp_abi_version() != 5:
             raise SdpNetLibraryError("libsdpnet_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

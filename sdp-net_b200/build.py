@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(HERE, "lib", "libsdpnet_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "norm.cu", "dwconv.cu", "dwconv_slab.cu", "attention.cu", "attention_tc.cu", "forward.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "norm.cu", "dwconv.cu", "dwconv_slab.cu", "attention.cu", "attention_tc.cu", "preprocess.cu", "forward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -245,6 +245,34 @@ def eval_metrics(logits: torch.Tensor, labels: torch.Tensor, acc: torch.Tensor, 
     return acc
 
 
+def val_preprocess_workspace_bytes(desc, B: int, resize, crop) -> int:
+    """Bytes of device workspace `val_preprocess` needs for these images (`desc`: _lib.ImageDesc array, host)."""
+    n = int(L.lib().sdp_val_preprocess_workspace_bytes(desc, B, resize[0], resize[1], crop[0], crop[1]))
+    if n < 0:
+        raise ValueError("sdp_val_preprocess_workspace_bytes: " + L.lib().sdp_last_error().decode("utf-8", "replace"))
+    return n
+
+
+def val_preprocess(pixels: torch.Tensor, desc, B: int, resize, crop, mean, std, workspace: torch.Tensor,
+                   out: torch.Tensor) -> torch.Tensor:
+    """Packed uint8 RGB images (device) -> out [B, 3, crop_h, crop_w] float32 / bfloat16: the reference's
+    val_transforms (hf_dataset_generator.py:27-41), see sdp_val_preprocess in the header."""
+    if pixels.dtype != torch.uint8 or not pixels.is_contiguous():
+        raise TypeError("val_preprocess: pixels must be a contiguous uint8 tensor")
+    if workspace.dtype != torch.uint8 or not workspace.is_contiguous():
+        raise TypeError("val_preprocess: workspace must be a contiguous uint8 tensor")
+    if tuple(out.shape) != (B, 3, crop[0], crop[1]) or not out.is_contiguous():
+        raise TypeError(f"val_preprocess: out must be contiguous [B, 3, {crop[0]}, {crop[1]}]")
+    end = max(desc[i].offset + 3 * desc[i].height * desc[i].width for i in range(B))
+    if end > pixels.numel():
+        raise ValueError(f"val_preprocess: descriptors reach byte {end}, the pixel buffer holds {pixels.numel()}")
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    L.check(L.lib().sdp_val_preprocess(_p(pixels), desc, B, resize[0], resize[1], crop[0], crop[1], m, s, _p(workspace),
+                                       workspace.numel(), _p(out), _dt(out), _stream()), "sdp_val_preprocess")
+    return out
+
+
 def activation(x: torch.Tensor, act, force_fast: bool = False) -> torch.Tensor:
     x = x.contiguous()
     y = torch.empty_like(x)
