@@ -65,6 +65,8 @@ class ValTransforms:
         self.out_dtype = out_dtype
         self.device = torch.device(device)
         self._ws = None                                            # device workspace, grown on demand
+        self._pinned = None                                        # pinned staging buffer, grown on demand
+        self._copied = None                                        # event: the last H2D copy out of it has finished
 
     def __call__(self, images):
         single = not isinstance(images, (list, tuple))
@@ -82,7 +84,11 @@ class ValTransforms:
         for i, a in enumerate(arrs):
             desc[i].offset, desc[i].height, desc[i].width = off, a.shape[0], a.shape[1]
             off = (off + a.size + 15) // 16 * 16
-        host = torch.empty(off, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        if self._copied is not None:                                # the previous batch may still be on its way out
+            self._copied.synchronize()
+        if self._pinned is None or self._pinned.numel() < off:
+            self._pinned = torch.empty(max(off, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        host = self._pinned[:off]
         hv = host.numpy()
         for i, a in enumerate(arrs):
             hv[desc[i].offset:desc[i].offset + a.size] = a.reshape(-1)
@@ -91,6 +97,9 @@ class ValTransforms:
     def run_packed(self, host: torch.Tensor, desc) -> torch.Tensor:
         B = len(desc)
         pixels = host.to(self.device, non_blocking=True)
+        if host.is_pinned():
+            self._copied = torch.cuda.Event()
+            self._copied.record()
         need = ops.val_preprocess_workspace_bytes(desc, B, self.image_size, self.crop_size)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)

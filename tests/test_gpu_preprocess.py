@@ -27,7 +27,7 @@ def bits(a):
 
 
 @pytest.mark.parametrize("name", CASES)
-def test_golden_fixture_bit_exact(sdp, name):
+def test_golden_fixture_bit_exact(sdp, name, path):
     z = np.load(os.path.join(GOLDEN, f"preprocess_{name}.npz"))
     img = P.synth_image(int(z["H"]), int(z["W"]), int(z["seed"]))
     rs, cs = tuple(int(v) for v in z["resize"]), tuple(int(v) for v in z["crop"])
@@ -41,7 +41,7 @@ def test_golden_fixture_bit_exact(sdp, name):
     assert float(out.astype(np.float64).sum()) == float(z["out_sum"])
 
 
-def test_ragged_batch_matches_oracle(sdp):
+def test_ragged_batch_matches_oracle(sdp, path):
     sizes = [(37, 53), (150, 97), (64, 40), (40, 91), (40, 40), (1, 1), (2, 300), (300, 2), (129, 131), (611, 807), (33, 40)]
     imgs = [P.synth_image(h, w, 100 + i) for i, (h, w) in enumerate(sizes)]
     rs, cs = (40, 40), (28, 28)
@@ -51,7 +51,17 @@ def test_ragged_batch_matches_oracle(sdp):
         assert np.array_equal(bits(out[i]), bits(P.val_preprocess(im, rs, cs))), sizes[i]
 
 
-def test_odd_crop_width_and_custom_statistics(sdp):
+@pytest.fixture(params=["fused", "general"])
+def path(request, monkeypatch):
+    """Both kernel paths: the fused band kernel (default) and the three-kernel path with a global intermediate."""
+    if request.param == "general":
+        monkeypatch.setenv("SDP_PREP_FUSED", "0")
+    else:
+        monkeypatch.delenv("SDP_PREP_FUSED", raising=False)
+    return request.param
+
+
+def test_odd_crop_width_and_custom_statistics(sdp, path):
     rs, cs, mean, std = (48, 36), (31, 21), [0.1, 0.5, 0.9], [0.5, 0.25, 2.0]      # 21 * 3 bytes per row: byte path
     imgs = [P.synth_image(75, 61, 5), P.synth_image(20, 90, 6)]
     out = sdp.val_transforms(rs, cs, mean, std)(imgs).cpu().numpy()
@@ -59,7 +69,7 @@ def test_odd_crop_width_and_custom_statistics(sdp):
         assert np.array_equal(bits(out[i]), bits(P.val_preprocess(im, rs, cs, mean, std)))
 
 
-def test_imagenet_sized_batch(sdp):
+def test_imagenet_sized_batch(sdp, path):
     sizes = [(375, 500), (500, 333), (333, 500), (480, 640), (1200, 1600), (224, 224), (320, 320), (64, 64)] * 2
     imgs = [P.synth_image(h, w, 200 + i) for i, (h, w) in enumerate(sizes)]
     t = sdp.val_transforms()
@@ -79,7 +89,14 @@ def test_imagenet_sized_batch(sdp):
     assert np.array_equal(bits(o[6]), bits(direct))
 
 
-def test_bf16_output_is_the_rounded_float_output(sdp):
+def test_huge_downscale_falls_back_to_the_general_path(sdp):
+    # 9000 columns -> 40: 1803 taps per output column; the tap table alone exceeds shared memory, so no band fits
+    im = P.synth_image(12, 9000, 3)
+    out = sdp.val_transforms((40, 40), (28, 28))([im, P.synth_image(30, 30, 4)]).cpu().numpy()
+    assert np.array_equal(bits(out[0]), bits(P.val_preprocess(im, (40, 40), (28, 28))))
+
+
+def test_bf16_output_is_the_rounded_float_output(sdp, path):
     imgs = [P.synth_image(90, 120, 1), P.synth_image(50, 45, 2)]
     f = sdp.val_transforms((64, 64), (48, 48))(imgs)
     h = sdp.val_transforms((64, 64), (48, 48), out_dtype=torch.bfloat16)(imgs)

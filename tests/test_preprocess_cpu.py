@@ -69,7 +69,7 @@ def test_host_plan_agrees_with_oracle(sdp):
     rs, cs = (320, 320), (224, 224)
     kmax, rows = P.plan([s[0] for s in sizes], [s[1] for s in sizes], rs, cs)
     up = lambda v: (v + 255) // 256 * 256
-    want = up(16 * len(sizes)) + up(len(sizes) * (cs[0] + cs[1]) * (kmax + 2) * 4) + up(len(sizes) * rows * cs[1] * 3)
+    want = up(16 * len(sizes)) + up(len(sizes) * (cs[0] + cs[1]) * (kmax + 2) * 4) + up(768 * 4) + up(len(sizes) * rows * cs[1] * 3)
     assert sdp.ops.val_preprocess_workspace_bytes(desc, len(sizes), rs, cs) == want
 
 
