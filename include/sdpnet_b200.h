@@ -211,7 +211,7 @@ int sdp_eval_metrics(const float *logits, int64_t ldl, const int64_t *labels, in
  * Validation preprocessing right in front of the forward (val_transforms, hf_dataset_generator.py:27-41:
  * RGB() -> Resize(resize, BICUBIC) -> CenterCrop(crop) -> ToImage() -> ToDtype(float32, scale=True) ->
  * Normalize(mean, std), applied to PIL images).  Input: decoded 8-bit RGB images of any sizes, packed in one device
- * buffer (3 bytes per pixel, rows contiguous); output: [B, 3, crop_h, crop_w] float32 (bit-identical to the
+ * buffer of `pixels_bytes` bytes (4-byte aligned; 3 bytes per pixel, rows contiguous, any image offsets); output: [B, 3, crop_h, crop_w] float32 (bit-identical to the
  * reference transform: Pillow's fixed-point bicubic resample with its two uint8 roundings, then the float32
  * scale / subtract / divide in torchvision's order) or the same values rounded to bf16 for the patcher.
  * `images` is a HOST array (sizes drive the launch geometry); it is copied into the workspace on `stream`.
@@ -226,7 +226,7 @@ typedef struct {
 
 int64_t sdp_val_preprocess_workspace_bytes(const sdp_image_desc *images, int B, int resize_h, int resize_w,
                                            int crop_h, int crop_w);
-int sdp_val_preprocess(const uint8_t *pixels, const sdp_image_desc *images, int B, int resize_h, int resize_w,
+int sdp_val_preprocess(const uint8_t *pixels, int64_t pixels_bytes, const sdp_image_desc *images, int B, int resize_h, int resize_w,
                        int crop_h, int crop_w, const float *mean, const float *std, void *workspace,
                        int64_t workspace_bytes, void *out, int out_dtype, void *stream);
 

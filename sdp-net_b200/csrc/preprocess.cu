@@ -206,8 +206,9 @@ struct PrepFused {
 
 template <typename T>
 __global__ void __launch_bounds__(PREP_THREADS)
-prep_fused_kernel(const uint8_t *__restrict__ pixels, const sdp_image_desc *__restrict__ img, const int *__restrict__ coef,
-                  const float *__restrict__ lut_g, T *__restrict__ out, int ch, int cw, int kmax, const PrepFused g) {
+prep_fused_kernel(const uint8_t *__restrict__ pixels, long long pixels_bytes, const sdp_image_desc *__restrict__ img,
+                  const int *__restrict__ coef, const float *__restrict__ lut_g, T *__restrict__ out, int ch, int cw, int kmax,
+                  const PrepFused g) {
   extern __shared__ __align__(16) uint8_t prep_smem[];
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rl = kmax + 2;
@@ -227,28 +228,45 @@ prep_fused_kernel(const uint8_t *__restrict__ pixels, const sdp_image_desc *__re
   const int W = img[b].width, n = (x1 - x0) * 3;
   const uint8_t *base = pixels + img[b].offset;
 
-  // ---- horizontal pass ----
-  for (int r0 = s0; r0 < s1; r0 += g.rs) {
+  // ---- horizontal pass: row segments arrive with cp.async (aligned 32-bit words covering the segment), one chunk
+  //      of RS rows ahead of the chunk being filtered ----
+  const uintptr_t pix_end = reinterpret_cast<uintptr_t>(pixels) + pixels_bytes;
+  auto stage_chunk = [&](int r0, int buf) {
     const int nr = min(g.rs, s1 - r0);
     for (int r = warp; r < nr; r += PREP_THREADS / 32) {         // one warp stages one row segment
-      const uint8_t *src = base + ((long long)(r0 + r) * W + x0) * 3;
-      const int head = min((int)((4 - (reinterpret_cast<uintptr_t>(src) & 3)) & 3), n);
-      uint8_t *srow = stage + r * g.seg_stride + 4;              // srow[j] <-> src[j]; srow + head is word-aligned
-      srow -= head;
-      const int nw = (n - head) >> 2;
-      const uint32_t *gw = reinterpret_cast<const uint32_t *>(src + head);
-      uint32_t *sw = reinterpret_cast<uint32_t *>(srow + head);
-      for (int i = lane; i < nw; i += 32) sw[i] = __ldg(gw + i);
-      if (lane < head) srow[lane] = src[lane];
-      const int tail0 = head + 4 * nw;
-      if (lane < n - tail0) srow[tail0 + lane] = src[tail0 + lane];
+      const uintptr_t src = reinterpret_cast<uintptr_t>(base) + ((long long)(r0 + r) * W + x0) * 3;
+      const uintptr_t w0 = src & ~uintptr_t(3);                  // byte j of the segment lands at row base + (src & 3) + j
+      const int nw = (int)((src + n + 3 - w0) >> 2);
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(stage + (buf * g.rs + r) * g.seg_stride));
+      for (int i = lane; i < nw; i += 32) {
+        const uintptr_t ga = w0 + 4 * (uintptr_t)i;
+        if (ga + 4 <= pix_end) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * i), "l"(ga) : "memory");
+        } else {                                                 // the buffer's last, partial word: byte by byte
+          for (int e = 0; e < 4; ++e)
+            if (ga + e < pix_end) stage[(buf * g.rs + r) * g.seg_stride + 4 * i + e] = *reinterpret_cast<const uint8_t *>(ga + e);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_chunk(s0, 0);
+  int cbuf = 0;
+  for (int r0 = s0; r0 < s1; r0 += g.rs, cbuf ^= 1) {
+    const int nr = min(g.rs, s1 - r0);
+    if (r0 + g.rs < s1) {
+      stage_chunk(r0 + g.rs, cbuf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const uint8_t *sbuf = stage + cbuf * g.rs * g.seg_stride;
     // thread <-> output column: the column's taps are read once per tap and applied to all staged rows
     for (int x = tid; x < cw; x += PREP_THREADS) {
       const int *rec = coefh + x * rl;
       const int cnt = rec[1];
-      const int off = 4 + (rec[0] - x0) * 3;
+      const int off = (rec[0] - x0) * 3;
       int a[PREP_THREADS / 32][3];
       int po[PREP_THREADS / 32];                                   // byte offset of the window in each staged row
 #pragma unroll
@@ -256,13 +274,13 @@ prep_fused_kernel(const uint8_t *__restrict__ pixels, const sdp_image_desc *__re
         a[r][0] = a[r][1] = a[r][2] = 1 << (PREP_PRECISION_BITS - 1);
         const int rr = min(r, nr - 1);                             // rows past the chunk repeat the last one (discarded)
         const uintptr_t src = reinterpret_cast<uintptr_t>(base) + ((long long)(r0 + rr) * W + x0) * 3;
-        po[r] = rr * g.seg_stride + off - min((int)((4 - (src & 3)) & 3), n);
+        po[r] = rr * g.seg_stride + off + (int)(src & 3);
       }
       for (int k = 0; k < cnt; ++k) {
         const int kk = rec[2 + k];
 #pragma unroll
         for (int r = 0; r < PREP_THREADS / 32; ++r) {
-          const uint8_t *p = stage + po[r] + 3 * k;
+          const uint8_t *p = sbuf + po[r] + 3 * k;
           a[r][0] += (int)p[0] * kk;
           a[r][1] += (int)p[1] * kk;
           a[r][2] += (int)p[2] * kk;
@@ -345,7 +363,7 @@ static void prep_fused_geometry(const sdp_image_desc *images, int B, int rh, int
     t.lut_off = t.coefv_off + up(band * rl * 4);
     t.temp_off = t.lut_off + 768 * 4;
     t.stage_off = t.temp_off + up(src_rows * t.rowb_pad);
-    t.ubuf_off = t.stage_off + up(t.rs * t.seg_stride);
+    t.ubuf_off = t.stage_off + up(2 * t.rs * t.seg_stride);     // double-buffered
     t.total = t.ubuf_off + up(band * t.rowb_pad);
     if (t.total <= budget) {
       *g = t;
@@ -405,7 +423,7 @@ extern "C" int64_t sdp_val_preprocess_workspace_bytes(const sdp_image_desc *imag
   return (int64_t)p.total;
 }
 
-extern "C" int sdp_val_preprocess(const uint8_t *pixels, const sdp_image_desc *images, int B, int resize_h, int resize_w,
+extern "C" int sdp_val_preprocess(const uint8_t *pixels, int64_t pixels_bytes, const sdp_image_desc *images, int B, int resize_h, int resize_w,
                                   int crop_h, int crop_w, const float *mean, const float *std_, void *workspace,
                                   int64_t workspace_bytes, void *out, int out_dtype, void *stream) {
   PrepPlan p;
@@ -416,6 +434,11 @@ extern "C" int sdp_val_preprocess(const uint8_t *pixels, const sdp_image_desc *i
             (long long)workspace_bytes, (long long)p.total);
   SDP_CHECK((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "sdp_val_preprocess: workspace not 16-byte aligned");
   SDP_CHECK(B <= 65535, "sdp_val_preprocess: at most 65535 images per call");
+  SDP_CHECK((reinterpret_cast<uintptr_t>(pixels) & 3) == 0, "sdp_val_preprocess: pixel buffer not 4-byte aligned");
+  for (int b = 0; b < B; ++b)
+    SDP_CHECK(images[b].offset + 3ll * images[b].height * images[b].width <= pixels_bytes,
+              "sdp_val_preprocess: image %d (%dx%d at byte %lld) reaches past the %lld-byte pixel buffer", b, images[b].height,
+              images[b].width, (long long)images[b].offset, (long long)pixels_bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
   sdp_image_desc *d_img = reinterpret_cast<sdp_image_desc *>(ws + p.desc_off);
@@ -435,7 +458,7 @@ extern "C" int sdp_val_preprocess(const uint8_t *pixels, const sdp_image_desc *i
         SDP_CUDA(cudaFuncSetAttribute(prep_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured_f32 = 1;
       }
-      prep_fused_kernel<float><<<grid, PREP_THREADS, p.fused.total, st>>>(pixels, d_img, d_coef, d_lut,
+      prep_fused_kernel<float><<<grid, PREP_THREADS, p.fused.total, st>>>(pixels, pixels_bytes, d_img, d_coef, d_lut,
                                                                           reinterpret_cast<float *>(out), crop_h, crop_w, p.kmax,
                                                                           p.fused);
     } else {
@@ -443,7 +466,7 @@ extern "C" int sdp_val_preprocess(const uint8_t *pixels, const sdp_image_desc *i
         SDP_CUDA(cudaFuncSetAttribute(prep_fused_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured_bf16 = 1;
       }
-      prep_fused_kernel<bf16><<<grid, PREP_THREADS, p.fused.total, st>>>(pixels, d_img, d_coef, d_lut,
+      prep_fused_kernel<bf16><<<grid, PREP_THREADS, p.fused.total, st>>>(pixels, pixels_bytes, d_img, d_coef, d_lut,
                                                                          reinterpret_cast<bf16 *>(out), crop_h, crop_w, p.kmax,
                                                                          p.fused);
     }

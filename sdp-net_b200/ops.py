@@ -263,12 +263,9 @@ def val_preprocess(pixels: torch.Tensor, desc, B: int, resize, crop, mean, std, 
         raise TypeError("val_preprocess: workspace must be a contiguous uint8 tensor")
     if tuple(out.shape) != (B, 3, crop[0], crop[1]) or not out.is_contiguous():
         raise TypeError(f"val_preprocess: out must be contiguous [B, 3, {crop[0]}, {crop[1]}]")
-    end = max(desc[i].offset + 3 * desc[i].height * desc[i].width for i in range(B))
-    if end > pixels.numel():
-        raise ValueError(f"val_preprocess: descriptors reach byte {end}, the pixel buffer holds {pixels.numel()}")
     m = (C.c_float * 3)(*mean)
     s = (C.c_float * 3)(*std)
-    L.check(L.lib().sdp_val_preprocess(_p(pixels), desc, B, resize[0], resize[1], crop[0], crop[1], m, s, _p(workspace),
+    L.check(L.lib().sdp_val_preprocess(_p(pixels), pixels.numel(), desc, B, resize[0], resize[1], crop[0], crop[1], m, s, _p(workspace),
                                        workspace.numel(), _p(out), _dt(out), _stream()), "sdp_val_preprocess")
     return out
 

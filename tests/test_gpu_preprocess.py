@@ -118,6 +118,23 @@ def test_constant_image_and_feeds_the_model(sdp):
     assert logits.shape == (2, 10) and bool(torch.isfinite(logits.float()).all())
 
 
+def test_unpadded_pixel_buffer_ending_mid_word(sdp, path):
+    """C-ABI callers need not pad: the last image may end at any byte (the kernels never read past pixels_bytes)."""
+    from sdpnet_b200 import _lib as L
+    a, b = P.synth_image(5, 7, 11), P.synth_image(9, 5, 12)          # 105 + 135 bytes, second image at an odd offset
+    px = torch.from_numpy(np.concatenate([a.reshape(-1), b.reshape(-1)])).cuda()
+    desc = (L.ImageDesc * 2)()
+    desc[0].offset, desc[0].height, desc[0].width = 0, 5, 7
+    desc[1].offset, desc[1].height, desc[1].width = 105, 9, 5
+    rs, cs = (40, 40), (28, 28)
+    ws = torch.empty(sdp.ops.val_preprocess_workspace_bytes(desc, 2, rs, cs), dtype=torch.uint8, device="cuda")
+    out = torch.empty(2, 3, 28, 28, device="cuda")
+    sdp.ops.val_preprocess(px, desc, 2, rs, cs, list(P.IMAGENET_MEAN), list(P.IMAGENET_STD), ws, out)
+    o = out.cpu().numpy()
+    assert np.array_equal(bits(o[0]), bits(P.val_preprocess(a, rs, cs)))
+    assert np.array_equal(bits(o[1]), bits(P.val_preprocess(b, rs, cs)))
+
+
 def test_bad_descriptors_raise(sdp):
     from sdpnet_b200 import _lib as L
     desc = (L.ImageDesc * 1)()
@@ -125,7 +142,7 @@ def test_bad_descriptors_raise(sdp):
     px = torch.zeros(100, dtype=torch.uint8, device="cuda")
     ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
     out = torch.empty(1, 3, 28, 28, device="cuda")
-    with pytest.raises(ValueError):
+    with pytest.raises(L.SdpNetLibraryError):
         sdp.ops.val_preprocess(px, desc, 1, (40, 40), (28, 28), [0.5] * 3, [0.5] * 3, ws, out)   # pixels too short
     px = torch.zeros(7500, dtype=torch.uint8, device="cuda")
     with pytest.raises(L.SdpNetLibraryError):
