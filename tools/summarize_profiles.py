@@ -54,7 +54,9 @@ if os.path.exists(launches):
     print("wrote launch list summary:", len(cnt), "kernels", f"{tot / 1e6:.1f} ms")
 
 if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .csv argument is the `ncu -i rep --page raw --csv` export made on the GPU box (large reports stay there)
+    raw = open(rep).read() if rep.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
