@@ -22,13 +22,13 @@ constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;          // default: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (320 threads)
 constexpr int EPI_WARPS_WIDE = 16;    // heavy epilogues (GELU): four warps per TMEM lane quadrant (576 threads)
 
-template <int BN, int STAGES, int CG = 1>
+template <int BN, int STAGES, int CG = 1, int OUTB = 32768>
 struct SmemLayout {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = (BN / CG) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_OFF = STAGES * STAGE_BYTES;              // epilogue staging: 8 warps x 2 x [32 rows x 64 B]
-  static constexpr int OUT_BYTES = 32768;                           // shared by 8 warps x 2 slots or 16 warps x 1 slot
+  static constexpr int OUT_BYTES = OUTB;                            // 2 KB slots: 8 warps x 2 (32 KB) or 16 warps x 2 (64 KB)
   static constexpr int BAR_OFF = OUT_OFF + OUT_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
   static_assert(TOTAL <= 232448, "shared memory budget exceeded");
@@ -42,13 +42,16 @@ __host__ __device__ constexpr uint32_t tmem_cols_for(int bn) {
 // 32-column chunk, 64B-swizzled, double-buffered per warp) instead of 16-byte-per-row global stores.
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: launched as clusters of 2 (one TPC); the pair owns a
 // 256 x BN tile, B traffic from L2 halves and the smem ring gets deeper for the same capacity.
-template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1, int EW = EPI_WARPS>
+// LEAN (16 epilogue warps, four per scheduler): bias + activation only, N a multiple of BN, every chunk staged and
+// TMA-stored; none of the residual / pass-through / statistics / LN-fold / head-norm paths are compiled in, which
+// is what lets the epilogue fit the 96 registers a 18-warp CTA leaves per thread.
+template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1, int EW = EPI_WARPS, bool LEAN = false>
 __global__ void __launch_bounds__((2 + EW) * 32, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO, const Epilogue epi, const int K, const int flags) {
   const int vec_ok = flags & 1;
   const bool nofeed = (flags & 2) != 0;   // SDP_GEMM_NOFEED=1 (diagnostic): no TMA loads, MMAs run on stale shared memory
-  using L = SmemLayout<BN, STAGES, CG>;
+  using L = SmemLayout<BN, STAGES, CG, LEAN ? 65536 : 32768>;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   // swizzle-128B tiles need 1024-byte alignment
@@ -179,6 +182,68 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
+  } else if constexpr (LEAN) {
+    // ================= lean epilogue: bias + activation, four warps per TMEM lane quadrant =================
+    static_assert(!LEAN || (EW == 16 && HN == 0 && STAGED && BN % 128 == 0), "lean epilogue: 16 warps, staged, no head-norm");
+    constexpr int WCOLS = BN / 4;                  // columns per warp
+    const int quad = warp & 3, part = (warp - 2) >> 2;
+    const uint32_t stage_base = smem_base + L::OUT_OFF + static_cast<uint32_t>(warp - 2) * 4096;   // two 2 KB slots
+    const uint32_t rowp = lane * 64, sw = (lane >> 1) & 3;
+    uint32_t cc = 0;
+    int it = 0;
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * TILE_M + rank * BLOCK_M;
+      const int n0 = (tile % n_tiles) * BN + part * WCOLS;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + part * WCOLS;
+#pragma unroll 1
+      for (int c = 0; c < WCOLS; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (c + 32 == WCOLS) {                     // this warp's share of the accumulator is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
+            else mbar_arrive_cta(tempty_bar(acc), 0);
+          }
+        }
+        const int col = n0 + c;
+        if (epi.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(epi.bias + col + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        apply_act_vec<32, false>(v, ACT < 0 ? epi.act : ACT);
+        const uint32_t slot = stage_base + ((cc & 1) << 11);
+        if (cc >= 2) {                             // the store issued from this slot two chunks ago has read it
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t p0 = pack_bf16x2(v[8 * j], v[8 * j + 1]), p1 = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+          const uint32_t p2 = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), p3 = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot + rowp + ((j ^ sw) << 4)), "r"(p0), "r"(p1),
+                       "r"(p2), "r"(p3)
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmO, slot, col, m0 + quad * 32);
+          bulk_commit();
+        }
+        ++cc;
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();
   } else {
     // ================= epilogue =================
     // Two warps per TMEM lane quadrant: warps 2..5 take the low half of the tile's columns,
@@ -529,11 +594,11 @@ static bool staged_ok(const Epilogue &e) {
          (e.ldo * 2) % 16 == 0 && (e.pass_seq == 0 || e.residual != nullptr);
 }
 
-template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1, int EW = EPI_WARPS>
+template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1, int EW = EPI_WARPS, bool LEAN = false>
 static int launch_tc2(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &to, const Epilogue &e, int K,
                       cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES, CG>;
-  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT, HN, STAGED, CG, EW>;
+  using L = SmemLayout<BN, STAGES, CG, LEAN ? 65536 : 32768>;
+  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT, HN, STAGED, CG, EW, LEAN>;
   static bool configured = false;
   if (!configured) {
     SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -582,12 +647,12 @@ static int launch_tc(const sdp_gemm_args &a, const CUtensorMap &ta, const Epilog
         constexpr int ST2 = (STAGES * (BLOCK_M + BN)) / (BLOCK_M + BN / 2);   // same bytes, deeper ring
         if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, BN / 2, &tw)) return rc;
         if constexpr (ACT == SDP_ACT_GELU && HN == 0 && BN == 256) {
-          // SDP_GEMM_WIDE_EPI=1 (experiment, measured slower: 1.40 vs 1.19 ms on the XL C->4C GEMM): four epilogue
-          // warps per scheduler instead of two; they share the same 32 KB of staging, so each has a single slot
-          // and waits for its previous TMA store.  The statistics producer always keeps the 8-warp kernel.
-          static const bool wide = [] { const char *v = getenv("SDP_GEMM_WIDE_EPI"); return v && v[0] == '1'; }();
-          if (wide && e.stats_out == nullptr && e.ln_stats == nullptr)
-            return launch_tc2<BN, ST2, ACT, HN, true, 2, EPI_WARPS_WIDE>(ta, tw, to, e, a.K, st);
+          // bias + GELU only (the C -> 4C GEMMs of the mixers and encoders): the lean 16-warp epilogue, one smem
+          // stage traded for 64 KB of output staging.  SDP_GEMM_WIDE_EPI=0 keeps the 8-warp kernel.
+          static const bool wide = [] { const char *v = getenv("SDP_GEMM_WIDE_EPI"); return !(v && v[0] == '0'); }();
+          if (wide && e.residual == nullptr && e.stats_out == nullptr && e.ln_stats == nullptr && e.pass_seq == 0 &&
+              e.seq_out == 0 && e.res_mod == 0 && a.N % BN == 0 && epilogue_vec_ok(e))
+            return launch_tc2<BN, ST2 - 1, ACT, HN, true, 2, EPI_WARPS_WIDE, true>(ta, tw, to, e, a.K, st);
         }
         return launch_tc2<BN, ST2, ACT, HN, true, 2>(ta, tw, to, e, a.K, st);
       }

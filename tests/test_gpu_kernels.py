@@ -86,6 +86,24 @@ def test_gemm_bf16_epilogues(sdp, act):
     assert relerr(out_b, gemm_ref(A, W, bias, act, res, True)) < 1.2e-2
 
 
+@pytest.mark.parametrize("M,N,K,use_bias", [(1024, 256, 64, True), (1100, 768, 768, False), (2610, 3072, 768, True),
+                                            (19000, 3072, 768, True), (1025, 512, 128, True), (5000, 1024, 320, False)])
+def test_gemm_bf16_gelu_lean_epilogue(sdp, M, N, K, use_bias):
+    """bias + GELU, N a multiple of 256, M spanning pairs: the 16-warp lean epilogue (C -> 4C GEMMs of the model)."""
+    A = rnd(M, K, seed=21, dtype=torch.bfloat16)
+    W = rnd(N, K, seed=22, scale=2 / math.sqrt(K), dtype=torch.bfloat16)
+    bias = rnd(N, seed=23, scale=0.5) if use_bias else None
+    out = torch.full((M + 3, N), 7.0, device="cuda", dtype=torch.bfloat16)     # guard rows behind M
+    sdp.ops.gemm(A, W, out[:M], bias=bias, act="gelu")
+    torch.cuda.synchronize()
+    ref = gemm_ref(A, W, bias, "gelu")
+    assert torch.isfinite(out.float()).all() and bool((out[M:] == 7.0).all())
+    assert (out[:M].float() - ref).abs().max() < 1.2e-2 * max(1.0, float(ref.abs().max()))
+    out2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    sdp.ops.gemm(A, W, out2, bias=bias, act="gelu")
+    assert torch.equal(out2, out[:M])                                          # run-to-run bit-exact
+
+
 def test_gemm_bf16_inplace_residual_and_passthrough(sdp):
     B, S, R, C, K = 7, 41, 5, 256, 128
     M = B * S
