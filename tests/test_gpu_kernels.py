@@ -104,19 +104,26 @@ def test_gemm_bf16_gelu_lean_epilogue(sdp, M, N, K, use_bias):
     assert torch.equal(out2, out[:M])                                          # run-to-run bit-exact
 
 
-def test_gemm_bf16_inplace_residual_and_passthrough(sdp):
-    B, S, R, C, K = 7, 41, 5, 256, 128
+@pytest.mark.parametrize("B,S,R,C,K,act", [(7, 41, 5, 256, 128, "gelu"), (40, 41, 5, 256, 128, "gelu"), (33, 261, 5, 768, 768, "gelu"),
+                                           (40, 41, 5, 512, 64, "none"), (9, 201, 5, 768, 768, "none"), (40, 41, 0, 256, 128, "none")])
+def test_gemm_bf16_inplace_residual_and_passthrough(sdp, B, S, R, C, K, act):
+    """In-place bf16 residual with pass-through rows (mixer 1x1 conv, o_proj), from one to many tiles."""
     M = B * S
     A = rnd(M, K, seed=7, dtype=torch.bfloat16)
     W = rnd(C, K, seed=8, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
     x = rnd(M, C, seed=9, dtype=torch.bfloat16)
-    ref = gemm_ref(A, W, None, "gelu", x)
+    ref = gemm_ref(A, W, None, act, x)
     rows = torch.arange(M, device="cuda") % S < R
     ref[rows] = x.float()[rows]
-    out = x.clone()
-    sdp.ops.gemm(A, W, out, act="gelu", residual=out, pass_rows=(S, R))
-    assert relerr(out, ref) < 1.2e-2
-    assert torch.equal(out[rows], x[rows])          # register rows bit-identical
+    out = torch.full((M + 2, C), 3.0, device="cuda", dtype=torch.bfloat16)
+    out[:M] = x
+    sdp.ops.gemm(A, W, out[:M], act=act, residual=out[:M], pass_rows=(S, R))
+    assert relerr(out[:M], ref) < 1.2e-2
+    assert torch.equal(out[:M][rows], x[rows])          # register rows bit-identical
+    assert bool((out[M:] == 3.0).all())                 # nothing written behind M
+    sep = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+    sdp.ops.gemm(A, W, sep, act=act, residual=x)                        # residual in a separate buffer: same bits
+    assert torch.equal(sep[~rows], out[:M][~rows])
 
 
 def test_gemm_bf16_patch_embed_epilogue(sdp):
