@@ -585,7 +585,17 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         xm[g * 128 + r] = m;
       }
-      pair_sync();                                            // partial maxima of tile t, partial sums of tile t - 1
+      // partial maxima of tile t, partial sums of tile t - 1: shared by the two warps of a row -- except after the
+      // transposed tail tile, whose row sums are spread over all eight softmax warps
+      if (tail_mode && t == tiles) {
+        asm volatile("bar.sync 9, 256;" ::: "memory");
+        if (stage_ok) {                                       // O(t - 2) was staged inside tail_tile with no P pass since:
+          if (lane == 0) bulk_wait_read<0>();                 // its TMA store must have read the staging rows
+          __syncwarp();
+        }
+      } else {
+        pair_sync();
+      }
       AT_T(26);
       if (t > 0) epilogue(t - 1, tail_mode && t == tiles);
       AT_T(27);
