@@ -82,3 +82,16 @@ eng = model.eval().to(dev).engine()
 x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(1234)).cuda().bfloat16()
 check("whole forward (sdp_forward)", lambda: (eng.forward(x, NUM_REGISTERS),))
 check("whole forward (op by op)", lambda: (eng.forward(x, NUM_REGISTERS, staged=True),))
+
+# the other BASELINE configs at their full batches, and the preprocessing kernels
+for name in ("S", "M"):
+    cfg_, b_ = CONFIGS[name]
+    m_ = sdp.MainModel.from_dict(**cfg_)
+    m_.load_state_dict(O.synth_state_dict(cfg_, seed=0), strict=True)
+    e_ = m_.eval().to(dev).engine()
+    x_ = torch.randn(b_, 3, 224, 224, generator=torch.Generator().manual_seed(99)).cuda().bfloat16()
+    check(f"whole forward {name} batch {b_}", lambda: (e_.forward(x_, NUM_REGISTERS),))
+import preprocess_oracle as P  # noqa: E402
+imgs = [P.synth_image(*hw, i) for i, hw in enumerate([(375, 500), (500, 333), (480, 640), (768, 1024), (224, 224), (90, 1200)])] * 64
+tf = sdp.val_transforms()
+check("val_transforms 384 images", lambda: (tf(imgs),))
