@@ -336,6 +336,40 @@ __global__ void im2col_kernel(const TI *__restrict__ x, TO *__restrict__ A, long
   }
 }
 
+// Even patch sizes: one thread per PAIR of neighbouring input pixels.  A warp reads 32 consecutive pairs of an image
+// row (coalesced) and writes them as p-element runs into the rows of the patches they belong to (a pair never
+// straddles two patches); the thread that owns a patch's first pair also zeroes the row's padding columns.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+im2col_pairs_kernel(const TI *__restrict__ x, TO *__restrict__ A, int ldA, int B, int H, int W, int p, int Gh, int Gw) {
+  const int Kc = 3 * p * p;
+  const int wp = W >> 1;                                     // pairs per image row
+  const long long n = (long long)B * 3 * H * wp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % wp);
+    const long long r = i / wp;                              // (b * 3 + c) * H + y
+    const int y = (int)(r % H);
+    const int bc = (int)(r / H);
+    const int c = bc % 3, b = bc / 3;
+    const int xx = 2 * w, j = xx / p, dx = xx - j * p, ii = y / p, dy = y - ii * p;
+    if (ii >= Gh || j >= Gw) continue;                       // pixels behind the last whole patch
+    float v0, v1;
+    if constexpr (sizeof(TI) == 4) {
+      const float2 t = *reinterpret_cast<const float2 *>(x + r * W + xx);
+      v0 = t.x; v1 = t.y;
+    } else {
+      const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(x + r * W + xx));
+      v0 = t.x; v1 = t.y;
+    }
+    TO *row = A + ((long long)(b * Gh + ii) * Gw + j) * ldA;
+    TO *dst = row + c * p * p + dy * p + dx;
+    if constexpr (sizeof(TO) == 4) *reinterpret_cast<float2 *>(dst) = make_float2(v0, v1);
+    else *reinterpret_cast<uint32_t *>(dst) = pack_bf16x2(v0, v1);
+    if (c == 0 && dy == 0 && dx == 0)
+      for (int k = Kc; k < ldA; ++k) row[k] = from_f<TO>(0.0f);
+  }
+}
+
 // one warp per row: log-sum-exp cross-entropy, smoothed-target BCE-with-logits, first-max argmax
 __global__ void __launch_bounds__(256)
 eval_metrics_kernel(const float *__restrict__ logits, long long ldl, const long long *__restrict__ labels, int B, int K,
@@ -503,6 +537,21 @@ extern "C" int sdp_im2col_patches(const void *x, int x_dtype, void *A, int a_dty
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int Gh = H / p, Gw = W / p;
   const int g = grid_for((long long)B * Gh * Gw * ldA);
+  // pair kernel: even patch size and width, pair-aligned buffers and row pitch, 32-bit sized problem
+  const size_t xs = dtype_size(x_dtype), as = dtype_size(a_dtype);
+  const bool pairs = p % 2 == 0 && W % 2 == 0 && ldA % 2 == 0 && ldA < (1 << 24) && (long long)B * Gh * Gw < (1ll << 31) &&
+                     (reinterpret_cast<uintptr_t>(x) % (2 * xs)) == 0 && (reinterpret_cast<uintptr_t>(A) % (2 * as)) == 0;
+  if (pairs) {
+    const int gp = grid_for((long long)B * 3 * H * (W / 2));
+#define I2P(TI, TO) im2col_pairs_kernel<TI, TO><<<gp, 256, 0, st>>>((const TI *)x, (TO *)A, (int)ldA, B, H, W, p, Gh, Gw)
+    if (x_dtype == SDP_F32 && a_dtype == SDP_BF16) I2P(float, bf16);
+    else if (x_dtype == SDP_F32) I2P(float, float);
+    else if (a_dtype == SDP_BF16) I2P(bf16, bf16);
+    else I2P(bf16, float);
+#undef I2P
+    SDP_LAUNCH_OK();
+    return 0;
+  }
 #define I2C(TI, TO) im2col_kernel<TI, TO><<<g, 256, 0, st>>>((const TI *)x, (TO *)A, ldA, B, H, W, p, Gh, Gw)
   if (x_dtype == SDP_F32 && a_dtype == SDP_BF16) I2C(float, bf16);
   else if (x_dtype == SDP_F32) I2C(float, float);

@@ -319,6 +319,20 @@ def test_im2col_matches_conv(sdp, p, H, W):
     assert (y - F.conv2d(x, w, stride=p)).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize("xd,ad", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("p,H,W,B", [(14, 224, 224, 5), (16, 224, 224, 3), (14, 28, 42, 2), (7, 21, 35, 2), (3, 9, 6, 4), (2, 8, 6, 3)])
+def test_im2col_exact_in_every_dtype(sdp, xd, ad, p, H, W, B):
+    """Pure data movement: every element equals the unfolded image converted once to the output dtype (even patch
+    sizes take the pair kernel, odd ones the scalar kernel), padding columns are zero."""
+    x = rnd(B, 3, H, W, seed=33).to(xd)
+    Kc = 3 * p * p
+    Kp = (Kc + 7) // 8 * 8
+    A = torch.full((B * (H // p) * (W // p), Kp), float("nan"), device="cuda", dtype=ad)
+    sdp.ops.im2col_patches(x, A, p)
+    ref = F.unfold(x.float(), p, stride=p).transpose(1, 2).reshape(-1, Kc).to(ad)
+    assert torch.equal(A[:, :Kc], ref) and bool((A[:, Kc:] == 0).all())
+
+
 def test_embed_tokens(sdp):
     B, T, R, C = 3, 12, 2, 16
     act = rnd(B, R + T, C, seed=31)
