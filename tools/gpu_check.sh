@@ -14,7 +14,7 @@ run() { # name timeout cmd...
   echo "[$name] rc=$rc $(( $(date +%s) - t0 ))s :: $(tail -n 1 "$OUT/$name.log" | cut -c1-160)" | tee -a $OUT/summary.txt
 }
 PT="python -m pytest -q -p no:cacheprovider -m gpu --timeout 600"
-GROUPS_DEFAULT="smoke gemm_bf16 gemm_fp32 act rows dwconv attention parity bench"
+GROUPS_DEFAULT="smoke gemm_bf16 gemm_fp32 act rows dwconv attention preprocess parity bench"
 for g in ${@:-$GROUPS_DEFAULT}; do
   case $g in
     smoke)     run smoke 600 python -c "import __graft_entry__ as g; g.smoke()" ;;
@@ -24,6 +24,7 @@ for g in ${@:-$GROUPS_DEFAULT}; do
     rows)      run k_rows 300 $PT tests/test_gpu_kernels.py -k "layernorm or pool_ln or bridges or im2col or embed_tokens" ;;
     dwconv)    run k_dwconv 300 $PT tests/test_gpu_kernels.py -k "ln_dwconv" ;;
     attention) run k_attention 300 $PT tests/test_gpu_kernels.py -k "attention" ;;
+    preprocess) run k_preprocess 300 $PT tests/test_gpu_preprocess.py ;;
     parity)    run parity 1500 $PT tests/test_gpu_parity.py ;;
     bench)     run bench 900 python bench.py --steps 5 --warmup 3 ;;
     bench_s)   run bench_s 600 python bench.py --steps 5 --warmup 3 --config S --no-cpu-baseline ;;
