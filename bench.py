@@ -126,8 +126,9 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_forward_rate(cfg, batch, warm_batch=2, threads=None):
-    """images/s of the oracle (reference-forward port) on the host cores, fp32."""
+def cpu_forward_rate(cfg, batch, warm_batch=2, threads=None, min_seconds=12.0, max_seconds=30.0):
+    """images/s of the oracle (reference-forward port) on the host cores, fp32: forwards of `batch` images repeated
+    until `min_seconds` of CPU work have been timed (a bounded sample of the workload)."""
     import torch
     import sdpnet_oracle as O
     threads = threads or os.cpu_count() or 1
@@ -138,10 +139,14 @@ def cpu_forward_rate(cfg, batch, warm_batch=2, threads=None):
     with torch.no_grad():
         O.forward(sd, cfg, torch.randn(warm_batch, 3, 224, 224, generator=g), NUM_REGISTERS)
         x = torch.randn(batch, 3, 224, 224, generator=g)
-        t0 = time.perf_counter()
-        O.forward(sd, cfg, x, NUM_REGISTERS)
-        dt = time.perf_counter() - t0
-    return batch / dt, threads, dt
+        n, t0 = 0, time.perf_counter()
+        while True:
+            O.forward(sd, cfg, x, NUM_REGISTERS)
+            n += batch
+            dt = time.perf_counter() - t0
+            if dt >= min_seconds or dt + dt / (n // batch) > max_seconds:
+                break
+    return n / dt, threads, dt, n
 
 
 def run_reference(args):
@@ -416,10 +421,10 @@ def main():
         line["hbm_peak_gbs"] = peaks["hbm"]
 
     if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (host cores are shared by the ranks)
-        v, cores, dt = cpu_forward_rate(cfg, args.cpu_batch)
+        v, cores, dt, n = cpu_forward_rate(cfg, args.cpu_batch)
         line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_batch} images, one fp32 forward of the oracle port "
-                                          f"(oracle/sdpnet_oracle.py) in {dt:.1f} s after a 2-image warm-up"}
+                                "sample": f"{n} images in fp32 forwards of {args.cpu_batch} through the oracle port "
+                                          f"(oracle/sdpnet_oracle.py), {dt:.1f} s after a 2-image warm-up"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
