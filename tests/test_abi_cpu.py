@@ -63,6 +63,7 @@ def test_ctypes_structs_follow_header_field_order(sdp):
     assert fields("sdp_mixer_weights") == [n for n, _ in L.MixerWeights._fields_]
     assert fields("sdp_model_desc") == [n for n, _ in L.ModelDesc._fields_]
     assert fields("sdp_workspace") == [n for n, _ in L.Workspace._fields_]
+    assert fields("sdp_image_desc") == [n for n, _ in L.ImageDesc._fields_] and ctypes.sizeof(L.ImageDesc) == 16
 
 
 def test_no_cpu_fallback_and_loud_errors(sdp):
