@@ -186,6 +186,19 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def algorithmic_flops_per_image(cfg, T, R):
+    """2 * MAC of one forward, SURVEY.md §8(d): patcher + nb * (cbn * mixer + encoder) + final encoder + head; the
+    mixers are counted on the T patch tokens, LN / GELU / softmax flops are not counted."""
+    C, m, nb, cbn, K, p, k = (cfg["embedding_dim"], cfg["ff_multiplication_factor"], cfg["num_blocks"], cfg["conv_block_num"],
+                              cfg["output_classes"], cfg["patch_size"], cfg["conv_kernel_size"])
+    S = T + R
+    patch = 2 * T * C * 3 * p * p
+    mixer = 2 * T * C * k * k + 2 * T * C * C + 16 * T * C * C
+    enc = 6 * S * C * C + 4 * S * S * C + 2 * S * C * C + 4 * m * S * C * C
+    head = 2 * C * K + 2 * K * K if cfg["head_output_from_register"] and not cfg["simple_mlp_output"] else 2 * C * K
+    return float(patch + nb * (cbn * mixer + enc) + enc + head)
+
+
 def gemm_flops_per_image(cfg, T, R):
     C, m, nb, cbn, K, p = (cfg["embedding_dim"], cfg["ff_multiplication_factor"], cfg["num_blocks"],
                            cfg["conv_block_num"], cfg["output_classes"], cfg["patch_size"])
@@ -256,8 +269,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import sdpnet_oracle as O
-    import sdpnet_b200 as sdp
+    import sdpnet_b200 as sdp          # the engine arm never touches oracle/ (only cpu_forward_rate / run_reference do)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -273,13 +285,11 @@ def main():
     p = cfg["patch_size"]
     T = (224 // p) ** 2
 
-    # weights: reference-layout state_dict -> nn.Module API (strict load) -> packed engine
-    sd = O.synth_state_dict(cfg, seed=0)
-    model = sdp.MainModel.from_dict(**cfg)
-    model.load_state_dict(sd, strict=True)
-    model = model.eval().to(dev)
+    # weights: random init of that architecture through the module API (the reference's own initialisation,
+    # model.py:121-126, seed 0 on every rank) -> packed engine
+    torch.manual_seed(0)
+    model = sdp.MainModel.from_dict(**cfg).eval().to(dev)
     eng = model.engine()
-    del sd
 
     # this rank's shard of the synthetic batch: host (pinned, fp32 like the reference's loaders) + device bf16
     g = torch.Generator().manual_seed(1234 + rank)
@@ -372,7 +382,7 @@ def main():
         return
 
     peaks = load_peaks()
-    flops_img = O.flops_per_image(cfg, 224, 224, R)
+    flops_img = algorithmic_flops_per_image(cfg, T, R)
     line = {
         "metric": METRIC if args.config == "XL" else f"SdP-Net {args.config} 224^2 bf16 fwd images/sec",
         "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
