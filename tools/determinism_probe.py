@@ -5,7 +5,6 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch  # noqa: E402
 import sdpnet_b200 as sdp  # noqa: E402
 
@@ -73,12 +72,10 @@ for name, fn in [("layernorm_rows", op_ln), ("ln_dwconv_slab", op_slab), ("gemm 
                  ("gemm ff2 bias res stats", op_ff2), ("gemm pw gelu res pass", op_pw)]:
     check(name, fn)
 
-import sdpnet_oracle as O  # noqa: E402
 from bench import CONFIGS, NUM_REGISTERS  # noqa: E402
 cfg, _ = CONFIGS["XL"]
-model = sdp.MainModel.from_dict(**cfg)
-model.load_state_dict(O.synth_state_dict(cfg, seed=0), strict=True)
-eng = model.eval().to(dev).engine()
+torch.manual_seed(0)
+eng = sdp.MainModel.from_dict(**cfg).eval().to(dev).engine()
 x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(1234)).cuda().bfloat16()
 check("whole forward (sdp_forward)", lambda: (eng.forward(x, NUM_REGISTERS),))
 check("whole forward (op by op)", lambda: (eng.forward(x, NUM_REGISTERS, staged=True),))
@@ -86,12 +83,11 @@ check("whole forward (op by op)", lambda: (eng.forward(x, NUM_REGISTERS, staged=
 # the other BASELINE configs at their full batches, and the preprocessing kernels
 for name in ("S", "M"):
     cfg_, b_ = CONFIGS[name]
-    m_ = sdp.MainModel.from_dict(**cfg_)
-    m_.load_state_dict(O.synth_state_dict(cfg_, seed=0), strict=True)
-    e_ = m_.eval().to(dev).engine()
+    e_ = sdp.MainModel.from_dict(**cfg_).eval().to(dev).engine()
     x_ = torch.randn(b_, 3, 224, 224, generator=torch.Generator().manual_seed(99)).cuda().bfloat16()
     check(f"whole forward {name} batch {b_}", lambda: (e_.forward(x_, NUM_REGISTERS),))
-import preprocess_oracle as P  # noqa: E402
-imgs = [P.synth_image(*hw, i) for i, hw in enumerate([(375, 500), (500, 333), (480, 640), (768, 1024), (224, 224), (90, 1200)])] * 64
+gi = torch.Generator().manual_seed(5)
+imgs = [torch.randint(0, 256, (*hw, 3), generator=gi, dtype=torch.uint8).numpy()
+        for hw in [(375, 500), (500, 333), (480, 640), (768, 1024), (224, 224), (90, 1200)]] * 64
 tf = sdp.val_transforms()
 check("val_transforms 384 images", lambda: (tf(imgs),))

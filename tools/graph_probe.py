@@ -7,9 +7,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import sdpnet_b200 as sdp  # noqa: E402
-import sdpnet_oracle as O  # noqa: E402
 from bench import CONFIGS, NUM_REGISTERS  # noqa: E402
 
 
@@ -17,9 +15,8 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     cfg, _ = CONFIGS["XL"]
-    model = sdp.MainModel.from_dict(**cfg)
-    model.load_state_dict(O.synth_state_dict(cfg, seed=0), strict=True)
-    eng = model.eval().to("cuda").engine()
+    torch.manual_seed(0)
+    eng = sdp.MainModel.from_dict(**cfg).eval().to("cuda").engine()
     x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(1234)).cuda().bfloat16()
     for _ in range(3):
         ref = eng.forward(x, NUM_REGISTERS)

@@ -11,10 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import preprocess_oracle as P  # noqa: E402
 import sdpnet_b200 as sdp  # noqa: E402
-import sdpnet_oracle as O  # noqa: E402
 from bench import CONFIGS, NUM_REGISTERS  # noqa: E402
 
 SIZES = [(375, 500), (500, 375), (333, 500), (500, 333), (480, 640), (360, 480), (500, 500), (768, 1024)]
@@ -24,10 +21,10 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     nb = int(sys.argv[2]) if len(sys.argv) > 2 else 6
     cfg, _ = CONFIGS["XL"]
-    model = sdp.MainModel.from_dict(**cfg)
-    model.load_state_dict(O.synth_state_dict(cfg, seed=0), strict=True)
-    model = model.eval().to("cuda")
-    base = [P.synth_image(h, w, i) for i, (h, w) in enumerate(SIZES)]
+    torch.manual_seed(0)
+    model = sdp.MainModel.from_dict(**cfg).eval().to("cuda")
+    gi = torch.Generator().manual_seed(5)
+    base = [torch.randint(0, 256, (h, w, 3), generator=gi, dtype=torch.uint8).numpy() for (h, w) in SIZES]
     imgs = [base[i % len(base)] for i in range(B)]
     labels = torch.randint(0, cfg["output_classes"], (B,), generator=torch.Generator().manual_seed(0)).cuda()
     tfs = [sdp.val_transforms(out_dtype=torch.bfloat16) for _ in range(2)]       # two pinned staging buffers
