@@ -54,6 +54,10 @@ def main():
     same = bool(torch.equal(out, ref2))
     t_graph = timed(g.replay)
     t_stream2 = timed(lambda: eng.forward(x, NUM_REGISTERS))
+    eng.forward_graph(x, NUM_REGISTERS)                              # captures
+    t_api = timed(lambda: eng.forward_graph(x, NUM_REGISTERS))       # the engine's own input copy + replay + output clone
+    print(f"Engine.forward_graph {t_api:.2f} ms ({B / t_api * 1e3:.0f} img/s), identical: "
+          f"{bool(torch.equal(eng.forward_graph(x, NUM_REGISTERS), ref2))}")
     print(f"B={B}: stream {t_stream:.2f} ms ({B / t_stream * 1e3:.0f} img/s) | graph replay {t_graph:.2f} ms "
           f"({B / t_graph * 1e3:.0f} img/s) | stream again {t_stream2:.2f} ms | graph output identical: {same}")
 
