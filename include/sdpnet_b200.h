@@ -155,7 +155,8 @@ int sdp_ln_dwconv_stats(const void *act, const float *stats, int parts, const fl
  * fragments of 32 channels' taps in registers and streams images past them (14 mma.sync per channel and image
  * for k = 7 instead of 12544 FMAs).  Needs `token_stats`: caller-owned scratch of 2 * B * Gh * Gw floats that
  * the call fills with (mean, rstd) of every spatial token and then consumes.  bf16 only;
- * sdp_ln_dwconv_slab_ok says whether the shape is covered (Gh <= 16, Gw in {8, 16}, C % 32 == 0, k in {3,5,7}). */
+ * sdp_ln_dwconv_slab_ok says whether the shape is covered (Gh, Gw <= 16 with an even token count, C % 32 == 0,
+ * C <= 2048, k in {3,5,7}). */
 int sdp_ln_dwconv_slab_ok(int Gh, int Gw, int C, int k, int dtype);
 int sdp_ln_dwconv_slab(const void *act, float *token_stats, const float *gamma, const float *beta,
                        const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int k,
