@@ -107,6 +107,40 @@ __device__ __forceinline__ float gelu_erf_fast3(float x) {
   const float e = fast_ex2(fmaf(q, t, -1.0f));
   return fmaf(-t, e, fmaxf(x, 0.0f));
 }
+// ---- packed fp32 pairs (sm_100 FADD2 / FFMA2: one issue slot for two lanes of fp32 math) ----------
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_erf_fast3 on two values at once, bit-identical to the scalar form: the polynomial runs in s = -t so that the
+// last step is a plain packed FMA (relu(x) + s * e); negating t flips the sign of the odd Horner steps only, every
+// intermediate has the same magnitude as in gelu_erf_fast3.  4.5 FMA-pipe slots per pair instead of 10.
+__device__ __forceinline__ void gelu_erf_fast3_x2(float &x0, float &x1) {
+  const uint64_t s = pack_f32x2(fmaxf(-fabsf(x0), -8.0f), fmaxf(-fabsf(x1), -8.0f));
+  uint64_t q = fma_f32x2(pack_f32x2(4.16165e-03f, 4.16165e-03f), s, pack_f32x2(4.573538e-02f, 4.573538e-02f));
+  q = fma_f32x2(q, s, pack_f32x2(-4.6493058e-01f, -4.6493058e-01f));
+  q = fma_f32x2(q, s, pack_f32x2(1.14956692e+00f, 1.14956692e+00f));
+  float a0, a1;
+  unpack_f32x2(fma_f32x2(q, s, pack_f32x2(-1.0f, -1.0f)), a0, a1);
+  const uint64_t r = fma_f32x2(s, pack_f32x2(fast_ex2(a0), fast_ex2(a1)), pack_f32x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+  unpack_f32x2(r, x0, x1);
+}
+
 #ifndef SDP_GELU_FAST_FN          // a translation unit whose outputs are bf16 may select gelu_erf_fast3
 #define SDP_GELU_FAST_FN gelu_erf_fast
 #endif
@@ -152,7 +186,17 @@ __device__ __forceinline__ void apply_act_vec(float *v, int act) {
       _Pragma("unroll") for (int j = 0; j < NV; ++j) v[j] = apply_act<EXACT>(v[j], ID); \
       break;
     SDP_ACT_CASE(SDP_ACT_RELU)
+#ifdef SDP_GELU_FAST_X2           // bf16-output epilogues: the packed-pair form of gelu_erf_fast3 (same bits)
+    case SDP_ACT_GELU:
+      if constexpr (!EXACT && NV % 2 == 0) {
+        _Pragma("unroll") for (int j = 0; j < NV; j += 2) gelu_erf_fast3_x2(v[j], v[j + 1]);
+      } else {
+        _Pragma("unroll") for (int j = 0; j < NV; ++j) v[j] = apply_act<EXACT>(v[j], SDP_ACT_GELU);
+      }
+      break;
+#else
     SDP_ACT_CASE(SDP_ACT_GELU)
+#endif
     SDP_ACT_CASE(SDP_ACT_GELU_TANH)
     SDP_ACT_CASE(SDP_ACT_TANH)
     SDP_ACT_CASE(SDP_ACT_SIGMOID)

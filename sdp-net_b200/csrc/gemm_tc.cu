@@ -12,6 +12,7 @@
 
 // this kernel only runs on bf16 operands and (bar the tiny head GEMMs) writes bf16: the degree-3 GELU is enough
 #define SDP_GELU_FAST_FN gelu_erf_fast3
+#define SDP_GELU_FAST_X2          // ... evaluated on packed fp32 pairs (FFMA2), bit-identical to the scalar form
 #include "tc5.cuh"
 
 namespace sdp {
@@ -217,7 +218,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4 *>(epi.bias + col + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            unpack_f32x2(add_f32x2(pack_f32x2(v[j], v[j + 1]), pack_f32x2(b.x, b.y)), v[j], v[j + 1]);
+            unpack_f32x2(add_f32x2(pack_f32x2(v[j + 2], v[j + 3]), pack_f32x2(b.z, b.w)), v[j + 2], v[j + 3]);
           }
         }
         apply_act_vec<32, false>(v, ACT < 0 ? epi.act : ACT);
