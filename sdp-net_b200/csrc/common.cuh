@@ -121,6 +121,11 @@ __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -323,18 +328,21 @@ __device__ __forceinline__ void epilogue_math_preres(const Epilogue &e, int c0, 
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b = __ldg(reinterpret_cast<const float4 *>(e.bias + c0 + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        unpack_f32x2(add_f32x2(pack_f32x2(v[j], v[j + 1]), pack_f32x2(b.x, b.y)), v[j], v[j + 1]);
+        unpack_f32x2(add_f32x2(pack_f32x2(v[j + 2], v[j + 3]), pack_f32x2(b.z, b.w)), v[j + 2], v[j + 3]);
       }
     }
     apply_act_vec<32, false>(v, act);
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float2 f;
-    f = unpack_bf16x2(r[j].x); v[8 * j] += f.x; v[8 * j + 1] += f.y;
-    f = unpack_bf16x2(r[j].y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
-    f = unpack_bf16x2(r[j].z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
-    f = unpack_bf16x2(r[j].w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+  for (int j = 0; j < 4; ++j) {                   // residual: packed fp32 pair adds (same sums as scalar adds)
+    const uint32_t rw[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 f = unpack_bf16x2(rw[q]);
+      unpack_f32x2(add_f32x2(pack_f32x2(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]), pack_f32x2(f.x, f.y)), v[8 * j + 2 * q],
+                   v[8 * j + 2 * q + 1]);
+    }
   }
 }
 

@@ -324,7 +324,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (col0 < 2 * epi.hn_C) {
             // one pass: sums of (v - shift) and (v - shift)^2 with the head's first column as the shift (no
             // cancellation even when |mean| >> std), four accumulators each so the adds are not one serial chain
-            float s1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, s2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            // (packed fp32 pairs: accumulator j & 3 is lane j & 1 of pair (j >> 1) & 1, the same sums as four scalars)
+            uint64_t s1p[2] = {0ull, 0ull}, s2p[2] = {0ull, 0ull};
             float shift = 0.0f;
 #pragma unroll 1
             for (int i = 0; i < HN; i += 32) {
@@ -333,13 +334,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tmem_ld_wait();
               if (lnf) ln_fold(v, col0 + i);
               if (i == 0) shift = v[0];
+              const uint64_t nshift = pack_f32x2(-shift, -shift);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float dlt = v[j] - shift;
-                s1[j & 3] += dlt;
-                s2[j & 3] = fmaf(dlt, dlt, s2[j & 3]);
+              for (int j = 0; j < 32; j += 2) {
+                const uint64_t dlt = add_f32x2(pack_f32x2(v[j], v[j + 1]), nshift);
+                s1p[(j >> 1) & 1] = add_f32x2(s1p[(j >> 1) & 1], dlt);
+                s2p[(j >> 1) & 1] = fma_f32x2(dlt, dlt, s2p[(j >> 1) & 1]);
               }
             }
+            float s1[4], s2[4];
+            unpack_f32x2(s1p[0], s1[0], s1[1]);
+            unpack_f32x2(s1p[1], s1[2], s1[3]);
+            unpack_f32x2(s2p[0], s2[0], s2[1]);
+            unpack_f32x2(s2p[1], s2[2], s2[3]);
             const float dm = ((s1[0] + s1[1]) + (s1[2] + s1[3])) * (1.0f / HN);
             mean = shift + dm;
             const float q = fmaxf(((s2[0] + s2[1]) + (s2[2] + s2[3])) * (1.0f / HN) - dm * dm, 0.0f) * HN;
@@ -357,14 +364,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (lnf && col0 + i + 32 <= epi.N) ln_fold(v, col0 + i);
           if constexpr (HN > 0) {
             if (hw != nullptr) {
+              const uint64_t nmean = pack_f32x2(-mean, -mean), rstd2 = pack_f32x2(rstd, rstd);
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
+              for (int j = 0; j < 32; j += 4) {   // ((v - mean) * rstd) * w + b on packed pairs: 1.5 slots per value
                 const float4 wv = __ldg(reinterpret_cast<const float4 *>(hw + i + j));
                 const float4 bv = __ldg(reinterpret_cast<const float4 *>(hb + i + j));
-                v[j] = (v[j] - mean) * rstd * wv.x + bv.x;
-                v[j + 1] = (v[j + 1] - mean) * rstd * wv.y + bv.y;
-                v[j + 2] = (v[j + 2] - mean) * rstd * wv.z + bv.z;
-                v[j + 3] = (v[j + 3] - mean) * rstd * wv.w + bv.w;
+                const uint64_t a0 = mul_f32x2(add_f32x2(pack_f32x2(v[j], v[j + 1]), nmean), rstd2);
+                const uint64_t a1 = mul_f32x2(add_f32x2(pack_f32x2(v[j + 2], v[j + 3]), nmean), rstd2);
+                unpack_f32x2(fma_f32x2(a0, pack_f32x2(wv.x, wv.y), pack_f32x2(bv.x, bv.y)), v[j], v[j + 1]);
+                unpack_f32x2(fma_f32x2(a1, pack_f32x2(wv.z, wv.w), pack_f32x2(bv.z, bv.w)), v[j + 2], v[j + 3]);
               }
             }
           }
