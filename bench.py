@@ -126,50 +126,62 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_forward_rate(cfg, batch, warm_batch=2, threads=None, min_seconds=12.0, max_seconds=30.0):
-    """images/s of the oracle (reference-forward port) on the host cores, fp32: forwards of `batch` images repeated
-    until `min_seconds` of CPU work have been timed (a bounded sample of the workload)."""
+def cpu_forward_fn(cfg):
+    """(callable x -> logits, kind, description): the reference's own `MainModel` (fp32, eval, CPU) from the vendored
+    baseline/_ref copy -- kind "reference" -- or, when no copy travelled to this box, the oracle port of it."""
     import torch
     import sdpnet_oracle as O
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
+    import reference_loader as RL
     torch.set_float32_matmul_precision("highest")
     sd = O.synth_state_dict(cfg, seed=0)
+    if RL.available():
+        model = RL.build_model(cfg, sd)
+        torch.set_float32_matmul_precision("highest")      # SURVEY.md §0.10
+        return (lambda x: model(x, NUM_REGISTERS)), "reference", "unmodified reference MainModel (baseline/_ref/model.py), torch CPU"
+    return (lambda x: O.forward(sd, cfg, x, NUM_REGISTERS)), "port", "oracle/sdpnet_oracle.py (port of the reference forward), torch CPU"
+
+
+def cpu_forward_rate(cfg, batch, warm_batch=2, threads=None, min_seconds=12.0, max_seconds=30.0):
+    """images/s of the reference forward on the host cores, fp32: forwards of `batch` images repeated until
+    `min_seconds` of CPU work have been timed (a bounded sample of the workload)."""
+    import torch
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    fwd, kind, what = cpu_forward_fn(cfg)
     g = torch.Generator().manual_seed(1234)
     with torch.no_grad():
-        O.forward(sd, cfg, torch.randn(warm_batch, 3, 224, 224, generator=g), NUM_REGISTERS)
+        fwd(torch.randn(warm_batch, 3, 224, 224, generator=g))
         x = torch.randn(batch, 3, 224, 224, generator=g)
         n, t0 = 0, time.perf_counter()
         while True:
-            O.forward(sd, cfg, x, NUM_REGISTERS)
+            fwd(x)
             n += batch
             dt = time.perf_counter() - t0
             if dt >= min_seconds or dt + dt / (n // batch) > max_seconds:
                 break
-    return n / dt, threads, dt, n
+    return n / dt, threads, dt, n, kind, what
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU forward (oracle port; the reference is pure PyTorch and
-    cannot travel to the GPU box) on all host cores, bounded sample per step."""
+    """--impl reference: the reference's own CPU forward -- the UNMODIFIED `MainModel` from baseline/_ref (vendored by
+    tools/vendor_reference.sh; falls back to the oracle port if that copy is absent) -- on all host cores, a bounded
+    sample of the workload per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    import sdpnet_oracle as O
     cfg, _ = CONFIGS[args.config]
     sample = args.cpu_batch
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    torch.set_float32_matmul_precision("highest")
-    sd = O.synth_state_dict(cfg, seed=0)
+    fwd, kind, what = cpu_forward_fn(cfg)
     x = torch.randn(sample, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
     with torch.no_grad():
         for _ in range(args.warmup):
-            O.forward(sd, cfg, x[:2], NUM_REGISTERS)
+            fwd(x[:2])
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            O.forward(sd, cfg, x, NUM_REGISTERS)
+            fwd(x)
         dt = time.perf_counter() - t0
     val = sample * args.steps / dt
     batch = args.batch or CONFIGS[args.config][1]
@@ -179,11 +191,77 @@ def run_reference(args):
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.config, batch), "num_registers": NUM_REGISTERS},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} images per step (fp32, oracle/sdpnet_oracle.py, torch CPU)"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": kind,
+                         "sample": f"{sample} images per step (fp32, {what})"},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_comparators(cfg, state_dict, x_host, dev, engine_logits, steps=3, warmup=2, compile_budget_s=420.0):
+    """The reference ITSELF on this GPU: the unmodified `MainModel` from baseline/_ref
+    with the engine's weights and batch, (a) eager under `torch.autocast('cuda', bfloat16)` -- its training /
+    inference precision path, training_tools.py:85-86 -- and (b) `torch.compile(model)` in eval, model_test.py:16,64
+    (fp32 parameters, TF32 matmuls as model.py:9 sets them, no autocast: exactly that script), plus (c) compile under
+    autocast, the fastest stock configuration.  PyTorch library kernels only; none of this repo's code runs here."""
+    import torch
+    import reference_loader as RL
+    out = {"unit": "images/s", "batch": int(x_host.shape[0]), "steps": steps, "warmup": warmup}
+    if not RL.available():
+        out["unavailable"] = "baseline/_ref not vendored (tools/vendor_reference.sh)"
+        return out
+    prec = torch.get_float32_matmul_precision()
+    model = RL.build_model(cfg, {k: v.detach().cpu() for k, v in state_dict.items()}).to(dev)
+    torch.set_float32_matmul_precision("high")          # what `import model` leaves behind (model.py:9)
+    x = x_host.to(dev)                                    # fp32 images, as the reference's loaders emit
+    B = x.shape[0]
+
+    def timed(fn):
+        with torch.no_grad():
+            for _ in range(warmup):
+                y = fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                y = fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+        return B * steps / (e0.elapsed_time(e1) / 1e3), y
+
+    def eager_autocast():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return model(x, NUM_REGISTERS)
+
+    try:
+        v, y = timed(eager_autocast)
+        out["eager_autocast_bf16"] = v
+        y = y.float()
+        out["engine_vs_reference_bf16_gpu"] = {
+            "logits_max_abs": float((engine_logits.float() - y).abs().max()),
+            "top1_agreement": float((engine_logits.argmax(-1) == y.argmax(-1)).float().mean())}
+        v, _ = timed(lambda: model(x, NUM_REGISTERS))
+        out["eager_fp32_tf32"] = v
+    except Exception as e:      # noqa: BLE001 -- a comparator must never take the engine line down
+        out["eager_error"] = repr(e)[:200]
+    try:
+        t0 = time.perf_counter()
+        cmodel = torch.compile(model)
+        v, _ = timed(lambda: cmodel(x, NUM_REGISTERS))
+        out["torch_compile"] = v
+        out["torch_compile_seconds_incl_compile"] = time.perf_counter() - t0
+        if time.perf_counter() - t0 < compile_budget_s:
+            def compiled_autocast():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return cmodel(x, NUM_REGISTERS)
+            v, _ = timed(compiled_autocast)
+            out["torch_compile_autocast_bf16"] = v
+    except Exception as e:      # noqa: BLE001
+        out["torch_compile_error"] = repr(e)[:300]
+    torch.set_float32_matmul_precision(prec)
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 def algorithmic_flops_per_image(cfg, T, R):
@@ -262,6 +340,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-comparators", action="store_true", help="skip the reference-on-this-GPU comparators")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     if args.impl == "reference":
@@ -277,7 +356,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SDP_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")     # NCCL logs to stderr; stdout stays the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg, default_batch = CONFIGS[args.config]
     B = args.batch or default_batch
@@ -430,11 +509,21 @@ def main():
             line["layernorm_gbs"] = nbytes / (fam["layernorm_rows"]["ms_per_step"] / 1e3) / 1e9
         line["hbm_peak_gbs"] = peaks["hbm"]
 
+    if not args.no_comparators and world == 1:
+        # the reference itself on this GPU, same weights and batch (eager autocast bf16, torch.compile)
+        line["gpu_comparators"] = gpu_comparators(cfg, model.state_dict(), x_host, dev, logits)
+        ec = line["gpu_comparators"].get("eager_autocast_bf16")
+        if ec:
+            best = max(v for k, v in line["gpu_comparators"].items()
+                       if k in ("eager_autocast_bf16", "eager_fp32_tf32", "torch_compile", "torch_compile_autocast_bf16"))
+            line["gpu_comparators"]["engine_over_eager_autocast"] = value / ec
+            line["gpu_comparators"]["engine_over_best_reference"] = value / best
+
     if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (host cores are shared by the ranks)
-        v, cores, dt, n = cpu_forward_rate(cfg, args.cpu_batch)
-        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                                "sample": f"{n} images in fp32 forwards of {args.cpu_batch} through the oracle port "
-                                          f"(oracle/sdpnet_oracle.py), {dt:.1f} s after a 2-image warm-up"}
+        v, cores, dt, n, kind, what = cpu_forward_rate(cfg, args.cpu_batch)
+        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": kind,
+                                "sample": f"{n} images in fp32 forwards of {args.cpu_batch} through the {what}, "
+                                          f"{dt:.1f} s after a 2-image warm-up"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
