@@ -298,6 +298,22 @@ def profile_families(eng, x, R, steps):
     pending = []
     orig = {}
 
+    def gemm_kind(a, k):
+        """GEMM launches by shape and epilogue: N x K + what rides in the epilogue."""
+        W = a[1]
+        tag = f"gemm N{W.shape[0]} K{k.get('K') or W.shape[1]}"
+        if k.get("ln_fold") is not None:
+            tag += " +lnfold"
+        if k.get("headnorm") is not None:
+            tag += " +headnorm"
+        if k.get("act", "none") not in ("none", 0):
+            tag += f" +{k['act']}"
+        if k.get("residual") is not None:
+            tag += " +residual" + ("(hi+lo)" if k.get("out_lo") is not None else "")
+        if k.get("stats_out") is not None:
+            tag += " +stats"
+        return tag
+
     def wrap(name, family):
         fn = getattr(ops, name)
         orig[name] = fn
@@ -307,7 +323,7 @@ def profile_families(eng, x, R, steps):
             e0.record()
             r = fn(*a, **k)
             e1.record()
-            pending.append((family, e0, e1))
+            pending.append((family, gemm_kind(a, k) if name == "gemm" else name, e0, e1))
             return r
         setattr(ops, name, timed)
 
@@ -322,11 +338,18 @@ def profile_families(eng, x, R, steps):
     finally:
         for name, fn in orig.items():
             setattr(ops, name, fn)
-    counts = {}
-    for family, e0, e1 in pending:
-        fam[family] = fam.get(family, 0.0) + e0.elapsed_time(e1)
+    counts, detail = {}, {}
+    for family, kind, e0, e1 in pending:
+        ms = e0.elapsed_time(e1)
+        fam[family] = fam.get(family, 0.0) + ms
         counts[family] = counts.get(family, 0) + 1
-    return {k: {"ms_per_step": v / steps, "launches_per_step": counts[k] // steps} for k, v in fam.items()}
+        d = detail.setdefault(kind, [0.0, 0])
+        d[0] += ms
+        d[1] += 1
+    out = {k: {"ms_per_step": v / steps, "launches_per_step": counts[k] // steps} for k, v in fam.items()}
+    out["_detail"] = {k: {"ms_per_launch": round(v[0] / v[1], 4), "launches_per_step": v[1] // steps,
+                          "ms_per_step": round(v[0] / steps, 3)} for k, v in sorted(detail.items(), key=lambda kv: -kv[1][0])}
+    return out
 
 
 def main():
@@ -481,6 +504,7 @@ def main():
 
     if not args.no_profile:
         fam = profile_families(eng, x_dev, R, 2)
+        detail = fam.pop("_detail")
         gf = gemm_flops_per_image(cfg, T, R) * B
         gms = fam["gemm_bf16_tc"]["ms_per_step"]
         nl = fam["gemm_bf16_tc"]["launches_per_step"]
@@ -499,6 +523,7 @@ def main():
             "how": "CUDA events around every launch of an instrumented op-by-op pass of the same forward",
         }
         line["kernel_families_ms_per_step"] = {k: round(v["ms_per_step"], 3) for k, v in fam.items()}
+        line["kernel_detail"] = detail
         # bandwidth-bound families, for the record (algorithmic bytes: read + write of [B,S,C] bf16)
         S = T + R
         if "ln_dwconv" in fam:

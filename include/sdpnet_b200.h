@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SDPNET_B200_ABI_VERSION 5
+#define SDPNET_B200_ABI_VERSION 6
 
 typedef enum { SDP_F32 = 0, SDP_BF16 = 1 } sdp_dtype;
 
@@ -85,6 +85,14 @@ int sdp_device_ok(void);
  *     v = rstd_r * (acc - mean_r * ln_s[c]) + ln_t[c]
  * where (mean_r, rstd_r) come from ln_stats (ln_parts partials per row, eps ln_eps, dim K).  Applied
  * before the head-norm / activation / residual steps; needs bias == NULL.
+ *
+ * Split residual stream (bf16 only).  The reference keeps its residual stream in fp32 even under autocast
+ * (model.py:129-149 adds bf16 GEMM outputs to an fp32 `x`); a bf16 stream rounds it at each of the 6 residual
+ * adds per block, which is 3-4 x the reference's own bf16 noise at XL depth.  With residual_lo / out_lo the
+ * stream is two bf16 planes of the same shape and pitch:  value = hi + lo,  hi = bf16(v),  lo = bf16(v - hi)
+ * (~16 mantissa bits).  `residual` / `out` are the hi planes -- which is also what every consumer GEMM, LayerNorm
+ * and the depthwise kernel read as their input, exactly the rounding the reference's autocast applies there --
+ * and only the residual epilogues, the head pooling and the raw-output bridge touch the lo plane.
  * --------------------------------------------------------------------------------------- */
 typedef struct {
   const void *A;        int64_t lda;   /* [M, K], row pitch in elements */
@@ -108,6 +116,8 @@ typedef struct {
   const float *ln_stats; int32_t ln_parts;        /* consumer side, or NULL */
   float ln_eps;
   const float *ln_s, *ln_t;                       /* [N] each */
+  const void *residual_lo;                        /* lo plane of the residual (pitch ldr), or NULL */
+  void *out_lo;                                   /* lo plane of the output (pitch ldo), or NULL */
 } sdp_gemm_args;
 
 int sdp_gemm(const sdp_gemm_args *args, void *stream);
@@ -125,8 +135,9 @@ int sdp_row_stats(const void *x, int64_t ldx, float *stats, int parts, int M, in
 int sdp_im2col_patches(const void *x, int x_dtype, void *A, int a_dtype, int64_t ldA,
                        int B, int H, int W, int p, void *stream);
 
-/* Register rows (layers.py:157,166 / :206-208): act[b, r, :] = table[r, :] for r < R. */
-int sdp_fill_registers(void *act, int dtype, const float *table, int B, int S, int R, int C,
+/* Register rows (layers.py:157,166 / :206-208): act[b, r, :] = table[r, :] for r < R.  act_lo: the lo plane of a
+ * split bf16 stream (see sdp_gemm), or NULL. */
+int sdp_fill_registers(void *act, void *act_lo, int dtype, const float *table, int B, int S, int R, int C,
                        void *stream);
 
 /* Token LayerNorm over the last dim (nn.LayerNorm eps 1e-5: layers.py:280,307; channel-first
@@ -179,8 +190,8 @@ int sdp_attention(const void *qkv, const float *qn_w, const float *qn_b, const f
 
 /* Head front (layers.py:464 `registers.mean(-2)` + LN at :445/:449, or AdaptiveAvgPool at
  * :457): out[b, :] = LN(mean over rows [row0, row0+nrows) of image b), LN skipped when
- * ln_w == NULL.  act [B, S, C] -> out [B, ldo]. */
-int sdp_pool_ln(const void *act, int dtype, int B, int S, int C, int row0, int nrows,
+ * ln_w == NULL.  act [B, S, C] (+ act_lo, the lo plane of a split bf16 stream, or NULL) -> out [B, ldo]. */
+int sdp_pool_ln(const void *act, const void *act_lo, int dtype, int B, int S, int C, int row0, int nrows,
                 const float *ln_w, const float *ln_b, float eps, void *out, int out_dtype,
                 int64_t ldo, void *stream);
 
@@ -188,8 +199,8 @@ int sdp_pool_ln(const void *act, int dtype, int B, int S, int C, int row0, int n
  * `return_raw_outputs` (model.py:147-149).  x NCHW [B,C,Gh,Gw], reg [B,R,C], both fp32. */
 int sdp_tokens_from_nchw(const float *x, const float *reg, void *act, int dtype, int B, int C,
                          int T, int R, void *stream);
-int sdp_tokens_to_nchw(const void *act, int dtype, float *x, float *reg, int B, int C, int T,
-                       int R, void *stream);
+int sdp_tokens_to_nchw(const void *act, const void *act_lo, int dtype, float *x, float *reg, int B, int C, int T,
+                       int R, void *stream);   /* act_lo: lo plane of a split bf16 stream, or NULL */
 
 /* Position-embedding add on token-major data (layers.py:162-168 / :205):
  * act[b, R + t, :] = actfn(act[b, R + t, :] + pos[t, :]); pos is [T, C] fp32.  (MainModel fuses
@@ -273,7 +284,8 @@ typedef struct {
 } sdp_model_desc;
 
 typedef struct {                 /* caller-allocated device workspaces */
-  void *act;      /* [B, S, C] */
+  void *act;      /* [B, S, C] the residual stream (bf16: its hi plane) */
+  void *act_lo;   /* [B, S, C] lo plane of the split bf16 residual stream (see sdp_gemm), or NULL: plain bf16 stream */
   void *norm;     /* [B, S, C] */
   void *qkv;      /* [B, S, 3C] */
   void *attn;     /* [B, S, C] */

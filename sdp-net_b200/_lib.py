@@ -40,6 +40,7 @@ class GemmArgs(C.Structure):
         ("stats_out", c_void_p), ("stats_parts", c_i32),
         ("ln_stats", c_void_p), ("ln_parts", c_i32), ("ln_eps", c_float),
         ("ln_s", c_void_p), ("ln_t", c_void_p),
+        ("residual_lo", c_void_p), ("out_lo", c_void_p),
     ]
 
 
@@ -74,7 +75,7 @@ class ImageDesc(C.Structure):
 
 class Workspace(C.Structure):
     _fields_ = [(n, c_void_p) for n in (
-        "act", "norm", "qkv", "attn", "hidden", "im2col", "pooled", "head_h", "stats")]
+        "act", "act_lo", "norm", "qkv", "attn", "hidden", "im2col", "pooled", "head_h", "stats")]
 
 
 # every symbol include/sdpnet_b200.h declares: name -> (restype, argtypes)
@@ -89,16 +90,16 @@ SYMBOLS = {
     "sdp_ln_dwconv_wants_stats": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "sdp_ln_dwconv_stats": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "sdp_im2col_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
-    "sdp_fill_registers": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "sdp_fill_registers": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_layernorm_rows": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_float, c_int, c_void_p]),
     "sdp_ln_dwconv_slab_ok": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "sdp_ln_dwconv_slab_stats": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "sdp_ln_dwconv_slab": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "sdp_ln_dwconv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "sdp_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
-    "sdp_pool_ln": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_i64, c_void_p]),
+    "sdp_pool_ln": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_i64, c_void_p]),
     "sdp_tokens_from_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "sdp_tokens_to_nchw": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "sdp_tokens_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_embed_tokens": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_eval_metrics": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
     "sdp_val_preprocess_workspace_bytes": (c_i64, [C.POINTER(ImageDesc), c_int, c_int, c_int, c_int, c_int]),
@@ -128,7 +129,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)   # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if handle.sdp_abi_version() != 5:
+        if handle.sdp_abi_version() != 6:
             raise SdpNetLibraryError("libsdpnet_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

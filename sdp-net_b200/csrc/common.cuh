@@ -218,6 +218,8 @@ struct Epilogue {
   const float *bias;
   const void *residual;
   void *out;
+  const void *res_lo;        // split residual stream (bf16 only): value = residual + res_lo, same pitch
+  void *out_lo;              // ... and out = bf16(v), out_lo = bf16(v - out)
   long long ldr, ldo;
   int M, N;
   int out_dtype, res_dtype;
@@ -280,20 +282,31 @@ __device__ __forceinline__ void epilogue_math(const Epilogue &e, const RowMap &m
   if (e.residual) {
     if (e.res_dtype == SDP_BF16) {
       const bf16 *rp = reinterpret_cast<const bf16 *>(e.residual) + m.rr * e.ldr + c0;
+      const bf16 *lp = e.res_lo ? reinterpret_cast<const bf16 *>(e.res_lo) + m.rr * e.ldr + c0 : nullptr;
       if (full) {
 #pragma unroll
         for (int j = 0; j < NV; j += 8) {
           const uint4 u = *reinterpret_cast<const uint4 *>(rp + j);
           float2 f;
-          f = unpack_bf16x2(u.x); v[j] += f.x; v[j + 1] += f.y;
-          f = unpack_bf16x2(u.y); v[j + 2] += f.x; v[j + 3] += f.y;
-          f = unpack_bf16x2(u.z); v[j + 4] += f.x; v[j + 5] += f.y;
-          f = unpack_bf16x2(u.w); v[j + 6] += f.x; v[j + 7] += f.y;
+          float r[8];
+          f = unpack_bf16x2(u.x); r[0] = f.x; r[1] = f.y;
+          f = unpack_bf16x2(u.y); r[2] = f.x; r[3] = f.y;
+          f = unpack_bf16x2(u.z); r[4] = f.x; r[5] = f.y;
+          f = unpack_bf16x2(u.w); r[6] = f.x; r[7] = f.y;
+          if (lp) {
+            const uint4 w = *reinterpret_cast<const uint4 *>(lp + j);
+            f = unpack_bf16x2(w.x); r[0] += f.x; r[1] += f.y;
+            f = unpack_bf16x2(w.y); r[2] += f.x; r[3] += f.y;
+            f = unpack_bf16x2(w.z); r[4] += f.x; r[5] += f.y;
+            f = unpack_bf16x2(w.w); r[6] += f.x; r[7] += f.y;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[j + q] += r[q];
         }
       } else {
 #pragma unroll
         for (int j = 0; j < NV; ++j)
-          if (c0 + j < e.N) v[j] += __bfloat162float(rp[j]);
+          if (c0 + j < e.N) v[j] += __bfloat162float(rp[j]) + (lp ? __bfloat162float(lp[j]) : 0.0f);
       }
     } else {
       const float *rp = reinterpret_cast<const float *>(e.residual) + m.rr * e.ldr + c0;
@@ -315,42 +328,12 @@ __device__ __forceinline__ void epilogue_math(const Epilogue &e, const RowMap &m
   }
 }
 
-// bias + activation + residual taken from registers (bf16 residual prefetched by the caller):
-// the staged tensor-core epilogue issues the next chunk's residual loads before it finishes this one.
-template <int ACT>
-__device__ __forceinline__ void epilogue_math_preres(const Epilogue &e, int c0, float *v, const uint4 *r, bool pass) {
-  const int act = ACT < 0 ? e.act : ACT;
-  if (pass) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-  } else {
-    if (e.bias) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(e.bias + c0 + j));
-        unpack_f32x2(add_f32x2(pack_f32x2(v[j], v[j + 1]), pack_f32x2(b.x, b.y)), v[j], v[j + 1]);
-        unpack_f32x2(add_f32x2(pack_f32x2(v[j + 2], v[j + 3]), pack_f32x2(b.z, b.w)), v[j + 2], v[j + 3]);
-      }
-    }
-    apply_act_vec<32, false>(v, act);
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {                   // residual: packed fp32 pair adds (same sums as scalar adds)
-    const uint32_t rw[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 f = unpack_bf16x2(rw[q]);
-      unpack_f32x2(add_f32x2(pack_f32x2(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]), pack_f32x2(f.x, f.y)), v[8 * j + 2 * q],
-                   v[8 * j + 2 * q + 1]);
-    }
-  }
-}
-
 template <int NV>
 __device__ __forceinline__ void epilogue_store(const Epilogue &e, const RowMap &m, int c0, const float *v, bool vec) {
   const bool full = vec && (c0 + NV <= e.N);
   if (e.out_dtype == SDP_BF16) {
     bf16 *op = reinterpret_cast<bf16 *>(e.out) + m.ro * e.ldo + c0;
+    bf16 *lp = e.out_lo ? reinterpret_cast<bf16 *>(e.out_lo) + m.ro * e.ldo + c0 : nullptr;
     if (full) {
 #pragma unroll
       for (int j = 0; j < NV; j += 8) {
@@ -360,11 +343,24 @@ __device__ __forceinline__ void epilogue_store(const Epilogue &e, const RowMap &
         u.z = pack_bf16x2(v[j + 4], v[j + 5]);
         u.w = pack_bf16x2(v[j + 6], v[j + 7]);
         *reinterpret_cast<uint4 *>(op + j) = u;
+        if (lp) {                            // what the bf16 rounding dropped, itself rounded to bf16
+          const uint32_t hw[4] = {u.x, u.y, u.z, u.w};
+          uint32_t lw[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            lw[q] = pack_bf16x2(v[j + 2 * q] - __uint_as_float(hw[q] << 16),
+                                v[j + 2 * q + 1] - __uint_as_float(hw[q] & 0xffff0000u));
+          *reinterpret_cast<uint4 *>(lp + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
       }
     } else {
 #pragma unroll
       for (int j = 0; j < NV; ++j)
-        if (c0 + j < e.N) op[j] = __float2bfloat16_rn(v[j]);
+        if (c0 + j < e.N) {
+          const bf16 h = __float2bfloat16_rn(v[j]);
+          op[j] = h;
+          if (lp) lp[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+        }
     }
   } else {
     float *op = reinterpret_cast<float *>(e.out) + m.ro * e.ldo + c0;
@@ -427,6 +423,8 @@ static inline bool epilogue_vec_ok(const Epilogue &e) {
   const size_t os = dtype_size(e.out_dtype), rs = dtype_size(e.res_dtype);
   bool ok = al(e.out) && (e.ldo * os) % 16 == 0;
   if (e.residual) ok = ok && al(e.residual) && (e.ldr * rs) % 16 == 0;
+  if (e.res_lo) ok = ok && al(e.res_lo);
+  if (e.out_lo) ok = ok && al(e.out_lo);
   if (e.bias) ok = ok && al(e.bias);
   return ok;
 }

@@ -64,6 +64,10 @@ int gemm(const Ctx &c, const void *A, long long lda, const void *W, long long ld
   a.M = M; a.N = N; a.K = K;
   a.dtype = c.m->dtype; a.out_dtype = out_dtype; a.res_dtype = c.m->dtype;
   a.act = act;
+  if (out == c.ws->act && c.ws->act_lo != nullptr) {   // the split residual stream: both planes, in place
+    a.out_lo = c.ws->act_lo;
+    if (res == c.ws->act) a.residual_lo = c.ws->act_lo;
+  }
   if (mask_regs && c.R > 0) { a.pass_seq = c.S; a.pass_rows = c.R; }
   if (fold) {
     a.ln_stats = c.ws->stats; a.ln_parts = c.parts; a.ln_eps = fold->eps; a.ln_s = fold->s; a.ln_t = fold->t;
@@ -114,27 +118,25 @@ int mixer(const Ctx &c, const sdp_mixer_weights &w) {
   const sdp_model_desc &m = *c.m;
   const int C = m.C, M = c.B * c.S, dt = m.dtype;
   const bool fold = m.ln_fold != 0;
-  const float *dw_stats = fold ? c.ws->stats : nullptr;
-  int dw_parts = c.parts;
-  if (!fold && c.ws->stats != nullptr && sdp_ln_dwconv_wants_stats(c.Gh, c.Gw, C, m.conv_k, c.R, dt)) {
-    // token (sum, sumsq) for the tensor-core depthwise kernel
-    if (int rc = sdp_row_stats(c.ws->act, C, c.ws->stats, 1, M, C, dt, c.st)) return rc;
-    dw_stats = c.ws->stats;
-    dw_parts = 1;
-  }
-  static const bool slab_on = [] { const char *e = getenv("SDP_DWCONV_SLAB"); return !(e && e[0] == '0'); }();
-  if (!fold && slab_on && c.ws->stats != nullptr && sdp_ln_dwconv_slab_ok(c.Gh, c.Gw, C, m.conv_k, dt)) {
-    // channel-stationary tensor-core kernel; the statistics workspace doubles as its (mean, rstd) scratch
-    // statistics: the producer GEMM's parts when it wrote them, else a pass over act.  The (mean, rstd) scratch is
-    // the head of the QKV buffer, which is dead between two encoders.
-    const bool have = c.emit && c.stats_fresh;
+  const bool have = (fold || c.emit) && c.stats_fresh;      // ws->stats holds the producer GEMM's (sum, sumsq) parts of act
+  if (c.ws->stats != nullptr && sdp_ln_dwconv_slab_ok(c.Gh, c.Gw, C, m.conv_k, dt)) {
+    // channel-stationary tensor-core kernel.  Token statistics: the producer GEMM's parts when it wrote them, else a
+    // pass over act.  Its (mean, rstd) scratch is the head of the QKV buffer (dead between two encoders) when the
+    // statistics workspace is in use, else the statistics workspace itself.
     float *scratch = have ? reinterpret_cast<float *>(c.ws->qkv) : c.ws->stats;
     if (int rc = sdp_ln_dwconv_slab_stats(c.ws->act, have ? c.ws->stats : nullptr, have ? c.parts : 0, scratch, w.ln1_g,
                                           w.ln1_b, w.w_dw, w.b_dw, c.ws->norm, c.B, c.Gh, c.Gw, C, m.conv_k, c.R, 1e-6f,
                                           c.st)) return rc;
-  } else if (int rc = sdp_ln_dwconv_stats(c.ws->act, dw_stats, dw_parts, w.ln1_g, w.ln1_b, w.w_dw, w.b_dw, c.ws->norm, c.B,
-                                          c.Gh, c.Gw, C, m.conv_k, c.R, 1e-6f, dt, c.st)) {
-    return rc;
+  } else {
+    const float *dw_stats = have ? c.ws->stats : nullptr;
+    int dw_parts = c.parts;
+    if (!have && c.ws->stats != nullptr && sdp_ln_dwconv_wants_stats(c.Gh, c.Gw, C, m.conv_k, c.R, dt)) {
+      if (int rc = sdp_row_stats(c.ws->act, C, c.ws->stats, 1, M, C, dt, c.st)) return rc;
+      dw_stats = c.ws->stats;
+      dw_parts = 1;
+    }
+    if (int rc = sdp_ln_dwconv_stats(c.ws->act, dw_stats, dw_parts, w.ln1_g, w.ln1_b, w.w_dw, w.b_dw, c.ws->norm, c.B,
+                                     c.Gh, c.Gw, C, m.conv_k, c.R, 1e-6f, dt, c.st)) return rc;
   }
   if (int rc = gemm(c, c.ws->norm, C, w.w_pw, C, w.b_pw, M, C, C, m.act, c.ws->act, c.ws->act, C, dt, true, nullptr, fold)) return rc;
   c.stats_fresh = fold;
@@ -165,14 +167,14 @@ extern "C" int sdp_forward(const sdp_model_desc *m, const sdp_workspace *ws, con
   c.Gh = H / m->patch; c.Gw = W / m->patch;
   c.T = c.Gh * c.Gw; c.S = c.T + R;
   const int C = m->C, dt = m->dtype, Kc3 = 3 * m->patch * m->patch;
-  static const bool slab_env = [] { const char *e = getenv("SDP_DWCONV_SLAB"); return !(e && e[0] == '0'); }();
   const int sparts = ws->stats != nullptr ? sdp_gemm_stats_parts(C, dt) : 0;
-  c.emit = !m->ln_fold && slab_env && sparts > 0 && sparts % 2 == 0 && sparts <= 16 && m->conv_block_num > 0 &&
+  c.emit = !m->ln_fold && sparts > 0 && sparts % 2 == 0 && sparts <= 16 && m->conv_block_num > 0 &&
            sdp_ln_dwconv_slab_ok(c.Gh, c.Gw, C, m->conv_k, dt);
   c.stats_fresh = false;
   c.parts = (m->ln_fold || c.emit) ? sparts : 0;
-  SDP_CHECK(!m->ln_fold || (dt == SDP_BF16 && c.parts > 0 && ws->stats != nullptr),
+  SDP_CHECK(!m->ln_fold || (dt == SDP_BF16 && c.parts > 0 && c.parts % 2 == 0 && ws->stats != nullptr),
             "sdp_forward: ln_fold needs bf16 and a statistics workspace");
+  SDP_CHECK(ws->act_lo == nullptr || dt == SDP_BF16, "sdp_forward: the split (hi + lo) residual stream is a bf16 feature");
 
   // patcher + position table + embedding activation, scattered behind the register rows
   // (layers.py:34-42, :152-168 / :202-209)
@@ -182,14 +184,16 @@ extern "C" int sdp_forward(const sdp_model_desc *m, const sdp_workspace *ws, con
     memset(&a, 0, sizeof(a));
     a.A = ws->im2col; a.lda = m->Kp; a.W = m->w_patch; a.ldw = m->Kp;
     a.residual = m->pos_table; a.ldr = C; a.res_dtype = SDP_F32; a.res_first = 1; a.res_mod = c.T;
-    a.out = ws->act; a.ldo = C; a.M = B * c.T; a.N = C; a.K = Kc3;
+    a.out = ws->act; a.out_lo = ws->act_lo; a.ldo = C; a.M = B * c.T; a.N = C; a.K = Kc3;
     a.dtype = dt; a.out_dtype = dt; a.act = m->embed_act;
     a.seq_in = c.T; a.seq_out = c.S; a.seq_off = R;
     if (int rc = sdp_gemm(&a, stream)) return rc;
   }
-  if (int rc = sdp_fill_registers(ws->act, dt, m->reg_table, B, c.S, R, C, stream)) return rc;
-  if (m->ln_fold)   // first statistics of the residual stream; every later producer GEMM refreshes its rows
+  if (int rc = sdp_fill_registers(ws->act, ws->act_lo, dt, m->reg_table, B, c.S, R, C, stream)) return rc;
+  if (m->ln_fold) {   // first statistics of the residual stream; every later producer GEMM refreshes its rows
     if (int rc = sdp_row_stats(ws->act, C, ws->stats, c.parts, B * c.S, C, dt, stream)) return rc;
+    c.stats_fresh = true;
+  }
 
   for (int i = 0; i < m->num_blocks; ++i) {            // model.py:139-140, layers.py:377-386
     if (m->conv_first)
@@ -205,9 +209,9 @@ extern "C" int sdp_forward(const sdp_model_desc *m, const sdp_workspace *ws, con
   // classification head (layers.py:443-465)
   const int K = m->classes;
   if (m->head_from_register) {
-    if (int rc = sdp_pool_ln(ws->act, dt, B, c.S, C, 0, R, m->head_ln_w, m->head_ln_b, 1e-5f, ws->pooled, dt, C, stream)) return rc;
+    if (int rc = sdp_pool_ln(ws->act, ws->act_lo, dt, B, c.S, C, 0, R, m->head_ln_w, m->head_ln_b, 1e-5f, ws->pooled, dt, C, stream)) return rc;
   } else {
-    if (int rc = sdp_pool_ln(ws->act, dt, B, c.S, C, R, c.T, nullptr, nullptr, 0.0f, ws->pooled, dt, C, stream)) return rc;
+    if (int rc = sdp_pool_ln(ws->act, ws->act_lo, dt, B, c.S, C, R, c.T, nullptr, nullptr, 0.0f, ws->pooled, dt, C, stream)) return rc;
   }
   const bool two = m->head_from_register && !m->head_simple;
   {

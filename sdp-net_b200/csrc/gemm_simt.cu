@@ -85,6 +85,8 @@ extern "C" int sdp_gemm(const sdp_gemm_args *a, void *stream) {
   e.bias = a->bias;
   e.residual = a->residual;
   e.out = a->out;
+  e.res_lo = a->residual_lo;
+  e.out_lo = a->out_lo;
   e.ldr = a->ldr;
   e.ldo = a->ldo;
   e.M = a->M;
@@ -106,6 +108,10 @@ extern "C" int sdp_gemm(const sdp_gemm_args *a, void *stream) {
   e.stats_out = a->stats_out; e.stats_parts = a->stats_parts;
   e.ln_stats = a->ln_stats; e.ln_parts = a->ln_parts; e.ln_K = a->K; e.ln_eps = a->ln_eps;
   e.ln_s = a->ln_s; e.ln_t = a->ln_t;
+  if (a->residual_lo || a->out_lo) {
+    SDP_CHECK(a->dtype == SDP_BF16 && a->out_dtype == SDP_BF16 && (a->residual_lo == nullptr || (a->residual && a->res_dtype == SDP_BF16)),
+              "sdp_gemm: a split (hi + lo) stream needs bf16 operands, bf16 output and a bf16 residual");
+  }
   if (a->stats_out) {
     SDP_CHECK(a->stats_parts > 0 && a->stats_parts == sdp_gemm_stats_parts(a->N, a->dtype) && a->out_dtype == SDP_BF16 &&
                   a->seq_in == 0,

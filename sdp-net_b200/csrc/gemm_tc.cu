@@ -23,17 +23,30 @@ constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;          // default: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (320 threads)
 constexpr int EPI_WARPS_WIDE = 16;    // heavy epilogues (GELU): four warps per TMEM lane quadrant (576 threads)
 
+// RSM (in-place residual epilogue): slots per epilogue warp, each [32 rows x 64 B] per plane (hi, or hi + lo)
+__host__ __device__ constexpr int rsm_slots(int cg) { return cg == 2 ? 3 : 2; }
+__host__ __device__ constexpr int out_bytes_for(bool lean, int rsm, int cg) {
+  return lean ? 65536 : rsm > 0 ? EPI_WARPS * rsm_slots(cg) * 2048 * rsm : 32768;
+}
+
 template <int BN, int STAGES, int CG = 1, int OUTB = 32768>
 struct SmemLayout {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = (BN / CG) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_OFF = STAGES * STAGE_BYTES;              // epilogue staging: 8 warps x 2 x [32 rows x 64 B]
-  static constexpr int OUT_BYTES = OUTB;                            // 2 KB slots: 8 warps x 2 (32 KB) or 16 warps x 2 (64 KB)
+  static constexpr int OUT_OFF = STAGES * STAGE_BYTES;              // epilogue staging: 2 KB [32 rows x 64 B] slots
+  static constexpr int OUT_BYTES = OUTB;                            // 8 warps x 2 (32 KB), 16 warps x 2 (64 KB), or the RSM slots
   static constexpr int BAR_OFF = OUT_OFF + OUT_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;   // barriers + slack for 1024B alignment
   static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
+
+// pipeline depth that fits next to `out_bytes` of epilogue staging
+__host__ __device__ constexpr int stages_for(int bn, int cg, int out_bytes, int want) {
+  const int stage = BLOCK_M * BLOCK_K * 2 + (bn / cg) * BLOCK_K * 2;
+  const int fit = (232448 - 512 - 1024 - out_bytes) / stage;
+  return fit < want ? fit : want;
+}
 
 __host__ __device__ constexpr uint32_t tmem_cols_for(int bn) {
   return 2 * bn <= 32 ? 32u : 2 * bn <= 64 ? 64u : 2 * bn <= 128 ? 128u : 2 * bn <= 256 ? 256u : 512u;
@@ -43,16 +56,29 @@ __host__ __device__ constexpr uint32_t tmem_cols_for(int bn) {
 // 32-column chunk, 64B-swizzled, double-buffered per warp) instead of 16-byte-per-row global stores.
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: launched as clusters of 2 (one TPC); the pair owns a
 // 256 x BN tile, B traffic from L2 halves and the smem ring gets deeper for the same capacity.
-// LEAN (16 epilogue warps, four per scheduler): bias + activation only, N a multiple of BN, every chunk staged and
-// TMA-stored; none of the residual / pass-through / statistics / LN-fold / head-norm paths are compiled in, which
-// is what lets the epilogue fit the 96 registers a 18-warp CTA leaves per thread.
-template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1, int EW = EPI_WARPS, bool LEAN = false>
+// LEAN (16 epilogue warps, four per scheduler): bias + activation (LEAN = 1) or the folded LayerNorm + activation
+// (LEAN = 2: v = rstd * (acc - mean * s[c]) + t[c], row statistics from the producer GEMM), N a multiple of BN,
+// every chunk staged and TMA-stored; none of the residual / pass-through / statistics / head-norm paths are
+// compiled in, which is what lets the epilogue fit the 96 registers a 18-warp CTA leaves per thread.
+// RSM (in-place residual GEMMs, out == residual: the four GEMMs per block that write the residual stream): the
+// residual tile travels like the operands -- each epilogue warp TMA-loads the [32 x 32] box it is going to
+// overwrite into its own shared-memory slot one to two chunks ahead (across tile boundaries), adds the accumulator
+// in place, and TMA-stores the slot back.  No residual registers, no exposed global-load latency.  RSM = 2: the
+// stream is split in two bf16 planes (hi = bf16(v), lo = bf16(v - hi), ~16 mantissa bits), both planes ride in
+// the slot; the consumers' A operand is the hi plane.  Pass-through rows (register tokens in the mixers) simply
+// leave their slot rows untouched.
+template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1, int EW = EPI_WARPS, int LEAN = 0, int RSM = 0>
 __global__ void __launch_bounds__((2 + EW) * 32, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ CUtensorMap tmO, const Epilogue epi, const int K, const int flags) {
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
+                    const Epilogue epi, const int K, const int flags) {
   const int vec_ok = flags & 1;
-  const bool nofeed = (flags & 2) != 0;   // SDP_GEMM_NOFEED=1 (diagnostic): no TMA loads, MMAs run on stale shared memory
-  using L = SmemLayout<BN, STAGES, CG, LEAN ? 65536 : 32768>;
+#ifdef SDP_DIAG
+  const bool nofeed = (flags & 2) != 0;   // diagnostic build only: no TMA loads, MMAs run on stale shared memory
+#else
+  constexpr bool nofeed = false;
+#endif
+  using L = SmemLayout<BN, STAGES, CG, out_bytes_for(LEAN != 0, RSM, CG)>;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   // swizzle-128B tiles need 1024-byte alignment
@@ -64,6 +90,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + L::BAR_OFF + 8 * (2 * STAGES + 4));
+  constexpr int NSLOT = rsm_slots(CG);
+  auto res_bar = [&](int ew, int sl) { return bar_base + 8u * (2 * STAGES + 5 + ew * NSLOT + sl); };   // RSM only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -73,6 +101,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     if (STAGED) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+    if (RSM == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO2) : "memory");
+    if constexpr (RSM > 0)
+      for (int i = 0; i < EW * NSLOT; ++i) mbar_init(res_bar(0, i), 1);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -183,9 +214,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if constexpr (LEAN) {
-    // ================= lean epilogue: bias + activation, four warps per TMEM lane quadrant =================
-    static_assert(!LEAN || (EW == 16 && HN == 0 && STAGED && BN % 128 == 0), "lean epilogue: 16 warps, staged, no head-norm");
+  } else if constexpr (LEAN != 0) {
+    // ================= lean epilogue: bias (or folded LayerNorm) + activation, four warps per TMEM lane quadrant =================
+    static_assert(LEAN == 0 || (EW == 16 && HN == 0 && STAGED && BN % 128 == 0 && RSM == 0), "lean epilogue: 16 warps, staged, no head-norm");
     constexpr int WCOLS = BN / 4;                  // columns per warp
     const int quad = warp & 3, part = (warp - 2) >> 2;
     const uint32_t stage_base = smem_base + L::OUT_OFF + static_cast<uint32_t>(warp - 2) * 4096;   // two 2 KB slots
@@ -197,6 +228,24 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * TILE_M + rank * BLOCK_M;
       const int n0 = (tile % n_tiles) * BN + part * WCOLS;
+      uint64_t nmean2 = 0ull, rstd2 = 0ull;
+      if constexpr (LEAN == 2) {                   // this row's (mean, rstd) from the producer's column-part sums
+        const int row = m0 + quad * 32 + lane;
+        float s1 = 0.0f, s2 = 0.0f;
+        if (row < epi.M) {
+          const float4 *sp = reinterpret_cast<const float4 *>(epi.ln_stats + (long long)row * epi.ln_parts * 2);
+          for (int p2 = 0; p2 < epi.ln_parts / 2; ++p2) {
+            const float4 t = __ldg(sp + p2);
+            s1 += t.x + t.z;
+            s2 += t.y + t.w;
+          }
+        }
+        const float inv = 1.0f / (float)epi.ln_K;
+        const float mean = s1 * inv;
+        const float rstd = rsqrtf(fmaxf(s2 * inv - mean * mean, 0.0f) + epi.ln_eps);
+        nmean2 = pack_f32x2(-mean, -mean);
+        rstd2 = pack_f32x2(rstd, rstd);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + part * WCOLS;
@@ -214,7 +263,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         const int col = n0 + c;
-        if (epi.bias) {
+        if constexpr (LEAN == 2) {                 // v = rstd * (acc - mean * s[c]) + t[c]: two packed FMAs per pair
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sv = __ldg(reinterpret_cast<const float4 *>(epi.ln_s + col + j));
+            const float4 tv = __ldg(reinterpret_cast<const float4 *>(epi.ln_t + col + j));
+            const uint64_t a0 = fma_f32x2(pack_f32x2(sv.x, sv.y), nmean2, pack_f32x2(v[j], v[j + 1]));
+            const uint64_t a1 = fma_f32x2(pack_f32x2(sv.z, sv.w), nmean2, pack_f32x2(v[j + 2], v[j + 3]));
+            unpack_f32x2(fma_f32x2(a0, rstd2, pack_f32x2(tv.x, tv.y)), v[j], v[j + 1]);
+            unpack_f32x2(fma_f32x2(a1, rstd2, pack_f32x2(tv.z, tv.w)), v[j + 2], v[j + 3]);
+          }
+        } else if (epi.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4 *>(epi.bias + col + j));
@@ -246,6 +305,140 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
     if (lane == 0) bulk_wait_read<0>();
+  } else if constexpr (RSM > 0) {
+    // ================= in-place residual epilogue (see the kernel comment) =================
+    static_assert(RSM == 0 || (EW == 8 && HN == 0 && STAGED && BN % 64 == 0), "RSM epilogue: 8 warps, staged, no head-norm");
+    constexpr uint32_t SLOT_BYTES = 2048u * RSM;             // hi plane [32 x 64 B] (+ lo plane behind it)
+    constexpr int HCOLS = BN / 2;                            // columns per warp (two warps per TMEM lane quadrant)
+    constexpr int CPW = HCOLS / 32;                          // 32-column chunks per warp and tile
+    const int quad = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
+    const uint32_t slot_base = smem_base + L::OUT_OFF + static_cast<uint32_t>(ew) * (NSLOT * SLOT_BYTES);
+    const uint32_t rowoff = lane * 64, sw = (lane >> 1) & 3;
+    // prefetch cursor: walks this warp's chunks (tile-major, then 32-column chunks, columns past N skipped) ahead
+    // of the compute loop; both enumerate the same sequence, so chunk number i always lives in slot i % NSLOT
+    int pf_tile = unit0, pf_k = 0, issued = 0;
+    auto pf_col = [&]() { return (pf_tile % n_tiles) * BN + half * HCOLS + pf_k * 32; };
+    auto pf_skip = [&]() {                                   // settle on the next chunk that has columns < N
+      while (pf_tile < num_tiles && pf_col() >= epi.N) {
+        if (++pf_k == CPW) { pf_k = 0; pf_tile += unit_stride; }
+      }
+    };
+    auto issue_load = [&]() {                                // warp-uniform bookkeeping, lane 0 issues
+      pf_skip();
+      if (pf_tile < num_tiles) {
+        const int sl = issued % NSLOT;
+        if (lane == 0) {
+          const uint32_t dst = slot_base + sl * SLOT_BYTES, bar = res_bar(ew, sl);
+          const int col = pf_col(), row = (pf_tile / n_tiles) * TILE_M + rank * BLOCK_M + quad * 32;
+          mbar_expect_tx(bar, SLOT_BYTES);
+          tma_load_2d(dst, &tmO, bar, col, row);
+          if constexpr (RSM == 2) tma_load_2d(dst + 2048, &tmO2, bar, col, row);
+        }
+        ++issued;
+        if (++pf_k == CPW) { pf_k = 0; pf_tile += unit_stride; }
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < NSLOT - 1; ++d) issue_load();
+    int done = 0, it = 0;
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * TILE_M + rank * BLOCK_M;
+      const int n0 = (tile % n_tiles) * BN + half * HCOLS;
+      const RowMap rm = map_row(epi, m0 + quad * 32 + lane);
+      const int nchunks = n0 >= epi.N ? 0 : (epi.N - n0 >= HCOLS ? CPW : (epi.N - n0 + 31) / 32);
+      uint64_t s1p = 0ull, s2p = 0ull;                       // producer statistics of the hi values this row stores
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * HCOLS;
+      if (nchunks == 0) {                                    // nothing of this tile is ours: hand the accumulator back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_cta(tempty_bar(acc), 0);
+        }
+      }
+#pragma unroll 1
+      for (int k = 0; k < nchunks; ++k, ++done) {
+        const int sl = done % NSLOT;
+        const uint32_t slot = slot_base + sl * SLOT_BYTES;
+        float v[32];
+        tmem_ld32(taddr + k * 32, v);
+        mbar_wait(res_bar(ew, sl), (done / NSLOT) & 1);      // this chunk's residual box has landed
+        tmem_ld_wait();
+        if (k == nchunks - 1) {                              // this warp's share of the accumulator is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
+            else mbar_arrive_cta(tempty_bar(acc), 0);
+          }
+        }
+        const int col = n0 + k * 32;
+        if (rm.live) {
+          if (epi.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4 *>(epi.bias + col + j));
+              unpack_f32x2(add_f32x2(pack_f32x2(v[j], v[j + 1]), pack_f32x2(b.x, b.y)), v[j], v[j + 1]);
+              unpack_f32x2(add_f32x2(pack_f32x2(v[j + 2], v[j + 3]), pack_f32x2(b.z, b.w)), v[j + 2], v[j + 3]);
+            }
+          }
+          apply_act_vec<32, false>(v, ACT < 0 ? epi.act : ACT);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t a = slot + rowoff + ((j ^ sw) << 4);
+            uint32_t h[4], l[4] = {0u, 0u, 0u, 0u};
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(a));
+            if constexpr (RSM == 2)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]) : "r"(a + 2048));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              // residual = hi + lo (exact in fp32), then v + residual; bf16 halves widen by a shift / mask
+              uint64_t r = pack_f32x2(__uint_as_float(h[q] << 16), __uint_as_float(h[q] & 0xffff0000u));
+              if constexpr (RSM == 2)
+                r = add_f32x2(r, pack_f32x2(__uint_as_float(l[q] << 16), __uint_as_float(l[q] & 0xffff0000u)));
+              const uint64_t x = add_f32x2(pack_f32x2(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]), r);
+              float x0, x1;
+              unpack_f32x2(x, x0, x1);
+              h[q] = pack_bf16x2(x0, x1);
+              const uint64_t hf = pack_f32x2(__uint_as_float(h[q] << 16), __uint_as_float(h[q] & 0xffff0000u));
+              if constexpr (RSM == 2) {                      // what the rounding dropped: x - hi (exact), rounded to bf16
+                float d0, d1;
+                unpack_f32x2(fma_f32x2(hf, pack_f32x2(-1.0f, -1.0f), x), d0, d1);
+                l[q] = pack_bf16x2(d0, d1);
+              }
+              s1p = add_f32x2(s1p, hf);
+              s2p = fma_f32x2(hf, hf, s2p);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+            if constexpr (RSM == 2)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        // the box that last left from the slot we are about to refill has been read (it was committed a whole
+        // chunk ago); then: next residual box in, this chunk out
+        if (lane == 0) bulk_wait_read<0>();
+        issue_load();
+        if (lane == 0) {
+          tma_store_2d(&tmO, slot, col, m0 + quad * 32);
+          if constexpr (RSM == 2) tma_store_2d(&tmO2, slot + 2048, col, m0 + quad * 32);
+          bulk_commit();
+        }
+      }
+      if (epi.stats_out != nullptr && rm.live) {          // a column half past N still owns its (zero) part
+        float a0, a1, b0, b1;
+        unpack_f32x2(s1p, a0, a1);
+        unpack_f32x2(s2p, b0, b1);
+        const int part = (tile % n_tiles) * 2 + half;
+        *reinterpret_cast<float2 *>(epi.stats_out + (rm.ro * epi.stats_parts + part) * 2) = make_float2(a0 + a1, b0 + b1);
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();
   } else {
     // ================= epilogue =================
     // Two warps per TMEM lane quadrant: warps 2..5 take the low half of the tile's columns,
@@ -260,10 +453,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr int SLOTS = 16 / EW;             // 2 KB staging slots per warp (8 warps: double-buffered)
     const uint32_t stage_base = smem_base + L::OUT_OFF + static_cast<uint32_t>(warp - 2) * (SLOTS * 2048);
     uint32_t cc = 0;                           // chunks this warp has staged (slot = cc % SLOTS)
-    // in-place bf16 residual (the common case): each chunk's residual is fetched one chunk ahead
-    const bool res_fast = STAGED && epi.residual != nullptr && epi.res_dtype == SDP_BF16 && !epi.res_first &&
-                          epi.res_mod == 0 && vec_ok != 0;
-    const int col_end = u_end * UNIT;          // end of this warp's column range inside the tile
     int it = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
       const int acc = it & 1;
@@ -271,16 +460,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m0 = (tile / n_tiles) * TILE_M + rank * BLOCK_M;
       const int n0 = (tile % n_tiles) * BN;
       const RowMap rm = map_row(epi, m0 + quad * 32 + lane);
-      uint4 rnext[4] = {};
-      const bf16 *res_row = reinterpret_cast<const bf16 *>(epi.residual) + rm.rr * epi.ldr;
-      auto fetch_res = [&](int col) {            // col: absolute column of a 32-wide chunk
-        if (res_fast && (rm.live || rm.pass) && col + 32 <= epi.N) {
-          const uint4 *p = reinterpret_cast<const uint4 *>(res_row + col);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rnext[j] = p[j];
-        }
-      };
-      fetch_res(n0 + u_begin * UNIT);            // before the accumulator is even ready
       // LayerNorm folded into this GEMM: the row's (mean, rstd) from the producer's column-part sums
       const bool lnf = epi.ln_stats != nullptr;
       float ln_mean = 0.0f, ln_rstd = 1.0f;
@@ -297,14 +476,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ln_rstd = rsqrtf(fmaxf(s2 * inv - ln_mean * ln_mean, 0.0f) + epi.ln_eps);
       }
       auto ln_fold = [&](float *v, int col) {      // v = rstd * (acc - mean * s[col..]) + t[col..], 32 columns
+        const uint64_t nmean2 = pack_f32x2(-ln_mean, -ln_mean), rstd2 = pack_f32x2(ln_rstd, ln_rstd);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 32; j += 4) {          // two packed FMAs per pair
           const float4 sv = __ldg(reinterpret_cast<const float4 *>(epi.ln_s + col + j));
           const float4 tv = __ldg(reinterpret_cast<const float4 *>(epi.ln_t + col + j));
-          v[j] = fmaf(ln_rstd, fmaf(-ln_mean, sv.x, v[j]), tv.x);
-          v[j + 1] = fmaf(ln_rstd, fmaf(-ln_mean, sv.y, v[j + 1]), tv.y);
-          v[j + 2] = fmaf(ln_rstd, fmaf(-ln_mean, sv.z, v[j + 2]), tv.z);
-          v[j + 3] = fmaf(ln_rstd, fmaf(-ln_mean, sv.w, v[j + 3]), tv.w);
+          const uint64_t a0 = fma_f32x2(pack_f32x2(sv.x, sv.y), nmean2, pack_f32x2(v[j], v[j + 1]));
+          const uint64_t a1 = fma_f32x2(pack_f32x2(sv.z, sv.w), nmean2, pack_f32x2(v[j + 2], v[j + 3]));
+          unpack_f32x2(fma_f32x2(a0, rstd2, pack_f32x2(tv.x, tv.y)), v[j], v[j + 1]);
+          unpack_f32x2(fma_f32x2(a1, rstd2, pack_f32x2(tv.z, tv.w)), v[j + 2], v[j + 3]);
         }
       };
       float st1 = 0.0f, st2 = 0.0f;              // producer side: sums of the bf16 values this thread stores
@@ -381,13 +561,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               epilogue_row<32, false, ACT>(epi, rm, col0 + i, v, vec_ok != 0);
             } else {
               const int col = col0 + i;
-              if (res_fast && col + 32 <= epi.N) {
-                uint4 rcur[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-                if (c + i + 32 < col_end) fetch_res(col + 32);
-                if (rm.live || rm.pass) epilogue_math_preres<ACT>(epi, col, v, rcur, rm.pass);
-              } else if (rm.live) {
+              if (rm.live) {
                 epilogue_math<32, false, ACT>(epi, rm, col, v, vec_ok != 0);
               } else {
                 epilogue_passthrough<32>(epi, rm, col, v, vec_ok != 0);
@@ -534,14 +708,13 @@ static int get_tensor_map(const void *ptr, uint64_t rows, uint64_t cols, uint64_
   return 0;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+static int num_sms() {            // per device: a process may drive several GPUs
+  static int n[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (n[dev] == 0) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
 }
 
 int make_tensor_map_bf16(const void *ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows,
@@ -604,15 +777,28 @@ static bool staged_ok(const Epilogue &e) {
          (e.ldo * 2) % 16 == 0 && (e.pass_seq == 0 || e.residual != nullptr);
 }
 
-template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1, int EW = EPI_WARPS, bool LEAN = false>
-static int launch_tc2(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &to, const Epilogue &e, int K,
-                      cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES, CG, LEAN ? 65536 : 32768>;
-  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT, HN, STAGED, CG, EW, LEAN>;
-  static bool configured = false;
-  if (!configured) {
+// In-place residual GEMM the RSM epilogue covers: out == residual (and out_lo == res_lo), bf16, plain row mapping,
+// whole 32-column chunks.  Returns the number of planes (1: hi only, 2: hi + lo), 0 if not applicable.
+static int rsm_planes(const Epilogue &e) {
+  if (!staged_ok(e) || e.residual == nullptr || e.residual != e.out || e.res_dtype != SDP_BF16 || e.res_first ||
+      e.res_mod != 0 || e.ldr != e.ldo || e.N % 32 != 0 || e.hn_d != 0 || e.ln_stats != nullptr || !epilogue_vec_ok(e))
+    return 0;
+  if (e.out_lo == nullptr && e.res_lo == nullptr) return 1;
+  return (e.out_lo != nullptr && e.out_lo == e.res_lo) ? 2 : 0;
+}
+
+template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1, int EW = EPI_WARPS, int LEAN = 0, int RSM = 0>
+static int launch_tc2(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &to, const CUtensorMap &to2,
+                      const Epilogue &e, int K, cudaStream_t st) {
+  using L = SmemLayout<BN, STAGES, CG, out_bytes_for(LEAN != 0, RSM, CG)>;
+  static_assert(STAGES >= 2, "pipeline too shallow");
+  auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT, HN, STAGED, CG, EW, LEAN, RSM>;
+  static unsigned long long configured = 0;     // one bit per device ordinal
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((configured >> (dev & 63)) & 1ull)) {
     SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
+    configured |= 1ull << (dev & 63);
   }
   const int units = ((e.M + BLOCK_M * CG - 1) / (BLOCK_M * CG)) * ((e.N + BN - 1) / BN);
   const int slots = num_sms() / CG;
@@ -629,49 +815,70 @@ static int launch_tc2(const CUtensorMap &ta, const CUtensorMap &tw, const CUtens
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG > 1 ? 1 : 0;
+  int flags = epilogue_vec_ok(e) ? 1 : 0;
+#ifdef SDP_DIAG
   static const int nofeed = [] { const char *v = getenv("SDP_GEMM_NOFEED"); return (v && v[0] == '1') ? 2 : 0; }();
-  SDP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw, to, e, K, (epilogue_vec_ok(e) ? 1 : 0) | nofeed));
+  flags |= nofeed;
+#endif
+  SDP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw, to, to2, e, K, flags));
   SDP_LAUNCH_OK();
   return 0;
 }
 
-// 0 / unset: automatic (pairs whenever the staged epilogue applies and M spans a pair); 1: never; 2: always if legal
-static int cta_group_pref() {
-  static int v = -1;
-  if (v < 0) {
-    const char *s = getenv("SDP_GEMM_CTA_GROUP");
-    v = s ? atoi(s) : 0;
-  }
-  return v;
+// pairs (cta_group::2, 256 x BN tiles) whenever the staged epilogue applies and M spans enough pairs
+static bool use_pairs(const Epilogue &e) {
+#ifdef SDP_DIAG
+  static const int pref = [] { const char *s = getenv("SDP_GEMM_CTA_GROUP"); return s ? atoi(s) : 0; }();
+  if (pref == 1) return false;
+  if (pref == 2) return e.M > BLOCK_M;
+#endif
+  return e.M >= 8 * BLOCK_M;
 }
 
 template <int BN, int STAGES, int ACT, int HN = 0>
 static int launch_tc(const sdp_gemm_args &a, const CUtensorMap &ta, const Epilogue &e, cudaStream_t st) {
   CUtensorMap tw;
-  if (staged_ok(e)) {
-    CUtensorMap to;
+  const int rsm = rsm_planes(e);
+  const bool lo = e.out_lo != nullptr || e.res_lo != nullptr;
+  if (staged_ok(e) && (!lo || rsm == 2)) {
+    CUtensorMap to, to2;
     if (int rc = get_tensor_map(e.out, e.M, e.N, e.ldo, 32, &to, 32)) return rc;
+    to2 = to;
+    if (rsm == 2)
+      if (int rc = get_tensor_map(e.out_lo, e.M, e.N, e.ldo, 32, &to2, 32)) return rc;
     if constexpr (BN >= 128) {
-      const int pref = cta_group_pref();
-      if (pref != 1 && e.M > BLOCK_M && (pref == 2 || e.M >= 8 * BLOCK_M)) {
+      if (use_pairs(e)) {
         constexpr int ST2 = (STAGES * (BLOCK_M + BN)) / (BLOCK_M + BN / 2);   // same bytes, deeper ring
         if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, BN / 2, &tw)) return rc;
-        if constexpr (ACT == SDP_ACT_GELU && HN == 0 && BN == 256) {
-          // bias + GELU only (the C -> 4C GEMMs of the mixers and encoders): the lean 16-warp epilogue, one smem
-          // stage traded for 64 KB of output staging.  SDP_GEMM_WIDE_EPI=0 keeps the 8-warp kernel.
-          static const bool wide = [] { const char *v = getenv("SDP_GEMM_WIDE_EPI"); return !(v && v[0] == '0'); }();
-          if (wide && e.residual == nullptr && e.stats_out == nullptr && e.ln_stats == nullptr && e.pass_seq == 0 &&
-              e.seq_out == 0 && e.res_mod == 0 && a.N % BN == 0 && epilogue_vec_ok(e))
-            return launch_tc2<BN, ST2 - 1, ACT, HN, true, 2, EPI_WARPS_WIDE, true>(ta, tw, to, e, a.K, st);
+        if constexpr (HN == 0) {
+          if (rsm == 2) return launch_tc2<BN, stages_for(BN, 2, out_bytes_for(false, 2, 2), ST2), ACT, 0, true, 2, EPI_WARPS, 0, 2>(ta, tw, to, to2, e, a.K, st);
+          if (rsm == 1) return launch_tc2<BN, stages_for(BN, 2, out_bytes_for(false, 1, 2), ST2), ACT, 0, true, 2, EPI_WARPS, 0, 1>(ta, tw, to, to2, e, a.K, st);
         }
-        return launch_tc2<BN, ST2, ACT, HN, true, 2>(ta, tw, to, e, a.K, st);
+        if constexpr (ACT == SDP_ACT_GELU && HN == 0 && BN == 256) {
+          // bias (or folded LayerNorm) + GELU only (the C -> 4C GEMMs of the mixers and encoders): the lean 16-warp
+          // epilogue, one smem stage traded for 64 KB of output staging
+          if (e.residual == nullptr && e.stats_out == nullptr && e.pass_seq == 0 && e.seq_out == 0 && e.res_mod == 0 &&
+              a.N % BN == 0 && epilogue_vec_ok(e)) {
+            if (e.ln_stats != nullptr)
+              return launch_tc2<BN, ST2 - 1, ACT, HN, true, 2, EPI_WARPS_WIDE, 2>(ta, tw, to, to2, e, a.K, st);
+            return launch_tc2<BN, ST2 - 1, ACT, HN, true, 2, EPI_WARPS_WIDE, 1>(ta, tw, to, to2, e, a.K, st);
+          }
+        }
+        return launch_tc2<BN, ST2, ACT, HN, true, 2>(ta, tw, to, to2, e, a.K, st);
       }
     }
     if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, BN, &tw)) return rc;
-    return launch_tc2<BN, STAGES, ACT, HN, true>(ta, tw, to, e, a.K, st);
+    if constexpr (HN == 0) {
+      if (rsm == 2) return launch_tc2<BN, stages_for(BN, 1, out_bytes_for(false, 2, 1), STAGES), ACT, 0, true, 1, EPI_WARPS, 0, 2>(ta, tw, to, to2, e, a.K, st);
+      if (rsm == 1) return launch_tc2<BN, stages_for(BN, 1, out_bytes_for(false, 1, 1), STAGES), ACT, 0, true, 1, EPI_WARPS, 0, 1>(ta, tw, to, to2, e, a.K, st);
+    }
+    if (!lo) return launch_tc2<BN, STAGES, ACT, HN, true>(ta, tw, to, to2, e, a.K, st);
   }
+  // direct global stores: row remaps (patch embedding), fp32 outputs, split-stream shapes the RSM epilogue does not cover
+  SDP_CHECK(e.stats_out == nullptr, "sdp_gemm: stats_out needs an epilogue that stages its output (bf16, no row remap; with "
+                                    "a split stream: in place, N %% 32 == 0)");
   if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, BN, &tw)) return rc;
-  return launch_tc2<BN, STAGES, ACT, HN, false>(ta, tw, ta, e, a.K, st);
+  return launch_tc2<BN, STAGES, ACT, HN, false>(ta, tw, ta, ta, e, a.K, st);
 }
 
 template <int BN, int STAGES>

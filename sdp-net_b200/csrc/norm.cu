@@ -214,29 +214,34 @@ row_stats_kernel(const T *__restrict__ x, long long ldx, float *__restrict__ sta
 
 // ---------------------------------------------------------------------------------------
 template <typename T>
-__global__ void fill_registers_kernel(T *act, const float *__restrict__ table, int B, int S, int R, int C) {
+__global__ void fill_registers_kernel(T *act, T *act_lo, const float *__restrict__ table, int B, int S, int R, int C) {
   const long long n = (long long)B * R * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = i % C;
     const int r = (i / C) % R;
     const long long b = i / ((long long)C * R);
-    act[(b * S + r) * C + c] = from_f<T>(__ldg(table + r * C + c));
+    const float v = __ldg(table + r * C + c);
+    const T h = from_f<T>(v);
+    act[(b * S + r) * C + c] = h;
+    if (act_lo) act_lo[(b * S + r) * C + c] = from_f<T>(v - to_f(h));     // split stream: what the rounding dropped
   }
 }
 
 // out[b, :] = LN(mean_{rows}(act[b, row0:row0+nrows, :])); one CTA per image
 template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
-pool_ln_kernel(const T *__restrict__ act, int S, int C, int row0, int nrows, const float *__restrict__ lw,
-               const float *__restrict__ lb, float eps, TO *__restrict__ out, long long ldo) {
+pool_ln_kernel(const T *__restrict__ act, const T *__restrict__ act_lo, int S, int C, int row0, int nrows,
+               const float *__restrict__ lw, const float *__restrict__ lb, float eps, TO *__restrict__ out, long long ldo) {
   extern __shared__ float pooled[];   // [C] + 32 scratch
   float *red = pooled + C;
   const int b = blockIdx.x;
   const T *base = act + ((long long)b * S + row0) * C;
+  const T *base_lo = act_lo ? act_lo + ((long long)b * S + row0) * C : nullptr;
   float s = 0.0f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.0f;
-    for (int r = 0; r < nrows; ++r) a += to_f(base[(long long)r * C + c]);
+    for (int r = 0; r < nrows; ++r)
+      a += to_f(base[(long long)r * C + c]) + (base_lo ? to_f(base_lo[(long long)r * C + c]) : 0.0f);
     a /= (float)nrows;
     pooled[c] = a;
     s += a;
@@ -289,13 +294,15 @@ __global__ void tokens_from_nchw_kernel(const float *__restrict__ x, T *__restri
   }
 }
 template <typename T>
-__global__ void tokens_to_nchw_kernel(const T *__restrict__ act, float *__restrict__ x, int C, int T_, int R) {
+__global__ void tokens_to_nchw_kernel(const T *__restrict__ act, const T *__restrict__ act_lo, float *__restrict__ x,
+                                      int C, int T_, int R) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int t = t0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (t < T_ && c < C) ? to_f(act[((long long)b * (R + T_) + R + t) * C + c]) : 0.0f;
+    const long long at = ((long long)b * (R + T_) + R + t) * C + c;
+    tile[i][threadIdx.x] = (t < T_ && c < C) ? to_f(act[at]) + (act_lo ? to_f(act_lo[at]) : 0.0f) : 0.0f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -304,7 +311,7 @@ __global__ void tokens_to_nchw_kernel(const T *__restrict__ act, float *__restri
   }
 }
 template <typename T, bool TO_ACT>
-__global__ void registers_copy_kernel(T *act, float *reg, int B, int S, int R, int C) {
+__global__ void registers_copy_kernel(T *act, const T *act_lo, float *reg, int B, int S, int R, int C) {
   const long long n = (long long)B * R * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = i % C;
@@ -312,7 +319,7 @@ __global__ void registers_copy_kernel(T *act, float *reg, int B, int S, int R, i
     const long long b = i / ((long long)C * R);
     T *a = act + (b * S + r) * C + c;
     if (TO_ACT) *a = from_f<T>(reg[i]);
-    else reg[i] = to_f(*a);
+    else reg[i] = to_f(*a) + (act_lo ? to_f(act_lo[(b * S + r) * C + c]) : 0.0f);
   }
 }
 
@@ -458,26 +465,28 @@ extern "C" int sdp_row_stats(const void *x, int64_t ldx, float *stats, int parts
   return 0;
 }
 
-extern "C" int sdp_fill_registers(void *act, int dtype, const float *table, int B, int S, int R, int C,
+extern "C" int sdp_fill_registers(void *act, void *act_lo, int dtype, const float *table, int B, int S, int R, int C,
                                   void *stream) {
   SDP_CHECK(act && table && B > 0 && R > 0 && R <= S && C > 0, "sdp_fill_registers: bad arguments");
+  SDP_CHECK(act_lo == nullptr || dtype == SDP_BF16, "sdp_fill_registers: a lo plane needs a bf16 stream");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int g = grid_for((long long)B * R * C);
-  if (dtype == SDP_BF16) fill_registers_kernel<bf16><<<g, 256, 0, st>>>((bf16 *)act, table, B, S, R, C);
-  else fill_registers_kernel<float><<<g, 256, 0, st>>>((float *)act, table, B, S, R, C);
+  if (dtype == SDP_BF16) fill_registers_kernel<bf16><<<g, 256, 0, st>>>((bf16 *)act, (bf16 *)act_lo, table, B, S, R, C);
+  else fill_registers_kernel<float><<<g, 256, 0, st>>>((float *)act, nullptr, table, B, S, R, C);
   SDP_LAUNCH_OK();
   return 0;
 }
 
-extern "C" int sdp_pool_ln(const void *act, int dtype, int B, int S, int C, int row0, int nrows,
+extern "C" int sdp_pool_ln(const void *act, const void *act_lo, int dtype, int B, int S, int C, int row0, int nrows,
                            const float *ln_w, const float *ln_b, float eps, void *out, int out_dtype,
                            int64_t ldo, void *stream) {
   SDP_CHECK(act && out && B > 0 && nrows > 0 && row0 >= 0 && row0 + nrows <= S, "sdp_pool_ln: bad arguments");
+  SDP_CHECK(act_lo == nullptr || dtype == SDP_BF16, "sdp_pool_ln: a lo plane needs a bf16 stream");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t sm = (C + 32) * sizeof(float);
   SDP_CHECK(sm <= 48 * 1024, "sdp_pool_ln: C=%d too large", C);
 #define POOL(TI, TO) \
-  pool_ln_kernel<TI, TO><<<B, 256, sm, st>>>((const TI *)act, S, C, row0, nrows, ln_w, ln_b, eps, (TO *)out, ldo)
+  pool_ln_kernel<TI, TO><<<B, 256, sm, st>>>((const TI *)act, (const TI *)act_lo, S, C, row0, nrows, ln_w, ln_b, eps, (TO *)out, ldo)
   if (dtype == SDP_BF16 && out_dtype == SDP_BF16) POOL(bf16, bf16);
   else if (dtype == SDP_BF16) POOL(bf16, float);
   else if (out_dtype == SDP_BF16) POOL(float, bf16);
@@ -499,31 +508,32 @@ extern "C" int sdp_tokens_from_nchw(const float *x, const float *reg, void *act,
   if (R > 0 && reg) {
     const int g = grid_for((long long)B * R * C);
     if (dtype == SDP_BF16)
-      registers_copy_kernel<bf16, true><<<g, 256, 0, st>>>((bf16 *)act, const_cast<float *>(reg), B, R + T, R, C);
+      registers_copy_kernel<bf16, true><<<g, 256, 0, st>>>((bf16 *)act, nullptr, const_cast<float *>(reg), B, R + T, R, C);
     else
-      registers_copy_kernel<float, true><<<g, 256, 0, st>>>((float *)act, const_cast<float *>(reg), B, R + T, R, C);
+      registers_copy_kernel<float, true><<<g, 256, 0, st>>>((float *)act, nullptr, const_cast<float *>(reg), B, R + T, R, C);
     SDP_LAUNCH_OK();
   }
   return 0;
 }
 
-extern "C" int sdp_tokens_to_nchw(const void *act, int dtype, float *x, float *reg, int B, int C, int T, int R,
-                                  void *stream) {
+extern "C" int sdp_tokens_to_nchw(const void *act, const void *act_lo, int dtype, float *x, float *reg, int B, int C,
+                                  int T, int R, void *stream) {
   SDP_CHECK(act && B > 0 && C > 0 && T > 0 && R >= 0, "sdp_tokens_to_nchw: bad arguments");
+  SDP_CHECK(act_lo == nullptr || dtype == SDP_BF16, "sdp_tokens_to_nchw: a lo plane needs a bf16 stream");
   SDP_CHECK(B <= 65535, "sdp_tokens_to_nchw: B too large");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (x) {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    if (dtype == SDP_BF16) tokens_to_nchw_kernel<bf16><<<grid, block, 0, st>>>((const bf16 *)act, x, C, T, R);
-    else tokens_to_nchw_kernel<float><<<grid, block, 0, st>>>((const float *)act, x, C, T, R);
+    if (dtype == SDP_BF16) tokens_to_nchw_kernel<bf16><<<grid, block, 0, st>>>((const bf16 *)act, (const bf16 *)act_lo, x, C, T, R);
+    else tokens_to_nchw_kernel<float><<<grid, block, 0, st>>>((const float *)act, nullptr, x, C, T, R);
     SDP_LAUNCH_OK();
   }
   if (R > 0 && reg) {
     const int g = grid_for((long long)B * R * C);
     if (dtype == SDP_BF16)
-      registers_copy_kernel<bf16, false><<<g, 256, 0, st>>>((bf16 *)const_cast<void *>(act), reg, B, R + T, R, C);
+      registers_copy_kernel<bf16, false><<<g, 256, 0, st>>>((bf16 *)const_cast<void *>(act), (const bf16 *)act_lo, reg, B, R + T, R, C);
     else
-      registers_copy_kernel<float, false><<<g, 256, 0, st>>>((float *)const_cast<void *>(act), reg, B, R + T, R, C);
+      registers_copy_kernel<float, false><<<g, 256, 0, st>>>((float *)const_cast<void *>(act), nullptr, reg, B, R + T, R, C);
     SDP_LAUNCH_OK();
   }
   return 0;

@@ -15,7 +15,6 @@ Activation layout everywhere: token-major `[B, S = R + T, C]`, registers first
 """
 from __future__ import annotations
 
-import os
 import ctypes as C
 from typing import Dict, Optional
 
@@ -246,13 +245,15 @@ class Buffers:
     """Workspaces for one (B, S) shape; allocated through torch, owned by the caller."""
 
     def __init__(self, pw: Packer, B: int, T: int, R: int, hid_mult: int = 4, Kp: int = 8, Kc: int = 8,
-                 classes: int = 1):
+                 classes: int = 1, split: bool = False):
         C_, dt, dev = pw.C, pw.dtype, pw.device
         S = T + R
         hid = max(int(hid_mult), 4) * C_
         e = lambda *shape: torch.empty(*shape, dtype=dt, device=dev)
         self.B, self.T, self.R, self.S = B, T, R, S
         self.act, self.norm, self.attn = e(B, S, C_), e(B, S, C_), e(B, S, C_)
+        # split residual stream (bf16): act = hi plane, act_lo = bf16(value - hi); see sdp_gemm in the header
+        self.act_lo = e(B, S, C_) if (split and dt == torch.bfloat16) else None
         self.qkv = e(B, S, 3 * C_)
         self.hidden = e(B, S, hid)
         self.im2col = e(B * T, Kp)
@@ -297,12 +298,14 @@ def run_encoder(pw: Packer, w: dict, bufs: Buffers, act_name: Optional[str] = No
         ops.attention(bufs.qkv, bufs.attn, pw.n_head, None, None, None, None, 1e-5)
     else:
         ops.attention(bufs.qkv, bufs.attn, pw.n_head, w["qn_w"], w["qn_b"], w["kn_w"], w["kn_b"], 1e-5)
-    ops.gemm(bufs.attn.view(M, C_), w["w_o"], a2, residual=a2, stats_out=st)
+    lo = None if bufs.act_lo is None else bufs.act_lo.view(M, C_)       # split residual stream: both planes in place
+    ops.gemm(bufs.attn.view(M, C_), w["w_o"], a2, residual=a2, stats_out=st, residual_lo=lo, out_lo=lo)
     if not fold:
         ops.layernorm_rows(a2, w["norm2_w"], w["norm2_b"], n2, 1e-5)
     ops.gemm(xin, w["w_ff1"], hid, bias=None if fold else w["b_ff1"], act=act_name or pw.act,
              ln_fold=(st, 1e-5, w["s_ff1"], w["t_ff1"]) if fold else None)
-    ops.gemm(hid, w["w_ff2"], a2, bias=w["b_ff2"], residual=a2, stats_out=bufs.stats if (fold or bufs.emit) else None)
+    ops.gemm(hid, w["w_ff2"], a2, bias=w["b_ff2"], residual=a2, stats_out=bufs.stats if (fold or bufs.emit) else None,
+             residual_lo=lo, out_lo=lo)
     bufs.stats_fresh = bool(fold or bufs.emit)
 
 
@@ -316,21 +319,23 @@ def run_mixer(pw: Packer, w: dict, bufs: Buffers, Gh: int, Gw: int, act_name: Op
     pr = (S, R) if R > 0 else (0, 0)
     fold = w["s_mlp1"] is not None and bufs.fold
     st = bufs.stats if fold else None
-    dw_stats = st
-    if not fold and bufs.stats is not None and ops.ln_dwconv_wants_stats(Gh, Gw, C_, w["conv_k"], R, pw.dtype):
-        ops.row_stats(a2, bufs.stats)        # token (sum, sumsq) for the tensor-core depthwise kernel
-        dw_stats = bufs.stats
     k_dw = int(round(w["w_dw"].shape[0] ** 0.5))
-    if (not fold and bufs.stats is not None and os.environ.get("SDP_DWCONV_SLAB", "1") != "0"
-            and ops.ln_dwconv_slab_ok(Gh, Gw, C_, k_dw, pw.dtype)):
-        # channel-stationary tensor-core kernel (same choice as sdp_forward); the statistics buffer is its scratch
-        have = bufs.emit and bufs.stats_fresh
-        scratch = bufs.qkv.view(-1).view(torch.float32) if have else bufs.stats.view(-1)   # qkv is dead between encoders
+    have = bool((fold or bufs.emit) and bufs.stats_fresh)     # bufs.stats holds the producer GEMM's parts of act
+    if bufs.stats is not None and ops.ln_dwconv_slab_ok(Gh, Gw, C_, k_dw, pw.dtype):
+        # channel-stationary tensor-core kernel (same choice as sdp_forward); (mean, rstd) scratch: the head of the
+        # qkv buffer (dead between two encoders) when the statistics workspace is in use, else that workspace
+        scratch = bufs.qkv.view(-1).view(torch.float32) if have else bufs.stats.view(-1)
         ops.ln_dwconv_slab(bufs.act, scratch, w["ln1_g"], w["ln1_b"], w["w_dw"], w["b_dw"], bufs.norm, Gh, Gw, R, 1e-6,
                            producer_stats=bufs.stats if have else None)
     else:
+        dw_stats = bufs.stats if have else None
+        if not have and bufs.stats is not None and ops.ln_dwconv_wants_stats(Gh, Gw, C_, w["conv_k"], R, pw.dtype):
+            ops.row_stats(a2, bufs.stats)        # token (sum, sumsq) in part 0
+            dw_stats = bufs.stats
         ops.ln_dwconv(bufs.act, w["ln1_g"], w["ln1_b"], w["w_dw"], w["b_dw"], bufs.norm, Gh, Gw, R, 1e-6, stats=dw_stats)
-    ops.gemm(n2, w["w_pw"], a2, bias=w["b_pw"], act=act_name, residual=a2, pass_rows=pr, stats_out=st)
+    lo = None if bufs.act_lo is None else bufs.act_lo.view(M, C_)
+    ops.gemm(n2, w["w_pw"], a2, bias=w["b_pw"], act=act_name, residual=a2, pass_rows=pr, stats_out=st,
+             residual_lo=lo, out_lo=lo)
     bufs.stats_fresh = bool(fold)
     xin = a2
     if not fold:
@@ -339,28 +344,35 @@ def run_mixer(pw: Packer, w: dict, bufs: Buffers, Gh: int, Gw: int, act_name: Op
     ops.gemm(xin, w["w_mlp1"], hid, bias=None if fold else w["b_mlp1"], act=act_name,
              ln_fold=(st, 1e-6, w["s_mlp1"], w["t_mlp1"]) if fold else None)
     ops.gemm(hid, w["w_mlp2"], a2, bias=w["b_mlp2"], residual=a2, pass_rows=pr,
-             stats_out=bufs.stats if (fold or bufs.emit) else None)
+             stats_out=bufs.stats if (fold or bufs.emit) else None, residual_lo=lo, out_lo=lo)
     bufs.stats_fresh = bool(fold or bufs.emit)
 
 
 class Engine:
     def __init__(self, cfg: dict, state_dict: Dict[str, torch.Tensor], device="cuda", precision: str = "bf16",
-                 ln_fold: bool = False):
-        # ln_fold: fold the token LayerNorms into their consumer GEMMs (producer GEMMs emit row statistics).
-        # Measured on B200 (XL, batch 1024): removes 13.3 ms of LayerNorm kernels and 9 ms of depthwise-conv
-        # statistics per step but makes the GELU / head-norm GEMM epilogues ~19 ms slower -- a wash (4511 vs
-        # 4488 img/s), so it is opt-in until the GEMM epilogue has more headroom.
+                 ln_fold: Optional[bool] = None, split_stream: bool = True):
+        # ln_fold (bf16; default on wherever the shapes allow): the token LayerNorms in front of the QKV / FFN / mixer
+        #   MLP GEMMs (layers.py:280,307 and :103) are folded into those GEMMs' epilogues; the GEMMs that write the
+        #   residual stream emit the row statistics.  No stand-alone LayerNorm kernel runs.
+        # split_stream (bf16; default on): the residual stream is kept as two bf16 planes hi + lo (~16 mantissa bits,
+        #   the reference's autocast keeps it in fp32); False = one bf16 plane, rounded at every residual add.
         if precision not in _TORCH_DT:
             raise ValueError("precision must be 'bf16' or 'fp32'")
         L.lib()   # fail loudly before anything else if the CUDA library is missing
-        self.pw = PackedWeights(cfg, state_dict, device, precision, ln_fold)
+        self.pw = PackedWeights(cfg, state_dict, device, precision, True if ln_fold is None else ln_fold)
         self.cfg = self.pw.cfg
+        self.split_stream = bool(split_stream) and precision == "bf16"
         self._bufs: Dict[tuple, Buffers] = {}
         self._graphs: Dict[tuple, tuple] = {}          # forward_graph: (shape, dtype, registers) -> captured replay
-        self._desc_keep = None
+        self._descs: Dict[tuple, tuple] = {}           # (Gh, Gw, R) -> (ModelDesc, the ctypes arrays it points into)
 
     # -- C-ABI model description -------------------------------------------------------------
     def _desc(self, Gh: int, Gw: int, R: int) -> L.ModelDesc:
+        """The C-ABI model description for one grid / register count, built once and cached (the packed tensors it
+        points into are owned by `self.pw` and never move)."""
+        ent = self._descs.get((Gh, Gw, R))
+        if ent is not None:
+            return ent[0]
         pw, cfg = self.pw, self.cfg
         p = lambda t: None if t is None else t.data_ptr()
         enc = (L.EncoderWeights * len(pw.enc))()
@@ -387,7 +399,9 @@ class Engine:
         d.head_ln_w, d.head_ln_b = p(pw.head_ln_w), p(pw.head_ln_b)
         d.w_head1, d.b_head1 = p(pw.w_head1), p(pw.b_head1)
         d.w_head2, d.b_head2 = p(pw.w_head2), p(pw.b_head2)
-        self._desc_keep = (enc, mix)
+        if len(self._descs) >= 8:
+            self._descs.clear()
+        self._descs[(Gh, Gw, R)] = (d, enc, mix)
         return d
 
     def buffers(self, B: int, Gh: int, Gw: int, R: int) -> Buffers:
@@ -396,7 +410,7 @@ class Engine:
             if len(self._bufs) >= 4:
                 self._bufs.clear()
             self._bufs[key] = Buffers(self.pw, B, Gh * Gw, R, int(self.cfg["ff_multiplication_factor"]),
-                                      self.pw.Kp, self.pw.Kc, int(self.cfg["output_classes"]))
+                                      self.pw.Kp, self.pw.Kc, int(self.cfg["output_classes"]), split=self.split_stream)
         return self._bufs[key]
 
     def _check_input(self, x: torch.Tensor, num_registers: int):
@@ -431,15 +445,14 @@ class Engine:
             for name, _ in L.Workspace._fields_:
                 t = getattr(bufs, name)
                 setattr(ws, name, None if t is None else t.data_ptr())
-            rc = L.lib().sdp_forward(C.byref(d), C.byref(ws), x.data_ptr(), ops._dt(x), B, x.shape[2], x.shape[3], R,
-                                     bufs.logits.data_ptr(), torch.cuda.current_stream().cuda_stream)
-            L.check(rc, "sdp_forward")
+            ops._call("sdp_forward", x, C.byref(d), C.byref(ws), x.data_ptr(), ops._dt(x), B, x.shape[2], x.shape[3], R,
+                      bufs.logits.data_ptr())
         logits = bufs.logits.clone()
         if not return_raw_outputs:
             return logits
         x_raw = torch.empty(B, pw.C, Gh, Gw, dtype=torch.float32, device=x.device)
         reg = torch.empty(B, R, pw.C, dtype=torch.float32, device=x.device)
-        ops.tokens_to_nchw(bufs.act, x_raw, reg, Gh * Gw, R)
+        ops.tokens_to_nchw(bufs.act, x_raw, reg, Gh * Gw, R, act_lo=bufs.act_lo)
         return logits, x_raw, reg
 
     def forward_graph(self, x: torch.Tensor, num_registers: int = 3) -> torch.Tensor:
@@ -478,20 +491,22 @@ class Engine:
 
         def note(name):
             if stages is not None:
-                stages[name] = bufs.act.float().clone()
+                stages[name] = bufs.act.float().clone() if bufs.act_lo is None else bufs.act.float() + bufs.act_lo.float()
 
         ops.im2col_patches(x, bufs.im2col, p)
         ops.gemm(bufs.im2col, pw.w_patch, bufs.act.view(B * S, C_), residual=pw.pos_table(Gh, Gw), res_first=True,
-                 res_mod=T, act=pw.embed_act, seq_remap=(T, S, R), K=3 * p * p)
-        ops.fill_registers(bufs.act, pw.reg_table(R))
+                 res_mod=T, act=pw.embed_act, seq_remap=(T, S, R), K=3 * p * p,
+                 out_lo=None if bufs.act_lo is None else bufs.act_lo.view(B * S, C_))
+        ops.fill_registers(bufs.act, pw.reg_table(R), act_lo=bufs.act_lo)
         k_dw = int(cfg["conv_kernel_size"]) if "conv_kernel_size" in cfg else 0
         sparts = bufs.stats.shape[1] if bufs.stats is not None else 0
-        bufs.emit = bool(not bufs.fold and bufs.stats is not None and os.environ.get("SDP_DWCONV_SLAB", "1") != "0"
+        bufs.emit = bool(not bufs.fold and bufs.stats is not None
                          and sparts > 1 and sparts % 2 == 0 and sparts <= 16 and int(cfg["conv_block_num"]) > 0
                          and k_dw > 0 and ops.ln_dwconv_slab_ok(Gh, Gw, C_, k_dw, torch.bfloat16))
         bufs.stats_fresh = False
         if bufs.fold:
             ops.row_stats(bufs.act, bufs.stats)
+            bufs.stats_fresh = True
         note("embed")
         cbn = int(cfg["conv_block_num"])
         for i in range(int(cfg["num_blocks"])):
@@ -509,9 +524,9 @@ class Engine:
         note("final")
         K = int(cfg["output_classes"])
         if pw.head_from_register:
-            ops.pool_ln(bufs.act, 0, R, pw.head_ln_w, pw.head_ln_b, bufs.pooled, 1e-5)
+            ops.pool_ln(bufs.act, 0, R, pw.head_ln_w, pw.head_ln_b, bufs.pooled, 1e-5, act_lo=bufs.act_lo)
         else:
-            ops.pool_ln(bufs.act, R, T, None, None, bufs.pooled, 0.0)
+            ops.pool_ln(bufs.act, R, T, None, None, bufs.pooled, 0.0, act_lo=bufs.act_lo)
         if pw.head_from_register and not pw.head_simple:
             ops.gemm(bufs.pooled, pw.w_head1, bufs.head_h, bias=pw.b_head1, act="tanh", N=K)
             ops.gemm(bufs.head_h, pw.w_head2, bufs.logits, bias=pw.b_head2, K=K)

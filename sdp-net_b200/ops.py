@@ -39,8 +39,25 @@ def _f32(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
     return t
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _call(name: str, ref: torch.Tensor, *args) -> None:
+    """Run the C-ABI entry `name(*args, stream)` on `ref`'s device and on that device's current stream.  The library
+    launches on the CUDA *current* device, so the call is made with `ref.device` current: a model on cuda:1 works
+    while cuda:0 is the process default."""
+    dev = ref.device
+    if dev.type != "cuda":
+        raise RuntimeError("sdpnet_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    fn = getattr(L.lib(), name)
+    if torch.cuda.current_device() == dev.index:
+        L.check(fn(*args, torch.cuda.current_stream(dev).cuda_stream), name)
+    else:
+        with torch.cuda.device(dev):
+            L.check(fn(*args, torch.cuda.current_stream(dev).cuda_stream), name)
+
+
+def _same_device(*tensors) -> None:
+    devs = {t.device for t in tensors if t is not None}
+    if len(devs) > 1:
+        raise RuntimeError(f"sdpnet_b200: tensors live on different devices: {sorted(str(d) for d in devs)}")
 
 
 def act_id(name) -> int:
@@ -55,8 +72,11 @@ def act_id(name) -> int:
 def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, act="none", res_first: bool = False, res_mod: int = 0,
          seq_remap=(0, 0, 0), pass_rows=(0, 0), M: Optional[int] = None, N: Optional[int] = None,
-         K: Optional[int] = None, headnorm=None, ln_fold=None, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = epi(A[M,K] @ W[N,K]^T); see sdp_gemm in the header for the epilogue definition."""
+         K: Optional[int] = None, headnorm=None, ln_fold=None, stats_out: Optional[torch.Tensor] = None,
+         residual_lo: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = epi(A[M,K] @ W[N,K]^T); see sdp_gemm in the header for the epilogue definition.  `residual_lo` / `out_lo`:
+    the lo planes of a split (hi + lo) bf16 stream, same shape and pitch as `residual` / `out`."""
+    _same_device(A, W, out, bias, residual, stats_out, residual_lo, out_lo)
     if A.dim() != 2 or W.dim() != 2 or out.dim() != 2:
         raise ValueError("gemm operands must be 2-D (views with a row pitch are fine)")
     if A.stride(1) != 1 or W.stride(1) != 1 or out.stride(1) != 1:
@@ -88,9 +108,14 @@ def gemm(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, bias: Optional[
         st, eps, ls, lt = ln_fold
         a.ln_stats, a.ln_parts, a.ln_eps = _p(_f32(st, "ln stats")), int(st.shape[-2]), float(eps)
         a.ln_s, a.ln_t = _p(_f32(ls, "ln_s")), _p(_f32(lt, "ln_t"))
+    for lo, hi, nm in ((residual_lo, residual, "residual_lo"), (out_lo, out, "out_lo")):
+        if lo is not None and (hi is None or lo.dtype != torch.bfloat16 or hi.dtype != torch.bfloat16 or lo.shape != hi.shape
+                               or lo.stride() != hi.stride()):
+            raise ValueError(f"{nm} must be a bfloat16 plane with the shape and strides of its hi plane")
+    a.residual_lo, a.out_lo = _p(residual_lo), _p(out_lo)
     if stats_out is not None:     # [M_out, parts, 2]: the producer emits row statistics of what it stores
         a.stats_out, a.stats_parts = _p(_f32(stats_out, "stats_out")), int(stats_out.shape[-2])
-    L.check(L.lib().sdp_gemm(C.byref(a), _stream()), "sdp_gemm")
+    _call("sdp_gemm", A, C.byref(a))
     return out
 
 
@@ -105,8 +130,8 @@ def gemm_stats_parts(N: int, dtype: torch.dtype) -> int:
 def row_stats(x: torch.Tensor, stats: torch.Tensor) -> torch.Tensor:
     """stats [M, parts, 2] fp32 <- per-row (sum, sum of squares) of x [M, C] in the producer-GEMM layout."""
     x2 = x.reshape(-1, x.shape[-1])
-    L.check(L.lib().sdp_row_stats(_p(x2), x2.stride(0), _p(_f32(stats, "stats")), int(stats.shape[-2]), x2.shape[0],
-                                  x2.shape[1], _dt(x2), _stream()), "sdp_row_stats")
+    _call("sdp_row_stats", x2, _p(x2), x2.stride(0), _p(_f32(stats, "stats")), int(stats.shape[-2]), x2.shape[0],
+                                  x2.shape[1], _dt(x2))
     return stats
 
 
@@ -114,16 +139,14 @@ def im2col_patches(x: torch.Tensor, A: torch.Tensor, patch: int) -> torch.Tensor
     if x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
         raise ValueError("x must be a contiguous NCHW tensor with 3 channels")
     B, _, H, W = x.shape
-    L.check(L.lib().sdp_im2col_patches(_p(x), _dt(x), _p(A), _dt(A), A.stride(0), B, H, W, patch, _stream()),
-            "sdp_im2col_patches")
+    _call("sdp_im2col_patches", x, _p(x), _dt(x), _p(A), _dt(A), A.stride(0), B, H, W, patch)
     return A
 
 
-def fill_registers(act: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+def fill_registers(act: torch.Tensor, table: torch.Tensor, act_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
     B, S, Cc = act.shape
     R = table.shape[0]
-    L.check(L.lib().sdp_fill_registers(_p(act), _dt(act), _p(_f32(table, "table")), B, S, R, Cc, _stream()),
-            "sdp_fill_registers")
+    _call("sdp_fill_registers", act, _p(act), _p(act_lo), _dt(act), _p(_f32(table, "table")), B, S, R, Cc)
     return act
 
 
@@ -132,9 +155,8 @@ def layernorm_rows(x: torch.Tensor, w: Optional[torch.Tensor], b: Optional[torch
     x2, o2 = x.reshape(-1, x.shape[-1]), out.reshape(-1, out.shape[-1])
     if x2.dtype != o2.dtype:
         raise TypeError("layernorm_rows: in/out dtype mismatch")
-    L.check(L.lib().sdp_layernorm_rows(_p(x2), x2.stride(0), _p(_f32(w, "w")), _p(_f32(b, "b")), _p(o2),
-                                       o2.stride(0), x2.shape[0], x2.shape[1], float(eps), _dt(x2), _stream()),
-            "sdp_layernorm_rows")
+    _call("sdp_layernorm_rows", x2, _p(x2), x2.stride(0), _p(_f32(w, "w")), _p(_f32(b, "b")), _p(o2),
+                                       o2.stride(0), x2.shape[0], x2.shape[1], float(eps), _dt(x2))
     return out
 
 
@@ -147,10 +169,9 @@ def ln_dwconv(act: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, wdw: t
     k = int(round(wdw.shape[0] ** 0.5))      # wdw is tap-major [k*k, C]
     if wdw.dim() != 2 or k * k != wdw.shape[0] or wdw.shape[1] != Cc:
         raise ValueError("ln_dwconv: wdw must be tap-major [k*k, C]")
-    L.check(L.lib().sdp_ln_dwconv_stats(_p(act), _p(_f32(stats, "stats")), 0 if stats is None else int(stats.shape[-2]),
+    _call("sdp_ln_dwconv_stats", act, _p(act), _p(_f32(stats, "stats")), 0 if stats is None else int(stats.shape[-2]),
                                         _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")), _p(_f32(wdw, "wdw")),
-                                        _p(_f32(bdw, "bdw")), _p(out), B, Gh, Gw, Cc, k, R, float(eps), _dt(act),
-                                        _stream()), "sdp_ln_dwconv")
+                                        _p(_f32(bdw, "bdw")), _p(out), B, Gh, Gw, Cc, k, R, float(eps), _dt(act))
     return out
 
 
@@ -178,9 +199,9 @@ def ln_dwconv_slab(act: torch.Tensor, token_stats: torch.Tensor, gamma: torch.Te
                 or producer_stats.shape[2] != 2 or not producer_stats.is_contiguous()):
             raise ValueError("ln_dwconv_slab: producer_stats must be contiguous fp32 [B*S, parts, 2]")
         parts = int(producer_stats.shape[1])
-    L.check(L.lib().sdp_ln_dwconv_slab_stats(_p(act), _p(producer_stats), parts, _p(token_stats), _p(_f32(gamma, "gamma")),
+    _call("sdp_ln_dwconv_slab_stats", act, _p(act), _p(producer_stats), parts, _p(token_stats), _p(_f32(gamma, "gamma")),
                                              _p(_f32(beta, "beta")), _p(_f32(wdw, "wdw")), _p(_f32(bdw, "bdw")), _p(out),
-                                             B, Gh, Gw, Cc, k, R, float(eps), _stream()), "sdp_ln_dwconv_slab")
+                                             B, Gh, Gw, Cc, k, R, float(eps))
     return out
 
 
@@ -194,17 +215,17 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, n_head: int, qn_w=None, qn_b
     Cc = C3 // 3
     if not qkv.is_contiguous() or not out.is_contiguous() or out.shape != (B, S, Cc):
         raise ValueError("attention: qkv [B,S,3C] and out [B,S,C] must be contiguous")
-    L.check(L.lib().sdp_attention(_p(qkv), _p(_f32(qn_w, "qn_w")), _p(_f32(qn_b, "qn_b")), _p(_f32(kn_w, "kn_w")),
+    _call("sdp_attention", qkv, _p(qkv), _p(_f32(qn_w, "qn_w")), _p(_f32(qn_b, "qn_b")), _p(_f32(kn_w, "kn_w")),
                                   _p(_f32(kn_b, "kn_b")), _p(out), B, S, n_head, Cc // n_head, float(eps),
-                                  _dt(qkv), _stream()), "sdp_attention")
+                                  _dt(qkv))
     return out
 
 
-def pool_ln(act: torch.Tensor, row0: int, nrows: int, ln_w, ln_b, out: torch.Tensor, eps: float = 1e-5):
+def pool_ln(act: torch.Tensor, row0: int, nrows: int, ln_w, ln_b, out: torch.Tensor, eps: float = 1e-5,
+            act_lo: Optional[torch.Tensor] = None):
     B, S, Cc = act.shape
-    L.check(L.lib().sdp_pool_ln(_p(act), _dt(act), B, S, Cc, row0, nrows, _p(_f32(ln_w, "ln_w")),
-                                _p(_f32(ln_b, "ln_b")), float(eps), _p(out), _dt(out), out.stride(0), _stream()),
-            "sdp_pool_ln")
+    _call("sdp_pool_ln", act, _p(act), _p(act_lo), _dt(act), B, S, Cc, row0, nrows, _p(_f32(ln_w, "ln_w")),
+                                _p(_f32(ln_b, "ln_b")), float(eps), _p(out), _dt(out), out.stride(0))
     return out
 
 
@@ -213,22 +234,20 @@ def tokens_from_nchw(x: torch.Tensor, reg: Optional[torch.Tensor], act: torch.Te
     R = 0 if reg is None else reg.shape[1]
     x = _f32(x.contiguous(), "x")
     reg = None if reg is None else _f32(reg.contiguous(), "reg")
-    L.check(L.lib().sdp_tokens_from_nchw(_p(x), _p(reg), _p(act), _dt(act), B, Cc, Gh * Gw, R, _stream()),
-            "sdp_tokens_from_nchw")
+    _call("sdp_tokens_from_nchw", x, _p(x), _p(reg), _p(act), _dt(act), B, Cc, Gh * Gw, R)
     return act
 
 
-def tokens_to_nchw(act: torch.Tensor, x: Optional[torch.Tensor], reg: Optional[torch.Tensor], T: int, R: int):
+def tokens_to_nchw(act: torch.Tensor, x: Optional[torch.Tensor], reg: Optional[torch.Tensor], T: int, R: int,
+                   act_lo: Optional[torch.Tensor] = None):
     B, S, Cc = act.shape
-    L.check(L.lib().sdp_tokens_to_nchw(_p(act), _dt(act), _p(_f32(x, "x")), _p(_f32(reg, "reg")), B, Cc, T, R,
-                                       _stream()), "sdp_tokens_to_nchw")
+    _call("sdp_tokens_to_nchw", act, _p(act), _p(act_lo), _dt(act), _p(_f32(x, "x")), _p(_f32(reg, "reg")), B, Cc, T, R)
     return x, reg
 
 
 def embed_tokens(act: torch.Tensor, pos: torch.Tensor, R: int, act_name="none") -> torch.Tensor:
     B, S, Cc = act.shape
-    L.check(L.lib().sdp_embed_tokens(_p(act), _dt(act), _p(_f32(pos, "pos")), B, S - R, R, Cc, act_id(act_name),
-                                     _stream()), "sdp_embed_tokens")
+    _call("sdp_embed_tokens", act, _p(act), _dt(act), _p(_f32(pos, "pos")), B, S - R, R, Cc, act_id(act_name))
     return act
 
 
@@ -240,8 +259,8 @@ def eval_metrics(logits: torch.Tensor, labels: torch.Tensor, acc: torch.Tensor, 
         raise TypeError("eval_metrics: labels must be contiguous int64 [B]")
     if acc.dtype != torch.float64 or acc.numel() != 4 or not acc.is_contiguous():
         raise TypeError("eval_metrics: acc must be 4 contiguous float64 values")
-    L.check(L.lib().sdp_eval_metrics(_p(logits), logits.stride(0), _p(labels), logits.shape[0], logits.shape[1],
-                                     float(label_smoothing), _p(acc), _stream()), "sdp_eval_metrics")
+    _call("sdp_eval_metrics", logits, _p(logits), logits.stride(0), _p(labels), logits.shape[0], logits.shape[1],
+                                     float(label_smoothing), _p(acc))
     return acc
 
 
@@ -265,16 +284,15 @@ def val_preprocess(pixels: torch.Tensor, desc, B: int, resize, crop, mean, std, 
         raise TypeError(f"val_preprocess: out must be contiguous [B, 3, {crop[0]}, {crop[1]}]")
     m = (C.c_float * 3)(*mean)
     s = (C.c_float * 3)(*std)
-    L.check(L.lib().sdp_val_preprocess(_p(pixels), pixels.numel(), desc, B, resize[0], resize[1], crop[0], crop[1], m, s, _p(workspace),
-                                       workspace.numel(), _p(out), _dt(out), _stream()), "sdp_val_preprocess")
+    _call("sdp_val_preprocess", pixels, _p(pixels), pixels.numel(), desc, B, resize[0], resize[1], crop[0], crop[1], m, s, _p(workspace),
+                                       workspace.numel(), _p(out), _dt(out))
     return out
 
 
 def activation(x: torch.Tensor, act, force_fast: bool = False) -> torch.Tensor:
     x = x.contiguous()
     y = torch.empty_like(x)
-    L.check(L.lib().sdp_activation(_p(x), _p(y), x.numel(), act_id(act) | (0x100 if force_fast else 0), _dt(x),
-                                   _stream()), "sdp_activation")
+    _call("sdp_activation", x, _p(x), _p(y), x.numel(), act_id(act) | (0x100 if force_fast else 0), _dt(x))
     return y
 
 

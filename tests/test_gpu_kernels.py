@@ -191,11 +191,12 @@ def test_gemm_bf16_emits_row_statistics(sdp, M, C, K, R):
     assert (st2[:, 1:] == 0).all()
 
 
+@pytest.mark.parametrize("M", [777, 2610])          # below / above the CTA-pair threshold (the lean GELU epilogue needs pairs)
 @pytest.mark.parametrize("C,N,act,hn", [(768, 3072, "gelu", False), (768, 2304, "none", True), (512, 1536, "none", True),
-                                        (128, 512, "relu", False), (32, 96, "none", False)])
-def test_gemm_bf16_layernorm_fold(sdp, C, N, act, hn):
+                                        (128, 512, "relu", False), (32, 96, "none", False), (512, 2048, "gelu", False)])
+def test_gemm_bf16_layernorm_fold(sdp, C, N, act, hn, M):
     """Consumer side: LN(x) @ W^T + b computed as rstd * (x @ W'^T - mean * s) + t from the row statistics."""
-    M, eps = 777, 1e-5
+    eps = 1e-5
     x = (rnd(M, C, seed=73) * 1.7 + 0.9).to(torch.bfloat16)
     W = rnd(N, C, seed=74, scale=1 / math.sqrt(C))
     gamma, beta, bias = rnd(C, seed=75) * 0.3 + 1, rnd(C, seed=76) * 0.3, rnd(N, seed=77) * 0.2
@@ -223,6 +224,129 @@ def test_gemm_bf16_layernorm_fold(sdp, C, N, act, hn):
     ref = O.ACTIVATIONS[act](ref)
     assert relerr(out, ref) < 1.5e-2
 
+
+
+def _split(x):
+    """fp32 -> (hi, lo) bf16 planes of the split residual stream."""
+    hi = x.to(torch.bfloat16)
+    return hi, (x - hi.float()).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,S,R,C,K,act,bias", [
+    (7, 41, 5, 256, 128, "gelu", False),      # one CTA, 2-slot ring
+    (40, 41, 5, 256, 128, "gelu", True),      # CTA pairs, 3-slot ring
+    (33, 261, 5, 768, 768, "gelu", False),    # mixer 1x1 conv at XL width
+    (9, 201, 5, 768, 3072, "none", True),     # ff2 / mlp2
+    (300, 261, 5, 768, 768, "none", False),   # many tiles per CTA: the prefetch cursor crosses tile boundaries
+    (40, 41, 0, 512, 64, "none", False),      # S-size width, no pass-through rows
+    (25, 50, 3, 128, 256, "relu", False),     # BN = 128
+    (25, 50, 3, 96, 64, "none", False),       # N not a multiple of the column half: ragged last chunk range
+    (9, 21, 2, 40, 64, "tanh", True),         # N % 32 != 0: direct-store fallback, same contract
+])
+def test_gemm_bf16_split_stream_inplace(sdp, B, S, R, C, K, act, bias):
+    """The split (hi + lo) residual stream through the in-place residual epilogue: out_hi + out_lo carries the fp32
+    sum to ~16 bits, pass-through rows keep both planes bit for bit, statistics describe the hi plane."""
+    M = B * S
+    A = rnd(M, K, seed=7, dtype=torch.bfloat16)
+    W = rnd(C, K, seed=8, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    bvec = rnd(C, seed=10) * 0.3 if bias else None
+    x = rnd(M, C, seed=9) * 1.5 + 0.3
+    hi, lo = _split(x)
+    x16 = hi.float() + lo.float()
+    ref = gemm_ref(A, W, bvec, act, x16)
+    rows = torch.arange(M, device="cuda") % S < R if R else torch.zeros(M, dtype=torch.bool, device="cuda")
+    oh = torch.full((M + 3, C), 3.0, device="cuda", dtype=torch.bfloat16)
+    ol = torch.full((M + 3, C), 5.0, device="cuda", dtype=torch.bfloat16)
+    oh[:M], ol[:M] = hi, lo
+    parts = sdp.ops.gemm_stats_parts(C, torch.bfloat16)
+    stats = torch.full((M, parts, 2), -7.0, device="cuda") if C % 32 == 0 else None
+    sdp.ops.gemm(A, W, oh[:M], bias=bvec, act=act, residual=oh[:M], pass_rows=(S, R) if R else (0, 0),
+                 residual_lo=ol[:M], out_lo=ol[:M], stats_out=stats)
+    got = oh[:M].float() + ol[:M].float()
+    live = ~rows
+    scale = float(ref.abs().max())
+    assert float((got[live] - ref[live]).abs().max()) < 1e-4 * scale          # bf16 alone would be ~4e-3 * scale
+    assert torch.equal(oh[:M][live], ref[live].to(torch.bfloat16)) or \
+        float((oh[:M][live].float() - ref[live]).abs().max()) < 8e-3 * scale      # hi = bf16(v) (ties may differ by an ulp)
+    assert float((ol[:M][live].float()).abs().max()) <= 2.0 ** -8 * scale       # lo is a rounding remainder
+    assert torch.equal(oh[:M][rows], hi[rows]) and torch.equal(ol[:M][rows], lo[rows])
+    assert bool((oh[M:] == 3.0).all()) and bool((ol[M:] == 5.0).all())            # nothing written behind M
+    if stats is not None:
+        h = oh[:M].float()
+        g = stats.sum(1)
+        assert (g[live, 0] - h[live].sum(1)).abs().max() < 2e-3 * (1 + h[live].abs().sum(1).max())
+        assert (g[live, 1] - (h[live] ** 2).sum(1)).abs().max() < 2e-3 * (1 + (h[live] ** 2).sum(1).max())
+        assert (stats[rows] == -7.0).all()
+    # hi-only in-place (no lo plane) through the same epilogue equals the separate-residual result bit for bit
+    o2 = hi.clone()
+    sdp.ops.gemm(A, W, o2, bias=bvec, act=act, residual=o2, pass_rows=(S, R) if R else (0, 0))
+    sep = torch.empty_like(hi)
+    sdp.ops.gemm(A, W, sep, bias=bvec, act=act, residual=hi)
+    assert torch.equal(o2[live], sep[live]) and torch.equal(o2[rows], hi[rows])
+
+
+def test_gemm_bf16_split_stream_is_repeatable_and_accumulates(sdp):
+    """Twenty in-place residual GEMMs in a row on the split stream (what a deep model does to it): the error against
+    an fp32 running sum stays at the 1e-5 level instead of growing like a bf16 stream's, and the run is bit-repeatable."""
+    M, C, K = 2610, 768, 768
+    A = rnd(M, K, seed=31, dtype=torch.bfloat16)
+    W = rnd(C, K, seed=32, scale=0.3 / math.sqrt(K), dtype=torch.bfloat16)
+    x = rnd(M, C, seed=33)
+    delta = A.float() @ W.float().t()
+
+    def run(split):
+        hi, lo = _split(x)
+        if not split:
+            lo = None
+        for _ in range(20):
+            sdp.ops.gemm(A, W, hi, residual=hi, residual_lo=lo, out_lo=lo)
+        return hi.float() + (lo.float() if split else 0.0), hi, lo
+
+    ref = x + 20 * delta
+    got, hi, lo = run(True)
+    got2, hi2, lo2 = run(True)
+    plain, _, _ = run(False)
+    assert torch.equal(hi, hi2) and torch.equal(lo, lo2)
+    e_split = float((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    e_plain = float((plain - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    assert e_split < 5e-5 and e_plain > 20 * e_split, (e_split, e_plain)
+
+
+def test_split_stream_row_kernels(sdp):
+    """fill_registers / pool_ln / tokens_to_nchw on the (hi, lo) planes."""
+    B, S, R, C = 6, 21, 5, 96
+    table = rnd(R, C, seed=23)
+    x = rnd(B, S, C, seed=24)
+    hi, lo = _split(x)
+    sdp.ops.fill_registers(hi, table, act_lo=lo)
+    full = hi.float() + lo.float()
+    assert float((full[:, :R] - table.expand(B, R, C)).abs().max()) < 2.0 ** -15 * float(table.abs().max())
+    assert torch.equal(full[:, R:], (x.to(torch.bfloat16).float() + (x - x.to(torch.bfloat16).float()).to(torch.bfloat16).float())[:, R:])
+    w, b = rnd(C, seed=25) + 1, rnd(C, seed=26)
+    out = torch.empty(B, C, device="cuda", dtype=torch.float32)
+    sdp.ops.pool_ln(hi, 0, R, w, b, out, 1e-5, act_lo=lo)
+    ref = F.layer_norm(full[:, :R].mean(1), (C,), w, b, 1e-5)
+    assert float((out - ref).abs().max()) < 2e-5
+    T = S - R
+    xo, ro = torch.empty(B, C, 4, 4, device="cuda"), torch.empty(B, R, C, device="cuda")
+    sdp.ops.tokens_to_nchw(hi, xo, ro, T, R, act_lo=lo)
+    assert torch.equal(xo.flatten(2).transpose(1, 2), full[:, R:]) and torch.equal(ro, full[:, :R])
+
+
+def test_gemm_bf16_patch_embed_split_stream(sdp):
+    """Patch-embedding epilogue (row remap + fp32 position table) writing both planes of the split stream."""
+    B, T, R, C, K = 5, 36, 4, 128, 200
+    S = T + R
+    A = rnd(B * T, K, seed=41, dtype=torch.bfloat16)
+    W = rnd(C, K, seed=42, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    pos = rnd(T, C, seed=43)
+    hi = torch.zeros(B * S, C, device="cuda", dtype=torch.bfloat16)
+    lo = torch.zeros_like(hi)
+    sdp.ops.gemm(A, W, hi, residual=pos, res_first=True, res_mod=T, seq_remap=(T, S, R), out_lo=lo)
+    ref = (A.float() @ W.float().t()).view(B, T, C) + pos
+    got = (hi.float() + lo.float()).view(B, S, C)
+    assert float((got[:, R:] - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+    assert bool((got[:, :R] == 0).all())
 
 @pytest.mark.parametrize("M,N,K", [(70, 50, 33), (129, 65, 100), (300, 128, 64)])
 def test_gemm_fp32(sdp, M, N, K):
