@@ -8,18 +8,23 @@
 // whole weight operand of a channel 2 registers per tap row and lane -- 14 for k = 7 -- small enough to stay in
 // registers for the lifetime of the CTA.  So the kernel is organised around the weights, not around the image:
 //   * a CTA owns 32 channels (each of its 8 warps owns 4, B fragments loaded once) and loops over images;
-//   * per image it streams the [tokens, 32 channels] slice in with cp.async (64 B per token = two full sectors),
-//     normalises and transposes it into per-channel planes with ldmatrix.trans (80-byte token rows and 48-byte
-//     plane rows: conflict-free both ways), runs 14 mma.sync.m16n8k16 per channel on ldmatrix'ed plane rows, and
-//     writes the [tokens, 32] result back through a token-major tile with 128-bit stores;
-//   * the token statistics (over all C channels) come from a separate warp-per-row pass, because a slab CTA never
-//     sees the whole row.
+//   * the [grid rows, 16 column slots, 32 channels] slice of an image (64 B per token = two full sectors) arrives by
+//     TMA through a 4-D view [image][grid row][grid column][channel] of the token-major stream -- 64B-swizzled, column
+//     slots past a narrow row's end zero-filled by the TMA unit -- into a three-deep mbarrier ring, together with the
+//     image's token statistics (one bulk copy); one elected thread issues both, nobody computes addresses;
+//   * the warps normalise and transpose the slice into per-channel planes with ldmatrix.trans (48-byte plane rows:
+//     conflict-free), run 14 mma.sync.m16n8k16 per channel on ldmatrix'ed plane rows, and write the [tokens, 32]
+//     result back into the ring slot the slice came in (64B-swizzled, free once the planes are built), which leaves
+//     as ONE TMA store through the same 4-D view of `out`; the slot is refilled once that store has read it: two
+//     CTA barriers per image (planes complete; result tile complete);
+//   * the token statistics (over all C channels) come from the producer GEMM's epilogue (or a warp-per-row pass),
+//     because a slab CTA never sees the whole row.
 // Two CTAs per SM overlap one's transposes with the other's MMAs.  12544 scalar FMAs per channel and image
-// become 14 MMAs.
+// become 14 MMAs; the per-image instruction count is what bounds the kernel, hence no index arithmetic in the loop.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
-#include "common.cuh"
+#include "tc5.cuh"
 
 namespace sdp {
 
@@ -27,9 +32,9 @@ constexpr int DS_THREADS = 256;
 constexpr int DS_CH = 32;                 // channels per CTA
 constexpr int DS_HL = 4;                  // left halo columns (keeps 8-column blocks 16-byte aligned)
 constexpr int DS_PROW = 48;               // bytes per plane row: 24 bf16 = 4 halo + 16 + 4 halo
-constexpr int DS_RAWP = 64;               // bytes per token in the raw tile; 16-byte chunk c of token t sits at c ^ ((t >> 1) & 3):
-                                          // conflict-free for the cp.async writes (whole rows) and the ldmatrix reads (8 tokens x 16 B)
-constexpr int DS_OUTP = 80;               // bytes per token in the out tile: 64 used + 16 pad
+constexpr int DS_RAWP = 64;               // bytes per token in the raw / out tiles; 16-byte chunk c of slot t sits at c ^ ((t >> 1) & 3)
+                                          // (the TMA unit's 64B swizzle): conflict-free for the ldmatrix reads (8 tokens x 16 B)
+constexpr int DS_STAGES = 4;              // ring slots per CTA: a slot holds an image's slice, then (in place) its result
 
 __device__ __forceinline__ void ds_mma(float *c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                        uint32_t b1) {
@@ -50,9 +55,6 @@ __device__ __forceinline__ void ds_ldmatrix_x4_trans(uint32_t addr, uint32_t *r)
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
-}
-__device__ __forceinline__ void ds_cp_async16(uint32_t dst, const void *src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
 // (mean, rstd) of every spatial token row over all C channels, compact [B][Tn]: warp per row, the row held in
@@ -119,8 +121,8 @@ token_stats_from_parts_kernel(const float2 *__restrict__ parts_in, float2 *__res
 template <int KS>
 struct DsLayout {
   static constexpr int ROWS = 16 + KS - 1;
-  int raw, stat, planes, otile, total;
-  int plane_bytes;
+  int raw, otile, stat, planes, bars, total;
+  int plane_bytes, tile_bytes, stat_bytes;
   __host__ __device__ explicit DsLayout(int Gh, int Tn) {
     const int TP = Gh * 16;                                 // token slots of the raw / out tiles: grid rows padded to 16
     // plane stride: a multiple of 16 bytes whose word count is 12 (mod 32): the eight channels a transposing
@@ -128,48 +130,53 @@ struct DsLayout {
     int pb = (ROWS * DS_PROW + 15) / 16 * 16;
     while ((pb / 4) % 32 != 12) pb += 16;
     plane_bytes = pb;
-    raw = 0;                                                // [2][TP][64 B]
-    stat = raw + 2 * TP * DS_RAWP;                          // [2][Tn] float2 (mean, rstd)
-    planes = stat + 2 * ((Tn * 8 + 15) / 16 * 16);          // [32][plane_bytes], zero halo
-    planes = (planes + 15) / 16 * 16;
-    otile = planes + DS_CH * pb;                            // [TP][80 B]
-    total = otile + TP * DS_OUTP;
+    tile_bytes = (TP * DS_RAWP + 1023) / 1024 * 1024;       // swizzled TMA boxes: 1 KB-aligned
+    stat_bytes = (Tn * 8 + 15) / 16 * 16;
+    raw = 0;                                                // [DS_STAGES][TP][64 B]: input slice, later the output tile
+    otile = raw;
+    stat = raw + DS_STAGES * tile_bytes;                    // [DS_STAGES][Tn] float2 (mean, rstd)
+    planes = (stat + DS_STAGES * stat_bytes + 15) / 16 * 16;   // [32][plane_bytes], zero halo
+    bars = planes + DS_CH * pb;                             // DS_STAGES mbarriers
+    total = bars + 64 + 1024;                               // + slack for the 1 KB alignment of the base
   }
 };
 
 template <int KS>
 __global__ void __launch_bounds__(DS_THREADS, 2)
-ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ stats, const float *__restrict__ gamma,
+ln_dwconv_slab_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
+                      const float2 *__restrict__ stats, const float *__restrict__ gamma,
                       const float *__restrict__ beta, const float *__restrict__ wdw, const float *__restrict__ bdw,
                       bf16 *__restrict__ out, int B, int Gh, int Gw, int C, int R, int img_per_cta) {
   constexpr int lo = (KS - 1) / 2;
-  extern __shared__ __align__(16) uint8_t ds_smem[];
+  extern __shared__ uint8_t ds_raw[];
+  uint8_t *ds_smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ds_raw) + 1023) & ~uintptr_t(1023));
   const int Tn = Gh * Gw, S = R + Tn;
   const DsLayout<KS> L(Gh, Tn);
   const int PB = L.plane_bytes;
-  const int TP = Gh * 16, SBUF = (Tn * 8 + 15) / 16 * 16;
-  const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(ds_smem));
+  const int TP = Gh * 16;
+  const uint32_t sbase = smem_u32(ds_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int c0 = blockIdx.x * DS_CH;
   const int b_begin = blockIdx.y * img_per_cta, b_end = min(B, b_begin + img_per_cta);
   if (b_begin >= b_end) return;
+  auto full_bar = [&](int st) { return sbase + L.bars + 8u * st; };
   // images are walked from the last to the first (loop index b -> image B - 1 - b): the producer GEMM wrote the
   // activations in ascending order, so the tail of the batch is still in L2, and the consumer GEMM starts at image 0
-  auto prefetch = [&](int bi, int buf) {   // the [Tn, 32-channel] slice of an image (64 B per token) + its statistics
-    const int b = B - 1 - bi;
-    const bf16 *src = act + ((long long)b * S + R) * C + c0;
-    for (int i = tid; i < Tn * 4; i += DS_THREADS) {
-      const int t = i >> 2, slot = (t / Gw) * 16 + t % Gw;   // token (y, x) sits in slot 16 y + x
-      ds_cp_async16(sbase + L.raw + buf * TP * DS_RAWP + slot * DS_RAWP + (((i & 3) ^ ((slot >> 1) & 3)) << 4),
-                    src + (long long)t * C + (i & 3) * 8);
-    }
-    const float2 *ss = stats + (long long)b * Tn;            // Tn is even: 16-byte aligned for every image
-    for (int i = tid; i < Tn / 2; i += DS_THREADS)
-      ds_cp_async16(sbase + L.stat + buf * SBUF + i * 16, ss + 2 * i);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  auto issue = [&](int bi) {               // one thread: the [Gh, 16, 32-channel] slice of an image + its statistics
+    const int st = (bi - b_begin) % DS_STAGES, b = B - 1 - bi;
+    const uint32_t bar = full_bar(st);
+    mbar_expect_tx(bar, (uint32_t)(TP * DS_RAWP + Tn * 8));
+    tma_load_4d(sbase + L.raw + st * L.tile_bytes, &tmIn, bar, c0, 0, 0, b);
+    bulk_load(sbase + L.stat + st * L.stat_bytes, stats + (long long)b * Tn, (uint32_t)(Tn * 8), bar);   // Tn is even: 16-byte units
   };
-  prefetch(b_begin, 0);
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmIn) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+    for (int st = 0; st < DS_STAGES; ++st) mbar_init(full_bar(st), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int bi = b_begin; bi < b_end && bi < b_begin + DS_STAGES; ++bi) issue(bi);
+  }
 
   // zero the planes once: halo cells are never written again
   for (int i = tid; i < DS_CH * PB / 16; i += DS_THREADS)
@@ -204,33 +211,35 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
   const uint32_t a_lane = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * DS_PROW + (lane >> 4) * 16);
   const uint32_t a_lane2 = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * DS_PROW + 32);
   const uint32_t planes_addr = sbase + L.planes;
+  const bool full_rows = Gw == 16;         // no padded column slots: every slot is a token
+  __syncthreads();                         // barriers initialised, planes zeroed
 
   for (int b = b_begin; b < b_end; ++b) {
-    const int buf = (b - b_begin) & 1;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                       // slice b has landed; everybody is past the previous image's stores
-    if (b + 1 < b_end) prefetch(b + 1, buf ^ 1);
+    const int it = b - b_begin, st = it % DS_STAGES;
+    mbar_wait(full_bar(st), (uint32_t)((it / DS_STAGES) & 1));       // slice b and its statistics have landed
 
     // ---- normalise + transpose: [token][channel] rows -> per-channel planes (two tokens per 32-bit store) ----
-    const uint32_t raw_addr = sbase + L.raw + buf * TP * DS_RAWP;
-    const float2 *s_stat = reinterpret_cast<const float2 *>(ds_smem + L.stat + buf * SBUF);
+    const uint32_t raw_addr = sbase + L.raw + st * L.tile_bytes;
+    const float2 *s_stat = reinterpret_cast<const float2 *>(ds_smem + L.stat + st * L.stat_bytes);
     for (int t0 = warp * 8; t0 < TP; t0 += 8 * (DS_THREADS / 32)) {      // eight slots of one grid row
       const int y = t0 >> 4, x = (t0 & 15) + 2 * q;
-      if ((t0 & 15) >= Gw) continue;                          // the padded half of a narrow row (warp-uniform)
+      if (!full_rows && (t0 & 15) >= Gw) continue;            // the padded half of a narrow row (warp-uniform)
       uint32_t r4[4];
       ds_ldmatrix_x4_trans(raw_addr + (t0 + (lane & 7)) * DS_RAWP + (((lane >> 3) ^ ((lane >> 1) & 3)) << 4), r4);
-      const bool in0 = x < Gw, in1 = x + 1 < Gw;              // slots past the row end hold stale bytes
-      const float2 st0 = s_stat[in0 ? y * Gw + x : 0], st1 = s_stat[in1 ? y * Gw + x + 1 : 0];
+      const bool in0 = full_rows || x < Gw, in1 = full_rows || x + 1 < Gw;   // slots past the row end are zero-filled
+      const float4 st01 = full_rows ? *reinterpret_cast<const float4 *>(s_stat + t0 + 2 * q)
+                                    : make_float4(s_stat[in0 ? y * Gw + x : 0].x, s_stat[in0 ? y * Gw + x : 0].y,
+                                                  s_stat[in1 ? y * Gw + x + 1 : 0].x, s_stat[in1 ? y * Gw + x + 1 : 0].y);
       const uint32_t cell = planes_addr + (y + lo) * DS_PROW + (DS_HL + x) * 2;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const float v0 = (__uint_as_float(r4[m] << 16) - st0.x) * st0.y;
-        const float v1 = (__uint_as_float(r4[m] & 0xffff0000u) - st1.x) * st1.y;
+        const float v0 = (__uint_as_float(r4[m] << 16) - st01.x) * st01.y;
+        const float v1 = (__uint_as_float(r4[m] & 0xffff0000u) - st01.z) * st01.w;
         const uint32_t pk = pack_bf16x2(in0 ? fmaf(v0, gm[m], bt[m]) : 0.0f, in1 ? fmaf(v1, gm[m], bt[m]) : 0.0f);
         if (in0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(cell + (8 * m + g) * PB), "r"(pk) : "memory");   // halo stays 0
       }
     }
-    __syncthreads();                       // planes of image b complete
+    __syncthreads();                       // planes of image b complete: its ring slot now takes the result
 
     // ---- MMA: four channels per warp, 2 * KS MMAs each ----
     float acc[4][2][4];
@@ -250,40 +259,44 @@ ln_dwconv_slab_kernel(const bf16 *__restrict__ act, const float2 *__restrict__ s
         ds_mma(acc[cc][1], a[2], a[3], a2[0], a2[1], bfr[cc][dy][0], bfr[cc][dy][1]);
       }
     }
-    // C fragments: (y = g | g + 8, x = 8n + 2q, +1); the warp's four channels of a token go out as one 8-byte store
-    // 8-byte slot w of token (y, x) sits at w ^ (y & 3): the 16 lanes of a half-warp (4 rows x 4 column pairs) then
-    // cover all 32 banks
-    const uint32_t otile_addr = sbase + L.otile;
+    const uint32_t otile_addr = raw_addr;
+    // C fragments: (y = g | g + 8, x = 8n + 2q, +1); the warp's four channels of a token are 8 bytes of the token's
+    // 64-byte row: 16-byte chunk warp / 2 (64B swizzle: ^ (slot >> 1) & 3 = q), half warp & 1
 #pragma unroll
     for (int n = 0; n < 2; ++n)
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int y = g + 8 * hh, x = 8 * n + 2 * q;
-        if (y < Gh && x < Gw) {                               // (a slot past a narrow row's end is never read back)
+        if (y < Gh) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const uint32_t lo2 = pack_bf16x2(acc[0][n][2 * hh + e], acc[1][n][2 * hh + e]);
             const uint32_t hi2 = pack_bf16x2(acc[2][n][2 * hh + e], acc[3][n][2 * hh + e]);
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(otile_addr + (y * 16 + x + e) * DS_OUTP + ((warp ^ (g & 3)) << 3)),
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(otile_addr + (y * 16 + x + e) * DS_RAWP +
+                                                                  ((((warp >> 1) ^ q) << 4) | ((warp & 1) << 3))),
                          "r"(lo2), "r"(hi2)
                          : "memory");
           }
         }
       }
-    __syncthreads();                       // out tile complete, planes free
-
-    // ---- 128-bit stores of the [Tn, 32] result; the R register rows of the slab are zero (passed through later) ----
-    bf16 *dst = out + (long long)(B - 1 - b) * S * C + c0;
-    for (int i = tid; i < R * 4; i += DS_THREADS)
-      *reinterpret_cast<uint4 *>(dst + (long long)(i >> 2) * C + (i & 3) * 8) = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < Tn * 4; i += DS_THREADS) {
-      const int t = i >> 2, y = t / Gw, sw = y & 3;
-      const uint8_t *row = ds_smem + L.otile + (y * 16 + t % Gw) * DS_OUTP;
-      const uint2 u0 = *reinterpret_cast<const uint2 *>(row + (((2 * (i & 3)) ^ sw) << 3));
-      const uint2 u1 = *reinterpret_cast<const uint2 *>(row + (((2 * (i & 3) + 1) ^ sw) << 3));
-      *reinterpret_cast<uint4 *>(dst + (long long)(R + t) * C + (i & 3) * 8) = make_uint4(u0.x, u0.y, u1.x, u1.y);
+    fence_proxy_async_smem();
+    __syncthreads();                       // result tile complete, planes free for the next image
+    // the [Gh, Gw, 32] result leaves as one TMA store (column slots past Gw are clipped); once the PREVIOUS image's
+    // store has read its slot, that slot takes the slice of image b - 1 + DS_STAGES.  The R register rows of the slab
+    // are zero (the consumer GEMM passes those rows through).
+    if (tid == 0) {
+      tma_store_4d(&tmOut, otile_addr, c0, 0, 0, B - 1 - b);
+      bulk_commit();
+      if (b > b_begin && b - 1 + DS_STAGES < b_end) {
+        bulk_wait_read<1>();
+        issue(b - 1 + DS_STAGES);
+      }
     }
+    bf16 *dst = out + (long long)(B - 1 - b) * S * C + c0;
+    for (int i = tid - 32; i >= 0 && i < R * 4; i += DS_THREADS - 32)
+      *reinterpret_cast<uint4 *>(dst + (long long)(i >> 2) * C + (i & 3) * 8) = make_uint4(0, 0, 0, 0);
   }
+  if (tid == 0) bulk_wait_read<0>();       // shared memory outlives the last store's read
 }
 
 static int num_sms_ds() {
@@ -302,7 +315,6 @@ static int launch_slab(const void *act, const float *producer, int parts, float 
                        float eps, cudaStream_t st) {
   const int Tn = Gh * Gw, S = R + Tn;
   const long long rows = (long long)B * Tn;
-  (void)S;
   const unsigned sblocks = (unsigned)((rows + 7) / 8);
   float2 *ts = reinterpret_cast<float2 *>(token_stats);
   if (producer != nullptr && parts > 0)
@@ -316,10 +328,15 @@ static int launch_slab(const void *act, const float *producer, int parts, float 
   SDP_LAUNCH_OK();
   const DsLayout<KS> L(Gh, Tn);
   auto kern = ln_dwconv_slab_kernel<KS>;
-  static int configured = 0;
-  if (L.total > configured) {
-    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    configured = L.total;
+  SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));   // per device, cheap
+  // [image][grid row][grid column][channel] views of the patch rows of act / out (behind the R register rows)
+  CUtensorMap tin, tout;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)Gw, (uint64_t)Gh, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)C, (uint64_t)Gw * C, (uint64_t)S * C};
+    const uint32_t box[4] = {DS_CH, 16, (uint32_t)Gh, 1};
+    if (int rc = make_tensor_map_bf16_4d(reinterpret_cast<const bf16 *>(act) + (long long)R * C, dims, str, box, &tin)) return rc;
+    if (int rc = make_tensor_map_bf16_4d(reinterpret_cast<bf16 *>(out) + (long long)R * C, dims, str, box, &tout)) return rc;
   }
   const int slabs = C / DS_CH;
   // two CTAs per SM; image groups sized so that the grid is (just under) one wave
@@ -328,7 +345,7 @@ static int launch_slab(const void *act, const float *producer, int parts, float 
   if (groups > B) groups = B;
   const int per = (B + groups - 1) / groups;
   groups = (B + per - 1) / per;
-  kern<<<dim3(slabs, groups), DS_THREADS, L.total, st>>>((const bf16 *)act, reinterpret_cast<const float2 *>(token_stats),
+  kern<<<dim3(slabs, groups), DS_THREADS, L.total, st>>>(tin, tout, reinterpret_cast<const float2 *>(token_stats),
                                                          gamma, beta, wdw, bdw, (bf16 *)out, B, Gh, Gw, C, R, per);
   SDP_LAUNCH_OK();
   return 0;

@@ -72,14 +72,20 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
                     const Epilogue epi, const int K, const int flags) {
+  // flags: bit 0 = 16-byte epilogue accesses are legal; bit 2 = clusters of two CTA pairs that share the weight tile
+  // (the pairs take neighbouring 256-row tiles of the same column block; each CTA loads a quarter of the block and
+  // multicasts it to its counterpart in the other pair: a quarter less L2 -> SM traffic, which is what bounds the GEMMs)
   const int vec_ok = flags & 1;
+  const int mc = (CG == 2 && (flags & 4)) ? 2 : 1;
 #ifdef SDP_DIAG
   const bool nofeed = (flags & 2) != 0;   // diagnostic build only: no TMA loads, MMAs run on stale shared memory
 #else
   constexpr bool nofeed = false;
 #endif
   using L = SmemLayout<BN, STAGES, CG, out_bytes_for(LEAN != 0, RSM, CG)>;
-  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
+  const uint32_t rank = crank & 1u;                 // position inside the CTA pair (0 = leader, issues the MMAs)
+  const uint32_t pairid = crank >> 1, leader = crank & ~1u;
   extern __shared__ uint8_t smem_raw[];
   // swizzle-128B tiles need 1024-byte alignment
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -106,7 +112,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int i = 0; i < EW * NSLOT; ++i) mbar_init(res_bar(0, i), 1);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), mc);           // one commit per pair that reads this slot
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -135,11 +141,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   constexpr int TILE_M = BLOCK_M * CG;
-  const int m_tiles = (epi.M + TILE_M - 1) / TILE_M;
+  const int UNIT_M = TILE_M * mc;                    // rows one cluster covers per tile
+  const int m_tiles = (epi.M + UNIT_M - 1) / UNIT_M;
   const int n_tiles = (epi.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-  const int unit0 = blockIdx.x / CG, unit_stride = gridDim.x / CG;
+  const int unit0 = blockIdx.x / (CG * mc), unit_stride = gridDim.x / (CG * mc);
+  const int row_off = pairid * TILE_M + rank * BLOCK_M;   // this CTA's rows inside the cluster's tile
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -148,7 +156,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
-        const int m0 = (tile / n_tiles) * TILE_M + rank * BLOCK_M;
+        const int m0 = (tile / n_tiles) * UNIT_M + row_off;
         const int n0 = (tile % n_tiles) * BN + rank * (BN / CG);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
@@ -164,7 +172,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               // both CTAs' bytes complete on the LEADER's full barrier; only the leader arms it
               if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
               tma_load_2d_2sm(sa, &tmA, full_bar(stage), kb * BLOCK_K, m0);
-              tma_load_2d_2sm(sa + L::A_BYTES, &tmW, full_bar(stage), kb * BLOCK_K, n0);
+              if (mc == 1) {
+                tma_load_2d_2sm(sa + L::A_BYTES, &tmW, full_bar(stage), kb * BLOCK_K, n0);
+              } else {       // our quarter of the column block, to us and to the same-rank CTA of the other pair
+                tma_load_2d_2sm_mc(sa + L::A_BYTES + pairid * (L::B_BYTES / 2), &tmW, full_bar(stage), kb * BLOCK_K,
+                                   n0 + pairid * (BN / 4), static_cast<uint16_t>(5u << rank));
+              }
             }
           }
           __syncwarp();
@@ -205,8 +218,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tc_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
               if (kb == num_kb - 1) tc_commit(tfull_bar(acc));
             } else {                                       // same barriers in both CTAs of the pair
-              tc_commit_2sm(empty_bar(stage));
-              if (kb == num_kb - 1) tc_commit_2sm(tfull_bar(acc));
+              tc_commit_2sm(empty_bar(stage), mc == 2 ? 15 : 3);         // every CTA whose slot these MMAs read or feed
+              if (kb == num_kb - 1) tc_commit_2sm(tfull_bar(acc), static_cast<uint16_t>(3u << leader));
             }
           }
           __syncwarp();
@@ -226,7 +239,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * TILE_M + rank * BLOCK_M;
+      const int m0 = (tile / n_tiles) * UNIT_M + row_off;
       const int n0 = (tile % n_tiles) * BN + part * WCOLS;
       uint64_t nmean2 = 0ull, rstd2 = 0ull;
       if constexpr (LEAN == 2) {                   // this row's (mean, rstd) from the producer's column-part sums
@@ -259,7 +272,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (lane == 0) {
             if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
-            else mbar_arrive_cta(tempty_bar(acc), 0);
+            else mbar_arrive_cta(tempty_bar(acc), leader);
           }
         }
         const int col = n0 + c;
@@ -329,7 +342,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int sl = issued % NSLOT;
         if (lane == 0) {
           const uint32_t dst = slot_base + sl * SLOT_BYTES, bar = res_bar(ew, sl);
-          const int col = pf_col(), row = (pf_tile / n_tiles) * TILE_M + rank * BLOCK_M + quad * 32;
+          const int col = pf_col(), row = (pf_tile / n_tiles) * UNIT_M + row_off + quad * 32;
           mbar_expect_tx(bar, SLOT_BYTES);
           tma_load_2d(dst, &tmO, bar, col, row);
           if constexpr (RSM == 2) tma_load_2d(dst + 2048, &tmO2, bar, col, row);
@@ -344,7 +357,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * TILE_M + rank * BLOCK_M;
+      const int m0 = (tile / n_tiles) * UNIT_M + row_off;
       const int n0 = (tile % n_tiles) * BN + half * HCOLS;
       const RowMap rm = map_row(epi, m0 + quad * 32 + lane);
       const int nchunks = n0 >= epi.N ? 0 : (epi.N - n0 >= HCOLS ? CPW : (epi.N - n0 + 31) / 32);
@@ -357,7 +370,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
         if (lane == 0) {
           if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
-          else mbar_arrive_cta(tempty_bar(acc), 0);
+          else mbar_arrive_cta(tempty_bar(acc), leader);
         }
       }
 #pragma unroll 1
@@ -373,7 +386,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (lane == 0) {
             if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
-            else mbar_arrive_cta(tempty_bar(acc), 0);
+            else mbar_arrive_cta(tempty_bar(acc), leader);
           }
         }
         const int col = n0 + k * 32;
@@ -457,7 +470,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * TILE_M + rank * BLOCK_M;
+      const int m0 = (tile / n_tiles) * UNIT_M + row_off;
       const int n0 = (tile % n_tiles) * BN;
       const RowMap rm = map_row(epi, m0 + quad * 32 + lane);
       // LayerNorm folded into this GEMM: the row's (mean, rstd) from the producer's column-part sums
@@ -610,7 +623,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
       if (lane == 0) {
         if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
-        else mbar_arrive_cta(tempty_bar(acc), 0);        // the leader's MMA warp waits for both CTAs' epilogues
+        else mbar_arrive_cta(tempty_bar(acc), leader);   // the leader's MMA warp waits for both CTAs' epilogues
       }
     }
     if (STAGED && lane == 0) bulk_wait_read<0>();   // staging slots must outlive their last store's read
@@ -759,6 +772,27 @@ int make_tensor_map_bf16_3d(const void *ptr, uint64_t n2, uint64_t n1, uint64_t 
   return 0;
 }
 
+// [n3][n2][n1][n0] bf16 tensor with element strides (1, s1, s2, s3) and a (b0 x b1 x b2 x 1) box, 64B-swizzled when the
+// box row is 64 bytes: the depthwise kernel's [image][grid row][grid column][channel] view of the token-major stream
+// (box columns past n1 are zero-filled on loads and clipped on stores).  Not cached: callers keep the map.
+int make_tensor_map_bf16_4d(const void *ptr, const uint64_t dims[4], const uint64_t strides_elems[3], const uint32_t box[4],
+                            CUtensorMap *out) {
+  EncodeTiledFn enc = get_encode_fn();
+  SDP_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  SDP_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "4-D tensor map: base not 16-byte aligned");
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstr[3] = {strides_elems[0] * 2, strides_elems[1] * 2, strides_elems[2] * 2};
+  for (int i = 0; i < 3; ++i) SDP_CHECK(gstr[i] % 16 == 0, "4-D tensor map: stride %d not a multiple of 16 bytes", i);
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = box[0] * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : box[0] * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), gdim, gstr, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SDP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (4-D) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 static int pick_bn(int N) {   // BLOCK_N minimising padded columns; ties -> the larger tile
   int bn = 256;
   long best = -1;
@@ -771,6 +805,18 @@ static int pick_bn(int N) {   // BLOCK_N minimising padded columns; ties -> the 
 }
 
 int gemm_stats_parts(int N) { const int bn = pick_bn(N); return 2 * ((N + bn - 1) / bn); }
+
+// Clusters of two CTA pairs with the weight tile multicast between them: measured on B200 (XL step, batch 1024) at
+// +4 % GEMM time -- a quarter less L2 -> SM traffic does not pay for the 16 SMs a cluster of four cannot reach (33
+// clusters = 132 of 148 SMs).  Correct (the GEMM tests pass with it on) and kept for diagnostic builds only.
+static bool gemm_multicast_enabled() {
+#ifdef SDP_DIAG
+  static const bool on = [] { const char *v = getenv("SDP_GEMM_MC"); return v && v[0] == '1'; }();
+  return on;
+#else
+  return false;
+#endif
+}
 
 static bool staged_ok(const Epilogue &e) {
   return e.out_dtype == SDP_BF16 && e.seq_in == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 &&
@@ -789,22 +835,16 @@ static int rsm_planes(const Epilogue &e) {
 
 template <int BN, int STAGES, int ACT, int HN, bool STAGED, int CG = 1, int EW = EPI_WARPS, int LEAN = 0, int RSM = 0>
 static int launch_tc2(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &to, const CUtensorMap &to2,
-                      const Epilogue &e, int K, cudaStream_t st) {
+                      const Epilogue &e, int K, cudaStream_t st, const sdp_gemm_args *wsrc = nullptr) {
   using L = SmemLayout<BN, STAGES, CG, out_bytes_for(LEAN != 0, RSM, CG)>;
   static_assert(STAGES >= 2, "pipeline too shallow");
   auto kern = gemm_bf16_tc_kernel<BN, STAGES, ACT, HN, STAGED, CG, EW, LEAN, RSM>;
   static unsigned long long configured = 0;     // one bit per device ordinal
+  static int max_quads[64] = {};                // co-resident clusters of two pairs, per device
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!((configured >> (dev & 63)) & 1ull)) {
-    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured |= 1ull << (dev & 63);
-  }
-  const int units = ((e.M + BLOCK_M * CG - 1) / (BLOCK_M * CG)) * ((e.N + BN - 1) / BN);
-  const int slots = num_sms() / CG;
-  const int grid = CG * (units < slots ? units : slots);
+  dev &= 63;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3((2 + EW) * 32);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = st;
@@ -815,12 +855,39 @@ static int launch_tc2(const CUtensorMap &ta, const CUtensorMap &tw, const CUtens
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG > 1 ? 1 : 0;
-  int flags = epilogue_vec_ok(e) ? 1 : 0;
+  if (!((configured >> dev) & 1ull)) {
+    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    if (CG == 2) {
+      cfg.gridDim = dim3(4 * num_sms());
+      attr[0].val.clusterDim.x = 4;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+      max_quads[dev] = n;
+      attr[0].val.clusterDim.x = CG;
+    }
+    configured |= 1ull << dev;
+  }
+  // Clusters of two pairs sharing the weight tile (multicast): worth it once there is more than one wave of tiles,
+  // so that the SMs a 4-cluster cannot use (132 of 148 are reachable) cost less than the L2 traffic saved.
+  CUtensorMap tw_used = tw;
+  int mc = 1;
+  if (CG == 2 && wsrc != nullptr && max_quads[dev] > 0 && (BN / 4) % 8 == 0) {
+    const long units2 = (long)((e.M + 4 * BLOCK_M - 1) / (4 * BLOCK_M)) * ((e.N + BN - 1) / BN);
+    if (units2 >= 2L * max_quads[dev] && gemm_multicast_enabled()) {
+      if (int rc = get_tensor_map(wsrc->W, wsrc->N, wsrc->K, wsrc->ldw, BN / 4, &tw_used)) return rc;
+      mc = 2;
+    }
+  }
+  const int units = ((e.M + BLOCK_M * CG * mc - 1) / (BLOCK_M * CG * mc)) * ((e.N + BN - 1) / BN);
+  const int slots = mc == 2 ? max_quads[dev] : num_sms() / CG;
+  cfg.gridDim = dim3(CG * mc * (units < slots ? units : slots));
+  attr[0].val.clusterDim.x = CG * mc;
+  int flags = (epilogue_vec_ok(e) ? 1 : 0) | (mc == 2 ? 4 : 0);
 #ifdef SDP_DIAG
   static const int nofeed = [] { const char *v = getenv("SDP_GEMM_NOFEED"); return (v && v[0] == '1') ? 2 : 0; }();
   flags |= nofeed;
 #endif
-  SDP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw, to, to2, e, K, flags));
+  SDP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw_used, to, to2, e, K, flags));
   SDP_LAUNCH_OK();
   return 0;
 }
@@ -851,8 +918,8 @@ static int launch_tc(const sdp_gemm_args &a, const CUtensorMap &ta, const Epilog
         constexpr int ST2 = (STAGES * (BLOCK_M + BN)) / (BLOCK_M + BN / 2);   // same bytes, deeper ring
         if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, BN / 2, &tw)) return rc;
         if constexpr (HN == 0) {
-          if (rsm == 2) return launch_tc2<BN, stages_for(BN, 2, out_bytes_for(false, 2, 2), ST2), ACT, 0, true, 2, EPI_WARPS, 0, 2>(ta, tw, to, to2, e, a.K, st);
-          if (rsm == 1) return launch_tc2<BN, stages_for(BN, 2, out_bytes_for(false, 1, 2), ST2), ACT, 0, true, 2, EPI_WARPS, 0, 1>(ta, tw, to, to2, e, a.K, st);
+          if (rsm == 2) return launch_tc2<BN, stages_for(BN, 2, out_bytes_for(false, 2, 2), ST2), ACT, 0, true, 2, EPI_WARPS, 0, 2>(ta, tw, to, to2, e, a.K, st, &a);
+          if (rsm == 1) return launch_tc2<BN, stages_for(BN, 2, out_bytes_for(false, 1, 2), ST2), ACT, 0, true, 2, EPI_WARPS, 0, 1>(ta, tw, to, to2, e, a.K, st, &a);
         }
         if constexpr (ACT == SDP_ACT_GELU && HN == 0 && BN == 256) {
           // bias (or folded LayerNorm) + GELU only (the C -> 4C GEMMs of the mixers and encoders): the lean 16-warp
@@ -860,11 +927,11 @@ static int launch_tc(const sdp_gemm_args &a, const CUtensorMap &ta, const Epilog
           if (e.residual == nullptr && e.stats_out == nullptr && e.pass_seq == 0 && e.seq_out == 0 && e.res_mod == 0 &&
               a.N % BN == 0 && epilogue_vec_ok(e)) {
             if (e.ln_stats != nullptr)
-              return launch_tc2<BN, ST2 - 1, ACT, HN, true, 2, EPI_WARPS_WIDE, 2>(ta, tw, to, to2, e, a.K, st);
-            return launch_tc2<BN, ST2 - 1, ACT, HN, true, 2, EPI_WARPS_WIDE, 1>(ta, tw, to, to2, e, a.K, st);
+              return launch_tc2<BN, ST2 - 1, ACT, HN, true, 2, EPI_WARPS_WIDE, 2>(ta, tw, to, to2, e, a.K, st, &a);
+            return launch_tc2<BN, ST2 - 1, ACT, HN, true, 2, EPI_WARPS_WIDE, 1>(ta, tw, to, to2, e, a.K, st, &a);
           }
         }
-        return launch_tc2<BN, ST2, ACT, HN, true, 2>(ta, tw, to, to2, e, a.K, st);
+        return launch_tc2<BN, ST2, ACT, HN, true, 2>(ta, tw, to, to2, e, a.K, st, &a);
       }
     }
     if (int rc = get_tensor_map(a.W, a.N, a.K, a.ldw, BN, &tw)) return rc;

@@ -84,10 +84,19 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap 
       ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t cta_mask = 3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3)
+               "h"(cta_mask)
                : "memory");
+}
+// the same load delivered to every CTA of `cta_mask` (same shared-memory offset in each); each destination's bytes
+// complete on the barrier of ITS pair's leader
+__device__ __forceinline__ void tma_load_2d_2sm_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                                 uint32_t accumulate) {
@@ -204,5 +213,26 @@ int make_tensor_map_bf16(const void *ptr, uint64_t rows, uint64_t cols, uint64_t
 // Dense [n2, n1, n0] bf16 tensor with 1 x box1 x box0 boxes, unswizzled (rows past n1 are clipped / zero-filled).
 int make_tensor_map_bf16_3d(const void *ptr, uint64_t n2, uint64_t n1, uint64_t n0, uint32_t box1, uint32_t box0,
                             CUtensorMap *out);
+
+int make_tensor_map_bf16_4d(const void *ptr, const uint64_t dims[4], const uint64_t strides_elems[3], const uint32_t box[4],
+                            CUtensorMap *out);
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// plain bulk copy global -> shared (size a multiple of 16 bytes), completing on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 
 }  // namespace sdp
