@@ -2,7 +2,9 @@
 // Reference: F.scaled_dot_product_attention at layers.py:289-291 (q, k already LayerNorm-ed by the QKV
 // GEMM epilogue, layers.py:286).
 //
-// One CTA per (image, head).  The whole K and V of the sequence (<= 288 keys) sit in shared memory as
+// Persistent: one CTA per SM walks (image, head) items; barriers, TMEM and tensor maps are set up once, and the next
+// item's Q tile 0 and K arrive (as soon as the last score MMA of the current item has retired) under the current item's
+// last softmax, its V under the next item's first scores.  The whole K and V of the sequence (<= 288 keys) sit in shared memory as
 // 64B-swizzled 32-column tiles loaded by TMA straight out of the [B*S, 3C] QKV buffer.  Per 128-query tile:
 //   S = Q K^T   tcgen05.mma, K-major A (Q) and B (K), fp32 scores in TMEM columns [0, KEYS)
 //   softmax     four warps, one thread per query row: tcgen05.ld the row, max, exp2, row sum; P (bf16) goes
@@ -16,13 +18,6 @@
 
 namespace sdp {
 
-#ifdef AT_TRACE
-#define AT_T(tag) do { if (trace_on && lane == 0 && ntr < 56) { tr_tag[ntr] = tag; tr_t[ntr++] = clock64() - t_begin; } } while (0)
-#define AT_DUMP(who) do { if (trace_on && lane == 0) for (int i_ = 0; i_ < ntr; ++i_) printf("%s w%d %3d %lld\n", who, warp, tr_tag[i_], tr_t[i_]); } while (0)
-#else
-#define AT_T(tag)
-#define AT_DUMP(who)
-#endif
 
 constexpr int AT_MT = 128;          // query rows per tile
 constexpr int AT_THREADS = 320;        // TMA warp, MMA warp, 8 softmax warps
@@ -118,7 +113,7 @@ __device__ __forceinline__ void at_exp_chunk(float (&v)[32], int lim, float scal
 //            same two instalments, so the tensor core works underneath the exponentials
 //   softmax: max over X, [O(t-1) -> global], max over Y, exp/sum/P over X, exp/sum/P over Y
 struct AtBars {
-  uint32_t kv_full, q_full, q_free, sx_full, sy_full, px_full, py_full, o_full, o_free, v_full, k1_full;   // o_*: two barriers each
+  uint32_t kv_full, q_full, q_free, sx_full, sy_full, px_full, py_full, o_full, o_free, v_full, k1_full, v_free;   // o_*: two barriers each
 };
 
 template <int D>
@@ -126,7 +121,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ32,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmKV,
                      const __grid_constant__ CUtensorMap tmO,
-                     bf16 *__restrict__ out, int S, int h, int KEYS, int kv_box_rows, float scale_log2, int tail_mode) {
+                     bf16 *__restrict__ out, int S, int h, int KEYS, int kv_box_rows, float scale_log2, int tail_mode,
+                     int n_items) {
   constexpr int NA = D / 32;                   // 32-column (64B-swizzled) atoms of V along the head dim
   // Q, K and P are K-major MMA operands read in 32-byte k-slices: only the 128B swizzle spreads the eight rows of
   // a slice over all banks (64B-swizzled rows collide two by two), so they use 64-column atoms wherever 64
@@ -141,7 +137,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (KA == 0) KA = (KEYS / 2) & ~31;
   if (KA == 0) KA = KEYS;
   const int KB = KEYS - KA;                    // keys in the Y half (may be 0)
-  const uint32_t q_off = 0;                                   // [N128][128 rows][128 B] [N64][128 rows][64 B]
+  // tail tile P^T: compact atoms [NP128][16 rows][128 B] [NP64][16 rows][64 B].  First in the layout: the P V MMAs of
+  // the tail tile are M = 128 wide and read 112 rows past each 16-row atom (their results land in TMEM lanes nobody
+  // reads), which must still be shared memory of this CTA -- the Q / K tiles behind it.
+  const uint32_t pt_off = 0;
+  const uint32_t q_off = NP128 * 2048 + NP64 * 1024;          // [N128][128 rows][128 B] [N64][128 rows][64 B]
   const uint32_t q64_off = q_off + N128 * AT_MT * 128;
   const uint32_t k_off = q_off + NA * AT_MT * 64;             // [N128][KEYS][128 B] [N64][KEYS][64 B]
   const uint32_t k64_off = k_off + N128 * KEYS * 128;
@@ -152,21 +152,46 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t bar = sbase + bar_off;
   AtBars B;
   B.kv_full = bar; B.q_full = bar + 8; B.q_free = bar + 16; B.sx_full = bar + 24; B.sy_full = bar + 32;
-  B.px_full = bar + 40; B.py_full = bar + 48; B.o_full = bar + 56; B.o_free = bar + 72; B.v_full = bar + 88; B.k1_full = bar + 96;
+  B.px_full = bar + 40; B.py_full = bar + 48; B.o_full = bar + 56; B.o_free = bar + 72; B.v_full = bar + 88; B.k1_full = bar + 96; B.v_free = bar + 112;
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + bar_off + 104);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = h * D;
-  // images from the last to the first: the QKV GEMM wrote its rows in ascending order (the tail of the batch is still in
-  // L2), and the output projection starts at image 0, which this grid then writes last
-  const int b = (int)(gridDim.x / h) - 1 - (int)(blockIdx.x / h), head = blockIdx.x % h;
+  // Items (image, head) are walked with a grid stride, images from the last to the first: the QKV GEMM wrote its rows
+  // in ascending order (the tail of the batch is still in L2), and the output projection starts at image 0, which
+  // this grid then writes last.
+  const int n_img = n_items / h;
+  auto item_image = [&](int item) { return n_img - 1 - item / h; };
   const int tiles = (S + AT_MT - 1) / AT_MT;
-#ifdef AT_TRACE
-  const bool trace_on = blockIdx.x == 4000;
-  const long long t_begin = clock64();
-  int ntr = 0, tr_tag[56];
-  long long tr_t[56];
-#endif
+  // Per-barrier completion counts.  Per tile (global tile index G = item iteration * tiles + t): q_full, q_free,
+  // sx_full, px_full; o_full / o_free alternate between the OB accumulators with G.  sy_full / py_full skip the
+  // transposed tail tile (HPT completions per item).  Per item: kv_full, k1_full, v_full.
+  const int HPT = tail_mode ? tiles - 1 : tiles;
+
+  // TMA issue helpers (one thread)
+  auto load_q = [&](int item, int t) {
+    const int row0 = item_image(item) * S + t * AT_MT, head = item % h;
+    mbar_expect_tx(B.q_full, NA * AT_MT * 64);
+    for (int a = 0; a < N128; ++a) tma_load_2d(sbase + q_off + a * AT_MT * 128, &tmQ, B.q_full, head * D + 64 * a, row0);
+    if (N64) tma_load_2d(sbase + q64_off, &tmQ32, B.q_full, head * D + 64 * N128, row0);
+  };
+  auto load_k = [&](int item) {            // the first box of K rows is all the X scores need
+    const int row0 = item_image(item) * S, head = item % h;
+    for (int r = 0; r < KEYS; r += kv_box_rows) {
+      const uint32_t kbar = r == 0 ? B.kv_full : B.k1_full;
+      mbar_expect_tx(kbar, NA * kv_box_rows * 64);
+      for (int a = 0; a < N128; ++a)
+        tma_load_2d(sbase + k_off + (a * KEYS + r) * 128, &tmK, kbar, C + head * D + 64 * a, row0 + r);
+      if (N64) tma_load_2d(sbase + k64_off + r * 64, &tmKV, kbar, C + head * D + 64 * N128, row0 + r);
+    }
+  };
+  auto load_v = [&](int item) {
+    const int row0 = item_image(item) * S, head = item % h;
+    mbar_expect_tx(B.v_full, NA * KEYS * 64);
+    for (int a = 0; a < NA; ++a)
+      for (int r = 0; r < KEYS; r += kv_box_rows)
+        tma_load_2d(sbase + v_off + (a * KEYS + r) * 64, &tmKV, B.v_full, 2 * C + head * D + 32 * a, row0 + r);
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -175,6 +200,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(B.kv_full, 1);
     mbar_init(B.v_full, 1);
     mbar_init(B.k1_full, 1);
+    mbar_init(B.v_free, 1);
     mbar_init(B.q_full, 1);
     mbar_init(B.q_free, 1);
     mbar_init(B.sx_full, 1);
@@ -186,23 +212,10 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(B.o_free, 8);
     mbar_init(B.o_free + 8, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // The loads of this (image, head) start before the rest of the CTA is set up: Q and the first box of K rows
-    // (all the X scores need), then the remaining K rows, then V.
-    const int row0 = b * S;
-    mbar_expect_tx(B.q_full, NA * AT_MT * 64);
-    for (int a = 0; a < N128; ++a) tma_load_2d(sbase + q_off + a * AT_MT * 128, &tmQ, B.q_full, head * D + 64 * a, row0);
-    if (N64) tma_load_2d(sbase + q64_off, &tmQ32, B.q_full, head * D + 64 * N128, row0);
-    for (int r = 0; r < KEYS; r += kv_box_rows) {
-      const uint32_t kbar = r == 0 ? B.kv_full : B.k1_full;
-      mbar_expect_tx(kbar, NA * kv_box_rows * 64);
-      for (int a = 0; a < N128; ++a)
-        tma_load_2d(sbase + k_off + (a * KEYS + r) * 128, &tmK, kbar, C + head * D + 64 * a, row0 + r);
-      if (N64) tma_load_2d(sbase + k64_off + r * 64, &tmKV, kbar, C + head * D + 64 * N128, row0 + r);
-    }
-    mbar_expect_tx(B.v_full, NA * KEYS * 64);
-    for (int a = 0; a < NA; ++a)
-      for (int r = 0; r < KEYS; r += kv_box_rows)
-        tma_load_2d(sbase + v_off + (a * KEYS + r) * 64, &tmKV, B.v_full, 2 * C + head * D + 32 * a, row0 + r);
+    // The loads of the first item start before the rest of the CTA is set up
+    load_q(blockIdx.x, 0);
+    load_k(blockIdx.x);
+    load_v(blockIdx.x);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -219,17 +232,24 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      const int row0 = b * S;
-      AT_T(1);
-      for (int t = 1; t < tiles; ++t) {
-        mbar_wait(B.q_free, (t - 1) & 1);
-        AT_T(2);                     // both score halves of tile t-1 are in TMEM
-        mbar_expect_tx(B.q_full, NA * AT_MT * 64);
-        for (int a = 0; a < N128; ++a)
-          tma_load_2d(sbase + q_off + a * AT_MT * 128, &tmQ, B.q_full, head * D + 64 * a, row0 + t * AT_MT);
-        if (N64) tma_load_2d(sbase + q64_off, &tmQ32, B.q_full, head * D + 64 * N128, row0 + t * AT_MT);
+      int G0 = 0;                                             // global index of the item's tile 0
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, G0 += tiles) {
+        for (int t = 1; t < tiles; ++t) {
+          mbar_wait(B.q_free, (G0 + t - 1) & 1);              // the scores of tile t - 1 have been issued and retired
+          load_q(item, t);
+        }
+        const int next = item + gridDim.x;
+        if (next < n_items) {
+          // the last score MMA of this item has retired: Q and K are free for the next item ...
+          mbar_wait(B.q_free, (G0 + tiles - 1) & 1);
+          load_q(next, 0);
+          load_k(next);
+          // ... and V once the last P V has.  (Its own once-per-item barrier: this thread does not follow the O-full
+          // barriers tile by tile, and a parity wait that skips completions aliases.)
+          mbar_wait(B.v_free, (G0 / tiles) & 1);
+          load_v(next);
+        }
       }
-      AT_DUMP("tma");
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
@@ -284,7 +304,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       };
       auto issue_pv_tail = [&](uint32_t o_col) {
-        const uint32_t pt128 = at_lo(sbase + q_off, 16), pt64 = at_lo(sbase + q_off + NP128 * 2048, 16);
+        const uint32_t pt128 = at_lo(sbase + pt_off, 16), pt64 = at_lo(sbase + pt_off + NP128 * 2048, 16);
 #pragma unroll 4
         for (int j = 0; j < 4 * NP128; ++j)
           at_mma(tmem + o_col, pt128 + (j >> 2) * (2048 >> 4) + ((j & 3) << 1), AT_HI_SW128, v_lo + j * (16 * 64 >> 4), AT_HI_SW64,
@@ -295,67 +315,62 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                  idesc_o, j != 0);
         }
       };
-      AT_T(10);
-      mbar_wait(B.kv_full, 0);
-      AT_T(11);
-      mbar_wait(B.q_full, 0);
-      AT_T(12);
-      tc_fence_after();
-      issue_qk(0, idesc_x);
-      tc_commit(B.sx_full);
-      if (KB > 0) {
-        if (kv_box_rows < KEYS) mbar_wait(B.k1_full, 0);      // the K rows past the first box
+      int G0 = 0, Y0 = 0, itn = 0;                            // global tile index / Y-half index of the item's tile 0
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, G0 += tiles, Y0 += HPT, ++itn) {
+        const uint32_t itp = itn & 1;
+        mbar_wait(B.kv_full, itp);
+        mbar_wait(B.q_full, G0 & 1);
         tc_fence_after();
-        issue_qk(KA, idesc_y);
-        tc_commit(B.sy_full);
-      }
-      tc_commit(B.q_free);
-      for (int t = 0; t < tiles; ++t) {
-        const int ob = t % OB;
-        const uint32_t o_col = AT_O_COL + ob * D;
-        if (t >= OB) mbar_wait(B.o_free + 8 * ob, ((t / OB) - 1) & 1);    // O(t - OB) has been read out
-        if (t == 0) mbar_wait(B.v_full, 0);
-        AT_T(13);
-        mbar_wait(B.px_full, t & 1);                          // P.X(t) in shared memory, S.X(t) consumed
-        AT_T(14);
-        tc_fence_after();
-        if (tail_mode && t == tiles - 1) {                    // the whole transposed P arrives with one barrier
-          issue_pv_tail(o_col);
-          tc_commit(B.o_full + 8 * ob);
-          break;
-        }
-        const bool next_tail = tail_mode && t + 2 == tiles;
-        issue_pv(0, KA / 16, o_col);
-        AT_T(17);
-        if (KB == 0) tc_commit(B.o_full + 8 * ob);
-        if (t + 1 < tiles) {
-          mbar_wait(B.q_full, (t + 1) & 1);
-          tc_fence_after();
-          if (next_tail) {
-            if (kv_box_rows < KEYS) mbar_wait(B.k1_full, 0);
-            issue_st();
-          } else {
-            issue_qk(0, idesc_x);
-          }
-          tc_commit(B.sx_full);
-          if (KB == 0) tc_commit(B.q_free);
-        }
+        issue_qk(0, idesc_x);                                 // (the S.X columns were handed back with px_full of the previous tile)
+        tc_commit(B.sx_full);
         if (KB > 0) {
-          AT_T(15);
-          mbar_wait(B.py_full, t & 1);
-          AT_T(16);
+          if (kv_box_rows < KEYS) mbar_wait(B.k1_full, itp);  // the K rows past the first box
           tc_fence_after();
-          if (t + 1 < tiles && !next_tail) {                    // the softmax warps wait on these scores next
-            issue_qk(KA, idesc_y);
-            tc_commit(B.sy_full);
-            tc_commit(B.q_free);
-          }
-          issue_pv(KA / 16, KEYS / 16, o_col);
-          tc_commit(B.o_full + 8 * ob);
+          issue_qk(KA, idesc_y);
+          tc_commit(B.sy_full);
         }
+        tc_commit(B.q_free);
+        for (int t = 0; t < tiles; ++t) {
+          const int G = G0 + t, ob = G % OB;
+          const uint32_t o_col = AT_O_COL + ob * D;
+          if (G >= OB) mbar_wait(B.o_free + 8 * ob, ((G / OB) - 1) & 1);    // O(G - OB) has been read out
+          if (t == 0) mbar_wait(B.v_full, itp);
+          mbar_wait(B.px_full, G & 1);                        // P.X(t) in shared memory, S.X(t) consumed
+          tc_fence_after();
+          if (tail_mode && t == tiles - 1) {                  // the whole transposed P arrives with one barrier
+            issue_pv_tail(o_col);
+            tc_commit(B.o_full + 8 * ob);
+            break;
+          }
+          const bool next_tail = tail_mode && t + 2 == tiles;
+          issue_pv(0, KA / 16, o_col);
+          if (KB == 0) tc_commit(B.o_full + 8 * ob);
+          if (t + 1 < tiles) {
+            mbar_wait(B.q_full, (G + 1) & 1);
+            tc_fence_after();
+            if (next_tail) {
+              if (kv_box_rows < KEYS) mbar_wait(B.k1_full, itp);
+              issue_st();
+            } else {
+              issue_qk(0, idesc_x);
+            }
+            tc_commit(B.sx_full);
+            if (KB == 0 || next_tail) tc_commit(B.q_free);    // (the transposed tail reads its Q rows in one go)
+          }
+          if (KB > 0) {
+            mbar_wait(B.py_full, (Y0 + t) & 1);
+            tc_fence_after();
+            if (t + 1 < tiles && !next_tail) {                // the softmax warps wait on these scores next
+              issue_qk(KA, idesc_y);
+              tc_commit(B.sy_full);
+              tc_commit(B.q_free);
+            }
+            issue_pv(KA / 16, KEYS / 16, o_col);
+            tc_commit(B.o_full + 8 * ob);
+          }
+        }
+        tc_commit(B.v_free);                                  // every MMA of this item has retired: V may be replaced
       }
-      AT_T(19);
-      AT_DUMP("mma");
     }
     __syncwarp();
   } else {
@@ -363,6 +378,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // Eight warps: TMEM lane quadrant = warp % 4 (a warp only reaches its own 32 lanes), so two warps share every
     // query row; warp group g = 0/1 takes the first / second part of each key half and of the O columns.  The
     // two partial maxima and sums of a row meet in shared memory across a 64-thread named barrier.
+    int b = 0, head = 0, G0 = 0, Y0 = 0;                      // current item: image, head, global index of its tile 0 / Y half 0
     const int quad = warp & 3;
     const int g = (warp - 2) >> 2;
     const int r = quad * 32 + lane;                           // row inside the tile = TMEM lane
@@ -393,8 +409,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     auto pass1 = [&](int key0, int nkeys, float m) {          // row maximum of this group's keys
       float mx[4] = {m, m, m, m};
 #pragma unroll 1
-      for (int k = 0; k < nkeys; k += 32) {                   // the partner warp on this scheduler hides the latency
-        const int n = nkeys - k < 32 ? nkeys - k : 32, kk = key0 + k;
+      for (int k = 0; k < nkeys; k += 32) {                   // one chunk per TMEM round trip: two in flight were measured
+        const int n = nkeys - k < 32 ? nkeys - k : 32, kk = key0 + k;   // at 1.09 vs 0.79 ms (spills at the 168-register cap)
         float v0[32];
         at_ld_chunk(t_lane + kk, n, v0);
         tmem_ld_wait();
@@ -429,8 +445,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
     auto epilogue = [&](int t, bool tail) {                   // this group's half of O(t) / row sum -> bf16 -> global
       constexpr int HALF = D / 2;
-      const int ob = t % OB;
-      const float *xs = xch + 512 + (t & 1) * 256;
+      const int G = G0 + t, ob = G % OB;
+      const float *xs = xch + 512 + (G & 1) * 256;
       float den = xs[r] + xs[128 + r];
       if (tail) {                                             // transposed tail tile: eight per-warp partial sums per row
         den = 0.0f;
@@ -442,9 +458,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       bf16 *orow = out + ((long long)b * S + row) * C + head * D + g * HALF;
       const bool warp_live = t * AT_MT + quad * 32 < S;
       if (warp_live) {
-        mbar_wait(B.o_full + 8 * ob, (t / OB) & 1);
+        mbar_wait(B.o_full + 8 * ob, (G / OB) & 1);
         tc_fence_after();
-        AT_T(40);
       }
       auto store8 = [&](const float *w, int c) {              // 8 columns -> 16 bytes
         const uint32_t p0 = pack_bf16x2(w[0] * inv, w[1] * inv), p1 = pack_bf16x2(w[2] * inv, w[3] * inv);
@@ -487,12 +502,10 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     auto tail_tile = [&](int t) {
       // All 8 query columns are processed without branches (columns past the live rows only produce garbage in P
       // rows and sums nobody reads), so the eight shuffle chains interleave.
-      float *tmax = xch + (t & 1) * 256;                      // [8 warps][8]
-      float *psum = xch + 512 + (t & 1) * 256;                // [8 warps][8]: partial row sums, added up by the epilogue
-      AT_T(49);
-      mbar_wait(B.sx_full, t & 1);
+      float *tmax = xch + ((G0 + t) & 1) * 256;               // [8 warps][8]
+      float *psum = xch + 512 + ((G0 + t) & 1) * 256;         // [8 warps][8]: partial row sums, added up by the epilogue
+      mbar_wait(B.sx_full, (G0 + t) & 1);
       tc_fence_after();
-      AT_T(50);
       float v[2][8];
       bool valid[2];
       uint32_t pbase[2], pch[2];                              // P row 0 address of this thread's key, its 16-byte chunk
@@ -505,7 +518,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (kt * 128 < KEYS) tmem_ld8(t_lane + 16 * kt, v[i]);
         sw128[i] = key < 64 * NP128;
         const int k2 = key - 64 * NP128;
-        pbase[i] = sw128[i] ? sbase + q_off + (key >> 6) * 2048 + (key & 7) * 2 : sbase + q_off + NP128 * 2048 + (k2 >> 5) * 1024 + (k2 & 7) * 2;
+        pbase[i] = sw128[i] ? sbase + pt_off + (key >> 6) * 2048 + (key & 7) * 2 : sbase + pt_off + NP128 * 2048 + (k2 >> 5) * 1024 + (k2 & 7) * 2;
         pch[i] = sw128[i] ? (key & 63) >> 3 : (k2 & 31) >> 3;
       }
       tmem_ld_wait();
@@ -522,11 +535,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int qi = 1; qi < 8; ++qi) mine = lane == qi ? mq[qi] : mine;
         tmax[(warp - 2) * 8 + lane] = mine;
       }
-      AT_T(51);
       asm volatile("bar.sync 9, 256;" ::: "memory");          // all eight softmax warps
-      AT_T(52);
       epilogue(t - 1, false);
-      AT_T(53);
       float mrow = -INFINITY;                                 // lane qi: maximum of query qi over all keys
       if (lane < 8) {
 #pragma unroll
@@ -559,11 +569,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int qi = 1; qi < 8; ++qi) mine = lane == qi ? ps[qi] : mine;
         psum[(warp - 2) * 8 + lane] = mine;
       }
-      AT_T(54);
       publish(B.px_full);
-      AT_T(55);
     };
 
+#pragma unroll 1
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, G0 += tiles, Y0 += HPT) {
+    b = item_image(item);
+    head = item % h;
 #pragma unroll 1
     for (int t = 0; t <= tiles; ++t) {                        // iteration t: scores of tile t, output of tile t - 1
       if (tail_mode && t == tiles - 1) {
@@ -571,17 +583,14 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         continue;
       }
       const bool live = t < tiles && t * AT_MT + quad * 32 < S;   // warps whose rows are all past the sequence idle
-      float *xm = xch + (t & 1) * 256, *xs = xch + 512 + (t & 1) * 256;
+      float *xm = xch + ((G0 + t) & 1) * 256, *xs = xch + 512 + ((G0 + t) & 1) * 256;
       float m = -INFINITY;
       if (t < tiles) {
 #pragma unroll 1
         for (int hf = 0; hf < (KB > 0 ? 2 : 1); ++hf) {       // X then Y: the Y scores land while X is scanned
-          AT_T(20 + hf);
-          mbar_wait(hf ? B.sy_full : B.sx_full, t & 1);
+          mbar_wait(hf ? B.sy_full : B.sx_full, (hf ? Y0 + t : G0 + t) & 1);
           tc_fence_after();
-          AT_T(22 + hf);
           if (live) m = pass1(hf ? yk0 : xk0, hf ? yn : xn, m);
-          AT_T(24 + hf);
         }
         xm[g * 128 + r] = m;
       }
@@ -596,9 +605,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       } else {
         pair_sync();
       }
-      AT_T(26);
       if (t > 0) epilogue(t - 1, tail_mode && t == tiles);
-      AT_T(27);
       if (t < tiles) {
         m = fmaxf(m, xm[(g ^ 1) * 128 + r]);
         const float nm = -m * scale_log2;
@@ -611,13 +618,12 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
           if (live) sum += pass2(hf ? yk0 : xk0, hf ? yn : xn, nm);
           publish(hf ? B.py_full : B.px_full);
-          AT_T(28 + hf);
         }
         xs[g * 128 + r] = sum;
       }
     }
+    }
     if (stage_ok && lane == 0) bulk_wait_read<0>();          // shared memory outlives the last output store
-    if (warp == 4 || warp == 8) AT_DUMP("smx");
   }
 
   tc_fence_before();
@@ -635,7 +641,9 @@ static int launch_attn_tc5(const void *qkv, void *out, int B, int S, int h, cuda
   const int nbox = (KEYS + 255) / 256;
   if (KEYS > 288 || KEYS % nbox != 0 || (KEYS / nbox) % 8 != 0) return -1;
   const int NA = D / 32, NKA = (KEYS + 31) / 32;
-  const size_t smem = (size_t)NA * AT_MT * 64 + 2 * (size_t)NA * KEYS * 64 + (size_t)NKA * AT_MT * 64 + 128 + 4096 + 1024;
+  const int NP128 = KEYS / 64, NP64 = (KEYS % 64 + 31) / 32;
+  const size_t smem = (size_t)NA * AT_MT * 64 + 2 * (size_t)NA * KEYS * 64 + (size_t)NKA * AT_MT * 64 +
+                      (size_t)NP128 * 2048 + (size_t)NP64 * 1024 + 128 + 4096 + 1024;
   if (smem > 227 * 1024) return -1;
   CUtensorMap tq, tq32, tk, tkv;          // 64-column boxes are 128B-swizzled, 32-column boxes 64B-swizzled
   if (int rc = make_tensor_map_bf16(qkv, (uint64_t)B * S, 3 * C, 3 * C, AT_MT, 64, &tq)) return rc;
@@ -645,17 +653,17 @@ static int launch_attn_tc5(const void *qkv, void *out, int B, int S, int h, cuda
   CUtensorMap to;                          // [B][S][C] output, 32-row x D/2-column boxes
   if (int rc = make_tensor_map_bf16_3d(out, B, S, C, 32, D / 2, &to)) return rc;
   auto kern = attention_tc5_kernel<D>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device, cheap
+  int dev = 0, sms = 0;
+  SDP_CUDA(cudaGetDevice(&dev));
+  SDP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
-  // the last query tile is transposed when it holds at most 8 rows (SDP_ATTN_TAIL=0: treat it like the others)
-  static const bool tail_on = [] { const char *e = getenv("SDP_ATTN_TAIL"); return !(e && e[0] == '0'); }();
+  // the last query tile is transposed when it holds at most 8 rows
   const int tiles = (S + AT_MT - 1) / AT_MT;
-  const int tail_mode = tail_on && tiles >= 2 && S - (tiles - 1) * AT_MT <= 8 ? 1 : 0;
-  kern<<<B * h, AT_THREADS, smem, st>>>(tq, tq32, tk, tkv, to, (bf16 *)out, S, h, KEYS, KEYS / nbox, scale_log2, tail_mode);
+  const int tail_mode = tiles >= 2 && S - (tiles - 1) * AT_MT <= 8 ? 1 : 0;
+  const int n_items = B * h;               // persistent: one CTA per SM (512 TMEM columns, ~210 KB of shared memory)
+  kern<<<n_items < sms ? n_items : sms, AT_THREADS, smem, st>>>(tq, tq32, tk, tkv, to, (bf16 *)out, S, h, KEYS, KEYS / nbox,
+                                                                scale_log2, tail_mode, n_items);
   SDP_LAUNCH_OK();
   return 0;
 }
