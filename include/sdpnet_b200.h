@@ -212,10 +212,12 @@ int sdp_embed_tokens(void *act, int dtype, const float *pos, int B, int T, int R
 int sdp_activation(const void *x, void *y, int64_t n, int act, int dtype, void *stream);
 
 /* Evaluation metrics right behind the forward, without per-batch host syncs (model_test.py:76-85,
- * training_utilities.py:50-88, 95-107): for logits [B, K] (fp32) and integer labels [B], ADD into acc[4]
+ * training_utilities.py:50-88, 95-107): for logits [B, K] (fp32) and integer labels [B], ADD into acc[5]
  * (device doubles): sum over rows of cross-entropy, sum over all B*K elements of
  * binary_cross_entropy_with_logits against the smoothed one-hot target
- * (one_hot*(1-ls) + ls/K), number of rows whose argmax equals the label, number of rows. */
+ * (one_hot*(1-ls) + ls/K), number of rows whose argmax equals the label, number of rows, and -- acc[4] -- the
+ * number of rows whose label lies outside [0, K) (nn.CrossEntropyLoss raises on those; such rows contribute to
+ * nothing else; label -100, its ignore_index, is skipped silently). */
 int sdp_eval_metrics(const float *logits, int64_t ldl, const int64_t *labels, int B, int K, float label_smoothing,
                      double *acc, void *stream);
 
@@ -236,11 +238,14 @@ typedef struct {
   int32_t height, width;
 } sdp_image_desc;
 
+/* path: 0 = automatic (one fused band kernel whenever the batch's tap tables fit shared memory), 1 = the three-kernel
+ * path with the uint8 intermediate in the workspace (what oversized batches take anyway); same results bit for bit.
+ * Pass the same value to both calls. */
 int64_t sdp_val_preprocess_workspace_bytes(const sdp_image_desc *images, int B, int resize_h, int resize_w,
-                                           int crop_h, int crop_w);
+                                           int crop_h, int crop_w, int path);
 int sdp_val_preprocess(const uint8_t *pixels, int64_t pixels_bytes, const sdp_image_desc *images, int B, int resize_h, int resize_w,
                        int crop_h, int crop_w, const float *mean, const float *std, void *workspace,
-                       int64_t workspace_bytes, void *out, int out_dtype, void *stream);
+                       int64_t workspace_bytes, void *out, int out_dtype, int path, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Whole-model forward (model.py:129-149) sequenced on the device side of the ABI: one call

@@ -102,8 +102,8 @@ SYMBOLS = {
     "sdp_tokens_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_embed_tokens": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_eval_metrics": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
-    "sdp_val_preprocess_workspace_bytes": (c_i64, [C.POINTER(ImageDesc), c_int, c_int, c_int, c_int, c_int]),
-    "sdp_val_preprocess": (c_int, [c_void_p, c_i64, C.POINTER(ImageDesc), c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p, c_i64, c_void_p, c_int, c_void_p]),
+    "sdp_val_preprocess_workspace_bytes": (c_i64, [C.POINTER(ImageDesc), c_int, c_int, c_int, c_int, c_int, c_int]),
+    "sdp_val_preprocess": (c_int, [c_void_p, c_i64, C.POINTER(ImageDesc), c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p, c_i64, c_void_p, c_int, c_int, c_void_p]),
     "sdp_activation": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
     "sdp_forward": (c_int, [C.POINTER(ModelDesc), C.POINTER(Workspace), c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sdp_launch_count": (c_i64, [c_int]),

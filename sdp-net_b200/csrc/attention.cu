@@ -565,11 +565,7 @@ static int launch_attn_mma2(const void *qkv, void *out, int B, int S, int h, cud
                       (tail ? (size_t)std::min(std::min(nw, S_pad / KVB), ATT2_TAILW) * ((D / 8) * 4 * 32 + 4 * 32) * sizeof(float) : 0);
   if (smem > 220 * 1024) return -1;             // does not fit: the dispatcher tries the next kernel
   auto kern = attention_bf16_mma2_kernel<D, TPW, MAXW>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device, cheap
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   kern<<<B * h, 32 * nw, smem, st>>>((const bf16 *)qkv, (bf16 *)out, S, h, scale_log2);
   SDP_LAUNCH_OK();
@@ -656,11 +652,7 @@ static int launch_attn_mma(const void *qkv, const float *qn_w, const float *qn_b
   const size_t smem = (size_t)2 * S_pad * (D + 8) * sizeof(bf16);
   if (smem > 220 * 1024) return -1;             // does not fit: the dispatcher falls back to the CUDA-core kernel
   auto kern = attention_bf16_mma_kernel<D>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device, cheap
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid(B * h, ny);
   kern<<<grid, 32 * tpc, smem, st>>>((const bf16 *)qkv, qn_w, qn_b, kn_w, kn_b, (bf16 *)out, S, h, eps,
@@ -676,11 +668,7 @@ static int launch_attn_simt(const void *qkv, const float *qn_w, const float *qn_
   const size_t smem = ((size_t)S * (d + 1) + (size_t)nw * (d + S)) * sizeof(float);
   SDP_CHECK(smem <= 220 * 1024, "sdp_attention(simt): S=%d d=%d needs %zu B of shared memory", S, d, smem);
   auto kern = attention_simt_kernel<T>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device, cheap
   kern<<<B * h, 32 * nw, smem, st>>>((const T *)qkv, qn_w, qn_b, kn_w, kn_b, (T *)out, S, h, d, eps,
                                      1.0f / sqrtf((float)d));
   SDP_LAUNCH_OK();
@@ -688,14 +676,6 @@ static int launch_attn_simt(const void *qkv, const float *qn_w, const float *qn_
 }
 
 int attention_tc5(const void *qkv, void *out, int B, int S, int h, int d, cudaStream_t st);   // attention_tc.cu
-
-static bool attn_tc5_enabled() {     // SDP_ATTN_TC=0 keeps the mma.sync kernels (A/B comparisons)
-  static const bool on = [] {
-    const char *e = getenv("SDP_ATTN_TC");
-    return !(e && e[0] == '0');
-  }();
-  return on;
-}
 
 }  // namespace sdp
 
@@ -712,7 +692,7 @@ extern "C" int sdp_attention(const void *qkv, const float *qn_w, const float *qn
   if (dtype == SDP_BF16) {
     const bool aligned = (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && ((long long)h * d) % 8 == 0;
     int rc = -1;
-    if (aligned && qn_w == nullptr && attn_tc5_enabled()) {
+    if (aligned && qn_w == nullptr) {
       rc = attention_tc5(qkv, out, B, S, h, d, st);      // tcgen05 path: d in {64, 96, 128}, S <= 288
       if (rc >= 0) return rc;
     }

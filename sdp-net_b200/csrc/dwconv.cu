@@ -354,288 +354,15 @@ static int launch_dw_bf16(const void *act, const float *stats, int parts, const 
   const size_t smem = (size_t)L.total * sizeof(float);
   if (smem > 220 * 1024) return -1;             // caller falls back to the generic kernel
   auto kern = ln_dwconv_bf16_kernel<KS>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  const char *sp = getenv("SDP_DWCONV_SPLIT");
-  const int split = sp ? atoi(sp) : 1;   // measured on B200: every extra CTA per image costs its own statistics pass
-  kern<<<dim3(B, split < 1 ? 1 : split), DWF_THREADS, smem, st>>>((const bf16 *)act, stats, parts, gamma, beta, wdw, bdw, (bf16 *)out, Gh, Gw, C, R, eps,
+  SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device, cheap
+  // one CTA per image: splitting an image's channel slabs over several CTAs was measured slower on B200 (every extra
+  // CTA pays the statistics pass again)
+  kern<<<dim3(B, 1), DWF_THREADS, smem, st>>>((const bf16 *)act, stats, parts, gamma, beta, wdw, bdw, (bf16 *)out, Gh, Gw, C, R, eps,
                                      PW);
   SDP_LAUNCH_OK();
   return 0;
 }
 
-
-// ---------------------------------------------------------------------------------------
-// Tensor-core depthwise conv (bf16, grids up to 16 x 16, k in {3,5,7}).
-//
-// For one channel the k x k 'same' conv of the zero-haloed G x G plane P is a sum over tap rows of small
-// matrix products:   Out[y, xo] = sum_dy  P[y + dy, :] . Toe_dy[:, xo],   Toe_dy[xi, xo] = w[dy][xi - xo]
-// (a banded Toeplitz matrix of the row's taps).  With M = y (<= 16), N = xo (two n8 tiles), K = xi (two k16
-// steps, of which only three (k-step, n-tile) bands are non-zero) that is 3 mma.sync.m16n8k16 per tap row,
-// 21 per channel and image for k = 7, against 12544 scalar FMAs.
-//
-// Same outer structure as the FMA kernel above -- one CTA per image so that every token row is read and
-// written as contiguous bytes, token statistics first, then channel slabs with the next slab streaming in
-// through cp.async -- but a slab is 32 channels held as per-channel bf16 planes (80-byte rows: conflict-free
-// ldmatrix), each of the 16 warps runs the MMAs of two channels, and the Toeplitz B fragments are read from a
-// per-slab table E[ch][dy][i] = (tap(i-16), tap(i-15)) so that a fragment register is one 32-bit load.
-// ---------------------------------------------------------------------------------------
-constexpr int DWT_THREADS = 512;
-constexpr int DWT_CH = 32;                // channels per slab
-constexpr int DWT_PITCH = 40;             // bf16 per plane row: 32 used + 8 pad (80 B)
-constexpr int DWT_EW = 40;                // words per (channel, tap row) in the fragment table
-
-__device__ __forceinline__ void dwt_mma(float *c, const uint32_t *a, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void dwt_ldmatrix_x4(uint32_t addr, uint32_t *r) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-
-template <int KS>
-struct DwtLayout {                         // byte offsets, all multiples of 16
-  static constexpr int ROWS = 16 + KS - 1;
-  static constexpr int PLANE = ROWS * DWT_PITCH;            // bf16 elements per channel plane
-  int stat, off, taps, raw, etab, planes, oplanes, total, opl;
-  __host__ __device__ explicit DwtLayout(int Tn) {
-    opl = (Tn + 7) & ~7;
-    stat = 0;                                               // mean[Tn], rstd[Tn] fp32
-    off = stat + ((2 * Tn * 4 + 15) & ~15);                 // int[Tn]
-    taps = off + ((Tn * 4 + 15) & ~15);                     // [KS*KS + 2][32] fp32 of the NEXT slab: taps, gamma, beta
-    raw = taps + (KS * KS + 2) * DWT_CH * 4;                // [Tn][64 B] raw rows of the NEXT slab
-    etab = raw + Tn * DWT_CH * 2;                           // [32][KS*DWT_EW + 1] uint2 (b0, b1) fragment pairs
-    planes = etab + ((DWT_CH * (KS * DWT_EW + 1) * 8 + 15) & ~15);   // [32][ROWS][PITCH] bf16, zero halo
-    oplanes = planes + DWT_CH * PLANE * 2;                  // [32][opl] bf16
-    total = oplanes + DWT_CH * opl * 2;
-  }
-};
-
-template <int KS>
-__global__ void __launch_bounds__(DWT_THREADS, 1)
-ln_dwconv_tc_kernel(const bf16 *__restrict__ act, const float *__restrict__ stats, int parts,
-                    const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ wdw,
-                    const float *__restrict__ bdw, bf16 *__restrict__ out, int Gh, int Gw, int C, int R, float eps) {
-  constexpr int lo = (KS - 1) / 2;
-  constexpr int PLANE = DwtLayout<KS>::PLANE;
-  constexpr int NW = DWT_THREADS / 32;
-  extern __shared__ __align__(16) uint8_t dwt_smem[];
-  const int Tn = Gh * Gw, S = R + Tn;
-  const DwtLayout<KS> L(Tn);
-  float *s_mean = reinterpret_cast<float *>(dwt_smem + L.stat);
-  float *s_rstd = s_mean + Tn;
-  int *s_off = reinterpret_cast<int *>(dwt_smem + L.off);
-  const float *s_taps = reinterpret_cast<const float *>(dwt_smem + L.taps);
-  uint2 *s_etab = reinterpret_cast<uint2 *>(dwt_smem + L.etab);
-  bf16 *planes = reinterpret_cast<bf16 *>(dwt_smem + L.planes);
-  bf16 *oplanes = reinterpret_cast<bf16 *>(dwt_smem + L.oplanes);
-  const int OPL = L.opl;
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, q = lane & 3;
-  const bf16 *xin = act + ((long long)b * S + R) * C;
-  bf16 *xout = out + (long long)b * S * C;
-  const uint32_t smem_addr = static_cast<uint32_t>(__cvta_generic_to_shared(dwt_smem));
-
-  auto prefetch = [&](int c0) {              // raw token rows (64 B each) + taps (128 B per tap) of one slab
-    const int chunks = min(4, (C - c0) / 8);
-    for (int i = tid; i < Tn * 4; i += DWT_THREADS) {
-      const int t = i >> 2, ch = i & 3;
-      if (ch < chunks) dw_cp_async16(smem_addr + L.raw + t * 64 + ch * 16, xin + (long long)t * C + c0 + ch * 8);
-    }
-    const int wchunks = min(8, (C - c0) / 4);
-    for (int i = tid; i < (KS * KS + 2) * 8; i += DWT_THREADS) {
-      const int tap = i >> 3, ch = i & 7;      // rows KS*KS and KS*KS + 1 carry the slab's gamma and beta
-      const float *src = tap < KS * KS ? wdw + (long long)tap * C : (tap == KS * KS ? gamma : beta);
-      if (ch < wchunks) dw_cp_async16(smem_addr + L.taps + tap * 128 + ch * 16, src + c0 + ch * 4);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  prefetch(0);
-
-  for (int i = tid; i < R * C / 8; i += DWT_THREADS) reinterpret_cast<uint4 *>(xout)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < DWT_CH * PLANE / 2; i += DWT_THREADS) reinterpret_cast<uint32_t *>(planes)[i] = 0u;   // halo stays 0
-  for (int t = tid; t < Tn; t += DWT_THREADS) s_off[t] = (t / Gw + lo) * DWT_PITCH + (t % Gw + lo);
-  constexpr int ESTR = KS * DWT_EW + 1;      // words per channel in the fragment table
-  for (int i = tid; i < DWT_CH * ESTR; i += DWT_THREADS) s_etab[i] = make_uint2(0u, 0u);   // entries away from the taps stay 0
-  // slab-invariant work list of the fragment-table build: (source tap row offset, table slot) per entry
-  constexpr int EENT = DWT_CH * KS * 16;       // 16 live (b0, b1) pairs per (channel, tap row)
-  constexpr int EPT = (EENT + DWT_THREADS - 1) / DWT_THREADS;
-
-  // ---- token statistics: supplied (sum, sumsq) parts, or one shifted pass over the rows ----
-  if (stats != nullptr) {
-    const float *sp = stats + ((long long)b * S + R) * parts * 2;
-    for (int t = tid; t < Tn; t += DWT_THREADS) {
-      float s1 = 0.0f, s2 = 0.0f;
-      for (int p = 0; p < parts; ++p) {
-        const float2 v = __ldg(reinterpret_cast<const float2 *>(sp + ((long long)t * parts + p) * 2));
-        s1 += v.x;
-        s2 += v.y;
-      }
-      const float mean = s1 / (float)C;
-      s_mean[t] = mean;
-      s_rstd[t] = 1.0f / sqrtf(fmaxf(s2 / (float)C - mean * mean, 0.0f) + eps);
-    }
-  } else {
-    const int nv = C >> 3;
-    for (int t0 = warp * 4; t0 < Tn; t0 += NW * 4) {
-      float s1[4], s2[4], sh[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int t = min(t0 + u, Tn - 1);
-        const uint4 *rv = reinterpret_cast<const uint4 *>(xin + (long long)t * C);
-        sh[u] = __bfloat162float(xin[(long long)t * C]);
-        s1[u] = s2[u] = 0.0f;
-        for (int i = lane; i < nv; i += 32) {
-          const uint4 v = __ldg(rv + i);
-          const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float a = __uint_as_float(wd[j] << 16) - sh[u], c2 = __uint_as_float(wd[j] & 0xffff0000u) - sh[u];
-            s1[u] += a + c2;
-            s2[u] = fmaf(a, a, fmaf(c2, c2, s2[u]));
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float a = warp_sum(s1[u]), qq = warp_sum(s2[u]);
-        const float dm = a / (float)C;
-        if (lane == 0 && t0 + u < Tn) {
-          s_mean[t0 + u] = sh[u] + dm;
-          s_rstd[t0 + u] = 1.0f / sqrtf(fmaxf(qq / (float)C - dm * dm, 0.0f) + eps);
-        }
-      }
-    }
-  }
-
-  // per-lane constants of the MMA phase
-  const uint32_t planes_addr = smem_addr + L.planes;
-  const uint32_t a_lane = (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * DWT_PITCH + (lane >> 4) * 8) * 2);
-  const int delta = 2 * q - g + 16;          // fragment-table index of (k = 2q, n = g) for band base 0
-  const int grp = tid >> 7, tl = tid & 127;  // transform / output mapping: 8-channel group, token lane
-
-  for (int c0 = 0; c0 < C; c0 += DWT_CH) {
-    const int nch = min(DWT_CH, C - c0);     // live channels of this slab (multiple of 8)
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                         // raw rows + taps of this slab (and the statistics) are visible;
-                                             // everybody is done with the previous slab's out planes
-    // ---- transform: 8 channels of one token per thread -> bf16 cells of 8 channel planes ----
-    if (grp * 8 < nch) {
-      float gm[8], bt[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { gm[j] = s_taps[KS * KS * DWT_CH + grp * 8 + j]; bt[j] = s_taps[(KS * KS + 1) * DWT_CH + grp * 8 + j]; }
-      for (int t = tl; t < Tn; t += 128) {
-        const uint4 u = *reinterpret_cast<const uint4 *>(dwt_smem + L.raw + t * 64 + grp * 16);
-        const float m = s_mean[t], r = s_rstd[t];
-        bf16 *cell = planes + (grp * 8) * PLANE + s_off[t];
-        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float a = (__uint_as_float(w4[j] << 16) - m) * r, c2 = (__uint_as_float(w4[j] & 0xffff0000u) - m) * r;
-          cell[(2 * j) * PLANE] = __float2bfloat16_rn(fmaf(a, gm[2 * j], bt[2 * j]));
-          cell[(2 * j + 1) * PLANE] = __float2bfloat16_rn(fmaf(c2, gm[2 * j + 1], bt[2 * j + 1]));
-        }
-      }
-    }
-    // ---- fragment table of the slab: E[ch][dy][i] = (b0, b1) = ((tap(i-16), tap(i-15)), (tap(i-8), tap(i-7))),
-    //      tap(j) = 0 outside [0, KS); only the 16 entries i in [7, 22] ever change.  Lanes run over channels:
-    //      conflict-free reads of the tap rows ----
-#pragma unroll
-    for (int k2 = 0; k2 < EPT; ++k2) {
-      const int i = tid + k2 * DWT_THREADS;
-      if (i < EENT) {
-        const int ch = i & (DWT_CH - 1), rest = i >> 5;
-        const int dy = rest >> 4, slot = (rest & 15) + 7;
-        const float *tr = s_taps + dy * KS * DWT_CH + ch;
-        auto tp = [&](int j) { return (j >= 0 && j < KS) ? tr[j * DWT_CH] : 0.0f; };
-        s_etab[ch * ESTR + dy * DWT_EW + slot] =
-            make_uint2(pack_bf16x2(tp(slot - 16), tp(slot - 15)), pack_bf16x2(tp(slot - 8), tp(slot - 7)));
-      }
-    }
-    __syncthreads();                         // planes + table ready; raw rows and taps consumed
-    if (c0 + DWT_CH < C) prefetch(c0 + DWT_CH);
-    // ---- MMA: two channels per warp, 3 MMAs per tap row ----
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int ch = 2 * warp + cc;
-      if (ch >= nch) break;
-      const float bias = bdw ? __ldg(bdw + c0 + ch) : 0.0f;
-      float acc[2][4];
-#pragma unroll
-      for (int n = 0; n < 2; ++n)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[n][j] = bias;
-      const uint32_t a_base = planes_addr + (uint32_t)ch * PLANE * 2 + a_lane;
-      const uint2 *et = s_etab + ch * ESTR + delta;
-#pragma unroll
-      for (int dy = 0; dy < KS; ++dy) {
-        uint32_t a0[4], a1[4];
-        dwt_ldmatrix_x4(a_base + dy * DWT_PITCH * 2, a0);            // plane cols 0..15
-        dwt_ldmatrix_x4(a_base + dy * DWT_PITCH * 2 + 32, a1);       // plane cols 16..31
-        const uint2 *e = et + dy * DWT_EW;
-        // bands (k-step, n-tile) = (0,0) base 0, (0,1) base -8, (1,1) base +8; one 64-bit load per (b0, b1)
-        const uint2 f0 = e[0], f1 = e[-8], f2 = e[8];
-        dwt_mma(acc[0], a0, f0.x, f0.y);
-        dwt_mma(acc[1], a0, f1.x, f1.y);
-        dwt_mma(acc[1], a1, f2.x, f2.y);
-      }
-      // C fragment: (y = g, xo = 8n + 2q, +1) and (y = g + 8, same xo) -> this channel's out plane
-      bf16 *op = oplanes + ch * OPL;
-#pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        const int xo = 8 * n + 2 * q;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int y = g + 8 * hh;
-          if (y < Gh) {
-            if (xo < Gw) op[y * Gw + xo] = __float2bfloat16_rn(acc[n][2 * hh]);
-            if (xo + 1 < Gw) op[y * Gw + xo + 1] = __float2bfloat16_rn(acc[n][2 * hh + 1]);
-          }
-        }
-      }
-    }
-    __syncthreads();                         // out planes complete; planes free for the next transform
-    // ---- output: 8 channels of one token per thread, one 128-bit store ----
-    if (grp * 8 < nch) {
-      for (int t = tl; t < Tn; t += 128) {
-        uint32_t o4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t lo16 = *reinterpret_cast<const uint16_t *>(oplanes + (grp * 8 + 2 * j) * OPL + t);
-          const uint32_t hi16 = *reinterpret_cast<const uint16_t *>(oplanes + (grp * 8 + 2 * j + 1) * OPL + t);
-          o4[j] = lo16 | (hi16 << 16);
-        }
-        *reinterpret_cast<uint4 *>(xout + (long long)(R + t) * C + c0 + grp * 8) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-      }
-    }
-  }
-}
-
-template <int KS>
-static int launch_dw_tc(const void *act, const float *stats, int parts, const float *gamma, const float *beta,
-                        const float *wdw, const float *bdw, void *out, int B, int Gh, int Gw, int C, int R, float eps,
-                        cudaStream_t st) {
-  const DwtLayout<KS> L(Gh * Gw);
-  const size_t smem = (size_t)L.total;
-  auto kern = ln_dwconv_tc_kernel<KS>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  kern<<<B, DWT_THREADS, smem, st>>>((const bf16 *)act, stats, parts, gamma, beta, wdw, bdw, (bf16 *)out, Gh, Gw, C, R,
-                                     eps);
-  SDP_LAUNCH_OK();
-  return 0;
-}
 
 template <typename T, int KS>
 static int launch_dw(const void *act, const float *gamma, const float *beta, const float *wdw, const float *bdw,
@@ -647,11 +374,7 @@ static int launch_dw(const void *act, const float *gamma, const float *beta, con
   SDP_CHECK(smem <= 220 * 1024, "sdp_ln_dwconv: grid %dx%d with k=%d needs %zu B of shared memory", Gh, Gw, k,
             smem);
   auto kern = ln_dwconv_kernel<T, KS, CH>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device, cheap
   kern<<<B, DW_THREADS, smem, st>>>((const T *)act, gamma, beta, wdw, bdw, (T *)out, Gh, Gw, C, k, R, eps, PW);
   SDP_LAUNCH_OK();
   return 0;
@@ -672,13 +395,8 @@ static int dispatch_dw(const void *act, const float *gamma, const float *beta, c
 
 using namespace sdp;
 
-// 1 if this shape runs on the tensor-core kernel (which also accepts producer-supplied statistics)
-static int dw_tc_ok(int Gh, int Gw, int C, int k, int dtype) {
-  return dtype == SDP_BF16 && (k == 3 || k == 5 || k == 7) && Gh <= 16 && Gw <= 16 && C % 8 == 0 ? 1 : 0;
-}
-
-// The tensor-core kernel computes the token statistics itself when none are supplied, so nobody needs to run
-// sdp_row_stats for it; kept in the ABI for callers that want to know whether supplied statistics are used.
+// Every kernel here computes the token statistics itself when none are supplied, so nobody needs to run
+// sdp_row_stats for it; kept in the ABI for callers that want to know whether supplied statistics are required.
 extern "C" int sdp_ln_dwconv_wants_stats(int Gh, int Gw, int C, int k, int R, int dtype) {
   (void)Gh; (void)Gw; (void)C; (void)k; (void)R; (void)dtype;
   return 0;
@@ -704,11 +422,6 @@ extern "C" int sdp_ln_dwconv_stats(const void *act, const float *stats, int part
                       (reinterpret_cast<uintptr_t>(out) & 3) == 0 && (reinterpret_cast<uintptr_t>(wdw) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(gamma) & 7) == 0 && (reinterpret_cast<uintptr_t>(beta) & 7) == 0 &&
                       (bdw == nullptr || (reinterpret_cast<uintptr_t>(bdw) & 7) == 0);
-    const bool tc = fast && dw_tc_ok(Gh, Gw, C, k, dtype) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                    getenv("SDP_DWCONV_TC") != nullptr;   // experimental: correct, not yet faster than the FMA kernel
-    if (tc && k == 7) return launch_dw_tc<7>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
-    if (tc && k == 5) return launch_dw_tc<5>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
-    if (tc && k == 3) return launch_dw_tc<3>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
     int rc = -1;
     if (fast && k == 7) rc = launch_dw_bf16<7>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);
     if (fast && k == 5) rc = launch_dw_bf16<5>(act, stats, parts, gamma, beta, wdw, bdw, out, B, Gh, Gw, C, R, eps, st);

@@ -299,13 +299,10 @@ ln_dwconv_slab_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_con
   if (tid == 0) bulk_wait_read<0>();       // shared memory outlives the last store's read
 }
 
-static int num_sms_ds() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
+static int num_sms_ds() {                 // per call: a process may drive several devices
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   return n;
 }
 

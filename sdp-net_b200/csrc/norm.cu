@@ -157,12 +157,9 @@ static int launch_ln_rows(const void *x, long long ldx, const float *w, const fl
   const T *xp = reinterpret_cast<const T *>(x);
   T *op = reinterpret_cast<T *>(out);
   const int wpb = 8;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  int dev = 0, sms = 0;                   // per call: a process may drive several devices
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int full = (M + wpb - 1) / wpb;
   const dim3 grid(full), block(32 * wpb);
   auto persistent_grid = [&](const void *kern) {         // one resident wave of the vector kernel
@@ -177,7 +174,7 @@ static int launch_ln_rows(const void *x, long long ldx, const float *w, const fl
   const int need = vec ? (C / EPV + 31) / 32 : 99;
 #define LN_CASE(V)                                                                             \
   if (need <= V) {                                                                             \
-    static const dim3 pg = persistent_grid(reinterpret_cast<const void *>(&ln_rows_vec_kernel<T, V>));   \
+    const dim3 pg = persistent_grid(reinterpret_cast<const void *>(&ln_rows_vec_kernel<T, V>));   \
     ln_rows_vec_kernel<T, V><<<full < (int)pg.x ? dim3(full) : pg, block, 0, st>>>(xp, ldx, w, b, op, ldo, M, C, eps); \
     SDP_LAUNCH_OK();                                                                           \
     return 0;                                                                                  \
@@ -385,7 +382,14 @@ eval_metrics_kernel(const float *__restrict__ logits, long long ldl, const long 
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
   const float *x = logits + (long long)row * ldl;
-  const int label = (int)labels[row];
+  const long long label64 = labels[row];
+  // nn.CrossEntropyLoss (model_test.py:66,80) ignores its ignore_index (-100) and raises on any other label outside
+  // [0, K): the former rows contribute nothing, the latter are counted in acc[4] for the host side to raise on
+  if (label64 < 0 || label64 >= K) {
+    if (lane == 0 && label64 != -100) atomicAdd(acc + 4, 1.0);
+    return;
+  }
+  const int label = (int)label64;
   float mx = -INFINITY;
   int arg = K;
   for (int c = lane; c < K; c += 32) {

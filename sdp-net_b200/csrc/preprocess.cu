@@ -372,7 +372,7 @@ static void prep_fused_geometry(const sdp_image_desc *images, int B, int rh, int
   }
 }
 
-static int prep_plan(const sdp_image_desc *images, int B, int rh, int rw, int ch, int cw, PrepPlan *p) {
+static int prep_plan(const sdp_image_desc *images, int B, int rh, int rw, int ch, int cw, int path, PrepPlan *p) {
   SDP_CHECK(images && B > 0 && rh > 0 && rw > 0 && ch > 0 && cw > 0, "sdp_val_preprocess: bad arguments");
   SDP_CHECK(ch <= rh && cw <= rw, "sdp_val_preprocess: crop %dx%d larger than the resized image %dx%d (the reference would pad)",
             ch, cw, rh, rw);
@@ -395,10 +395,10 @@ static int prep_plan(const sdp_image_desc *images, int B, int rh, int rw, int ch
     prep_bounds_host(ah, W, p->left + cw - 1, &lo2, &cnt2);
     p->max_seg_bytes = max(p->max_seg_bytes, (lo2 + cnt2 - lo) * 3);
   }
-  // fused path: two CTAs per SM when the band fits 100 KB, else one CTA with up to 200 KB; SDP_PREP_FUSED=0 disables it
-  const char *e = getenv("SDP_PREP_FUSED");
+  // fused path: two CTAs per SM when the band fits 100 KB, else one CTA with up to 200 KB; path == 1 asks for the
+  // three-kernel path (the one batches with oversized tap tables take anyway)
   p->fused.band = 0;
-  if (!(e && e[0] == '0')) {
+  if (path != 1) {
     prep_fused_geometry(images, B, rh, ch, cw, *p, 100 * 1024, &p->fused);
     if (p->fused.band < 8) prep_fused_geometry(images, B, rh, ch, cw, *p, 200 * 1024, &p->fused);
   }
@@ -417,17 +417,17 @@ static int prep_plan(const sdp_image_desc *images, int B, int rh, int rw, int ch
 using namespace sdp;
 
 extern "C" int64_t sdp_val_preprocess_workspace_bytes(const sdp_image_desc *images, int B, int resize_h, int resize_w,
-                                                      int crop_h, int crop_w) {
+                                                      int crop_h, int crop_w, int path) {
   PrepPlan p;
-  if (prep_plan(images, B, resize_h, resize_w, crop_h, crop_w, &p) != 0) return -1;
+  if (prep_plan(images, B, resize_h, resize_w, crop_h, crop_w, path, &p) != 0) return -1;
   return (int64_t)p.total;
 }
 
 extern "C" int sdp_val_preprocess(const uint8_t *pixels, int64_t pixels_bytes, const sdp_image_desc *images, int B, int resize_h, int resize_w,
                                   int crop_h, int crop_w, const float *mean, const float *std_, void *workspace,
-                                  int64_t workspace_bytes, void *out, int out_dtype, void *stream) {
+                                  int64_t workspace_bytes, void *out, int out_dtype, int path, void *stream) {
   PrepPlan p;
-  if (int rc = prep_plan(images, B, resize_h, resize_w, crop_h, crop_w, &p)) return rc;
+  if (int rc = prep_plan(images, B, resize_h, resize_w, crop_h, crop_w, path, &p)) return rc;
   SDP_CHECK(pixels && mean && std_ && workspace && out, "sdp_val_preprocess: null pointer");
   SDP_CHECK(out_dtype == SDP_F32 || out_dtype == SDP_BF16, "sdp_val_preprocess: out_dtype %d", out_dtype);
   SDP_CHECK(workspace_bytes >= (int64_t)p.total, "sdp_val_preprocess: workspace of %lld bytes, %lld needed",
@@ -451,21 +451,16 @@ extern "C" int sdp_val_preprocess(const uint8_t *pixels, int64_t pixels_bytes, c
                                                                              mean[2], std_[0], std_[1], std_[2]);
   SDP_LAUNCH_OK();
   if (p.fused.band > 0) {
-    static int configured_f32 = 0, configured_bf16 = 0;
     const dim3 grid((crop_h + p.fused.band - 1) / p.fused.band, B);
     if (out_dtype == SDP_F32) {
-      if (p.fused.total > 48 * 1024 && !configured_f32) {
+      if (p.fused.total > 48 * 1024)      // per device, cheap
         SDP_CUDA(cudaFuncSetAttribute(prep_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured_f32 = 1;
-      }
       prep_fused_kernel<float><<<grid, PREP_THREADS, p.fused.total, st>>>(pixels, pixels_bytes, d_img, d_coef, d_lut,
                                                                           reinterpret_cast<float *>(out), crop_h, crop_w, p.kmax,
                                                                           p.fused);
     } else {
-      if (p.fused.total > 48 * 1024 && !configured_bf16) {
+      if (p.fused.total > 48 * 1024)
         SDP_CUDA(cudaFuncSetAttribute(prep_fused_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured_bf16 = 1;
-      }
       prep_fused_kernel<bf16><<<grid, PREP_THREADS, p.fused.total, st>>>(pixels, pixels_bytes, d_img, d_coef, d_lut,
                                                                          reinterpret_cast<bf16 *>(out), crop_h, crop_w, p.kmax,
                                                                          p.fused);
@@ -477,11 +472,8 @@ extern "C" int sdp_val_preprocess(const uint8_t *pixels, int64_t pixels_bytes, c
   const int seg_smem = p.max_seg_bytes + 16;
   SDP_CHECK(seg_smem <= 200 * 1024, "sdp_val_preprocess: a source row segment of %d bytes does not fit shared memory",
             p.max_seg_bytes);
-  static int configured = 0;
-  if (seg_smem > 48 * 1024 && !configured) {
+  if (seg_smem > 48 * 1024)
     SDP_CUDA(cudaFuncSetAttribute(prep_horizontal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 1;
-  }
   const int row_ctas = min(p.temp_rows, max(1, (148 * 8 + B - 1) / B));   // >= 8 CTAs per SM over the batch
   prep_horizontal_kernel<<<dim3(row_ctas, B), PREP_THREADS, seg_smem, st>>>(pixels, d_img, d_coef, d_temp, crop_h, crop_w,
                                                                             p.kmax, p.temp_rows);

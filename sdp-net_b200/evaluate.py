@@ -12,7 +12,7 @@ from . import ops
 
 class EvalMeter:
     def __init__(self, device="cuda", label_smoothing: float = 0.0):
-        self.acc = torch.zeros(4, dtype=torch.float64, device=device)   # ce_sum, bce_sum, correct, rows
+        self.acc = torch.zeros(5, dtype=torch.float64, device=device)   # ce_sum, bce_sum, correct, rows, bad labels
         self.label_smoothing = float(label_smoothing)
         self.classes = None
 
@@ -23,15 +23,21 @@ class EvalMeter:
     def reset(self) -> None:
         self.acc.zero_()
 
-    def synchronize(self, group=None) -> None:
+    def synchronize(self, group=None) -> torch.Tensor:
+        """Global sums over the ranks.  The local accumulator is left untouched (a clone is reduced), so `result()`
+        can be read as often as wanted between `update()`s -- the running readout of model_test.py:84."""
+        total = self.acc.clone()
         if dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.acc, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        return total
 
     def result(self, group=None) -> dict:
         """One host sync: per-sample mean CE, per-element mean BCE (the reduction both reference losses use
-        within a batch, here over the whole evaluation), top-1 accuracy."""
-        self.synchronize(group)
-        ce, bce, correct, rows = (float(v) for v in self.acc.cpu())
+        within a batch, here over the whole evaluation), top-1 accuracy.  Raises if any label was outside
+        [0, classes) (what nn.CrossEntropyLoss does upstream; its ignore_index -100 is skipped)."""
+        ce, bce, correct, rows, bad = (float(v) for v in self.synchronize(group).cpu())
+        if bad > 0:
+            raise ValueError(f"{int(bad)} label(s) outside [0, {self.classes}) reached EvalMeter.update")
         if rows == 0:
             return {"cross_entropy": 0.0, "bce_with_logits": 0.0, "accuracy": 0.0, "samples": 0}
         return {"cross_entropy": ce / rows, "bce_with_logits": bce / (rows * (self.classes or 1)),

@@ -43,12 +43,19 @@ class _KernelModule(nn.Module):
 
     def _packed(self, build):
         key = (self.precision, tuple((p.data_ptr(), p._version) for p in self.parameters()),
-               tuple(b.data_ptr() for b in self.buffers()))
+               tuple((b.data_ptr(), b._version) for b in self.buffers()))
         cache = self.__dict__.get("_pack_cache")
         if cache is None or cache[0] != key:
             cache = (key, build())
             self.__dict__["_pack_cache"] = cache
         return cache[1]
+
+    def repack(self):
+        """Drop the packed-weight cache (needed after writes the version counters do not see, e.g. through `.data`)."""
+        for m in self.modules():
+            if isinstance(m, _KernelModule):
+                m.__dict__.pop("_pack_cache", None)
+        return self
 
     def _device(self):
         try:

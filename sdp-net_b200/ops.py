@@ -252,28 +252,29 @@ def embed_tokens(act: torch.Tensor, pos: torch.Tensor, R: int, act_name="none") 
 
 
 def eval_metrics(logits: torch.Tensor, labels: torch.Tensor, acc: torch.Tensor, label_smoothing: float = 0.0):
-    """acc [4] float64 (device) += (sum CE, sum BCE-with-logits vs smoothed one-hot, #correct, #rows)."""
+    """acc [5] float64 (device) += (sum CE, sum BCE-with-logits vs smoothed one-hot, #correct, #rows, #rows whose
+    label is outside [0, K) -- those contribute to nothing else)."""
     if logits.dtype != torch.float32 or logits.dim() != 2 or logits.stride(1) != 1:
         raise TypeError("eval_metrics: logits must be float32 [B, K]")
     if labels.dtype != torch.int64 or not labels.is_contiguous() or labels.shape[0] != logits.shape[0]:
         raise TypeError("eval_metrics: labels must be contiguous int64 [B]")
-    if acc.dtype != torch.float64 or acc.numel() != 4 or not acc.is_contiguous():
-        raise TypeError("eval_metrics: acc must be 4 contiguous float64 values")
+    if acc.dtype != torch.float64 or acc.numel() != 5 or not acc.is_contiguous():
+        raise TypeError("eval_metrics: acc must be 5 contiguous float64 values")
     _call("sdp_eval_metrics", logits, _p(logits), logits.stride(0), _p(labels), logits.shape[0], logits.shape[1],
                                      float(label_smoothing), _p(acc))
     return acc
 
 
-def val_preprocess_workspace_bytes(desc, B: int, resize, crop) -> int:
+def val_preprocess_workspace_bytes(desc, B: int, resize, crop, general_path: bool = False) -> int:
     """Bytes of device workspace `val_preprocess` needs for these images (`desc`: _lib.ImageDesc array, host)."""
-    n = int(L.lib().sdp_val_preprocess_workspace_bytes(desc, B, resize[0], resize[1], crop[0], crop[1]))
+    n = int(L.lib().sdp_val_preprocess_workspace_bytes(desc, B, resize[0], resize[1], crop[0], crop[1], int(general_path)))
     if n < 0:
         raise ValueError("sdp_val_preprocess_workspace_bytes: " + L.lib().sdp_last_error().decode("utf-8", "replace"))
     return n
 
 
 def val_preprocess(pixels: torch.Tensor, desc, B: int, resize, crop, mean, std, workspace: torch.Tensor,
-                   out: torch.Tensor) -> torch.Tensor:
+                   out: torch.Tensor, general_path: bool = False) -> torch.Tensor:
     """Packed uint8 RGB images (device) -> out [B, 3, crop_h, crop_w] float32 / bfloat16: the reference's
     val_transforms (hf_dataset_generator.py:27-41), see sdp_val_preprocess in the header."""
     if pixels.dtype != torch.uint8 or not pixels.is_contiguous():
@@ -285,7 +286,7 @@ def val_preprocess(pixels: torch.Tensor, desc, B: int, resize, crop, mean, std, 
     m = (C.c_float * 3)(*mean)
     s = (C.c_float * 3)(*std)
     _call("sdp_val_preprocess", pixels, _p(pixels), pixels.numel(), desc, B, resize[0], resize[1], crop[0], crop[1], m, s, _p(workspace),
-                                       workspace.numel(), _p(out), _dt(out))
+                                       workspace.numel(), _p(out), _dt(out), int(general_path))
     return out
 
 

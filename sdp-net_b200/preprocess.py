@@ -48,6 +48,8 @@ def _as_rgb_u8(img) -> np.ndarray:
 
 
 class ValTransforms:
+    general_path = False     # True: the three-kernel path of sdp_val_preprocess (same bits; what oversized batches take anyway)
+
     def __init__(self, image_size=(320, 320), crop_size=(224, 224), mean=IMAGENET_MEAN, std=IMAGENET_STD,
                  out_dtype: torch.dtype = torch.float32, device="cuda"):
         self.image_size = _pair(image_size, "image_size")
@@ -100,11 +102,12 @@ class ValTransforms:
         if host.is_pinned():
             self._copied = torch.cuda.Event()
             self._copied.record()
-        need = ops.val_preprocess_workspace_bytes(desc, B, self.image_size, self.crop_size)
+        need = ops.val_preprocess_workspace_bytes(desc, B, self.image_size, self.crop_size, self.general_path)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         out = torch.empty(B, 3, *self.crop_size, dtype=self.out_dtype, device=self.device)
-        return ops.val_preprocess(pixels, desc, B, self.image_size, self.crop_size, self.mean, self.std, self._ws, out)
+        return ops.val_preprocess(pixels, desc, B, self.image_size, self.crop_size, self.mean, self.std, self._ws, out,
+                                  self.general_path)
 
 
 def val_transforms(image_size=(320, 320), crop_size=(224, 224), mean=IMAGENET_MEAN, std=IMAGENET_STD,

@@ -41,7 +41,7 @@ def load_fixture(name):
 
 def model_fixture_names():
     return sorted(f[:-4] for f in os.listdir(GOLDEN)
-                  if f.endswith(".npz") and not f.startswith(("layer_", "act_", "preprocess_")))
+                  if f.endswith(".npz") and not f.startswith(("layer_", "act_", "preprocess_", "ckpt_")))
 
 
 def fixture_inputs(meta, embedded_sd=None):

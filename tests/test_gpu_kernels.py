@@ -487,7 +487,7 @@ def dw_ref(act, R, Gh, Gw, gamma, beta, wdw, bdw, eps=1e-6):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("Gh,Gw,C,k,R,bias", [(16, 16, 768, 7, 5, False), (14, 14, 96, 7, 4, True), (8, 8, 32, 5, 1, True),
                                               (4, 6, 40, 3, 2, False), (5, 3, 16, 9, 3, True), (2, 2, 128, 7, 5, False)])
-def test_ln_dwconv(sdp, dtype, Gh, Gw, C, k, R, bias, monkeypatch):
+def test_ln_dwconv(sdp, dtype, Gh, Gw, C, k, R, bias):
     B = 3
     act = (rnd(B, R + Gh * Gw, C, seed=40) * 2 + 0.3).to(dtype)
     gamma, beta = rnd(C, seed=41) * 0.3 + 1, rnd(C, seed=42) * 0.3
@@ -506,13 +506,6 @@ def test_ln_dwconv(sdp, dtype, Gh, Gw, C, k, R, bias, monkeypatch):
         out2 = torch.full_like(act, float("nan"))
         sdp.ops.ln_dwconv(act, gamma, beta, wdw.reshape(C, k * k).t().contiguous(), bdw, out2, Gh, Gw, R, stats=stats)
         assert (out2.float() - ref).abs().max() < tol
-        # the experimental tensor-core (Toeplitz mma.sync) kernel, with and without supplied statistics
-        monkeypatch.setenv("SDP_DWCONV_TC", "1")
-        for st in (None, stats):
-            out3 = torch.full_like(act, float("nan"))
-            sdp.ops.ln_dwconv(act, gamma, beta, wdw.reshape(C, k * k).t().contiguous(), bdw, out3, Gh, Gw, R, stats=st)
-            assert (out3[:, :R] == 0).all()
-            assert (out3.float() - ref).abs().max() < tol
 
 
 @pytest.mark.parametrize("B,Gh,Gw,C,k,R,bias", [(3, 16, 16, 768, 7, 5, False), (5, 16, 16, 64, 7, 4, True), (2, 8, 8, 32, 5, 1, True),
@@ -630,6 +623,48 @@ def test_eval_metrics_kernel(sdp, B, K, ls):
     assert abs(got["cross_entropy"] - ref["cross_entropy"]) < 1e-4
     assert abs(got["bce_with_logits"] - ref["bce_with_logits"]) < 1e-5
     assert abs(got["accuracy"] - ref["accuracy"]) < 1e-9
+    # a running readout does not disturb the accumulator (result() reduces a clone): same numbers twice
+    assert meter.result() == got
+
+
+def test_eval_metrics_rejects_labels_out_of_range(sdp):
+    """nn.CrossEntropyLoss semantics (model_test.py:66,80): ignore_index -100 rows are skipped, any other label
+    outside [0, K) is an error -- never an out-of-bounds read folded into the sums."""
+    B, K = 64, 10
+    logits = rnd(B, K, seed=92)
+    labels = torch.randint(0, K, (B,), generator=_g(93), device="cuda")
+    ign = labels.clone()
+    ign[::4] = -100
+    meter = sdp.evaluate.EvalMeter("cuda")
+    meter.update(logits, ign)
+    got = meter.result()
+    keep = ign >= 0
+    ref = O.eval_metrics(logits[keep].cpu(), labels[keep].cpu(), 0.0)
+    assert got["samples"] == int(keep.sum()) and abs(got["cross_entropy"] - ref["cross_entropy"]) < 1e-4
+    for bad in (-1, K, 10 ** 6):
+        lb = labels.clone()
+        lb[5] = bad
+        meter = sdp.evaluate.EvalMeter("cuda")
+        meter.update(logits, lb)
+        with pytest.raises(ValueError):
+            meter.result()
+
+
+def test_ops_run_on_the_tensors_device_not_the_current_one(sdp):
+    """Every op launches on its tensors' device and that device's current stream (a model on cuda:1 while cuda:0 is
+    current); tensors on different devices are refused.  Needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with torch.cuda.device(0):
+        A = torch.randn(300, 256, device="cuda:1").bfloat16()
+        W = torch.randn(512, 256, device="cuda:1").bfloat16()
+        out = torch.empty(300, 512, device="cuda:1", dtype=torch.bfloat16)
+        sdp.ops.gemm(A, W, out, act="gelu")
+        torch.cuda.synchronize(1)
+        ref = torch.nn.functional.gelu(A.float() @ W.float().t())
+        assert relerr(out, ref) < 1.5e-2
+        with pytest.raises(RuntimeError):
+            sdp.ops.gemm(A, W.to("cuda:0"), out)
 
 
 def test_launch_counter(sdp):

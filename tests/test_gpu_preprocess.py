@@ -52,12 +52,10 @@ def test_ragged_batch_matches_oracle(sdp, path):
 
 
 @pytest.fixture(params=["fused", "general"])
-def path(request, monkeypatch):
-    """Both kernel paths: the fused band kernel (default) and the three-kernel path with a global intermediate."""
-    if request.param == "general":
-        monkeypatch.setenv("SDP_PREP_FUSED", "0")
-    else:
-        monkeypatch.delenv("SDP_PREP_FUSED", raising=False)
+def path(request, monkeypatch, sdp):
+    """Both kernel paths: the fused band kernel (default) and the three-kernel path with a global intermediate (the
+    `path` argument of sdp_val_preprocess, here through ValTransforms.general_path)."""
+    monkeypatch.setattr(sdp.preprocess.ValTransforms, "general_path", request.param == "general")
     return request.param
 
 

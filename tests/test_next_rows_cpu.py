@@ -40,6 +40,34 @@ def test_trainer_snapshot_with_ddp_and_compile_prefixes(sdp):
     assert all(torch.equal(model.state_dict()[k], sd[k]) for k in sd)
 
 
+def test_checkpoints_written_by_the_reference_itself(sdp):
+    """Files produced by the reference's own writers (oracle/make_golden_checkpoints.py: SdPModel.save_model,
+    Trainer._save_checkpoint behind a DDP-style `module.` wrapper, EMA_model.save_ema_model): layouts recognised,
+    prefixes stripped, strict load into the mirrored modules, from_pretrained reads the save_model file."""
+    paths = {k: os.path.join(GOLDEN, f"ckpt_{k}.pt") for k in ("save_model", "trainer", "ema")}
+    cfg_a, sd_a, ex_a = sdp.checkpoint.read_checkpoint(paths["save_model"])
+    cfg_b, sd_b, ex_b = sdp.checkpoint.read_checkpoint(paths["trainer"])
+    cfg_c, sd_c, _ = sdp.checkpoint.read_checkpoint(paths["ema"])
+    assert cfg_a == cfg_b and cfg_c is None and ex_a == {} and ex_b == {"epoch": 7}
+    raw = torch.load(paths["trainer"], map_location="cpu")
+    assert all(k.startswith("module.") for k in raw["model_state_dict"])          # what the reference really wrote
+    assert set(sd_a) == set(sd_b) == set(sd_c) and not any(k.startswith("module.") for k in sd_b)
+    assert all(torch.equal(sd_a[k], sd_b[k]) for k in sd_a)
+    model, ema = sdp.checkpoint.load_model(paths["trainer"], ema_path=paths["ema"], device=None)
+    assert model.config == cfg_a and not model.training
+    assert all(torch.equal(model.state_dict()[k], sd_a[k]) for k in sd_a)
+    k = "blocks.1.conv_blocks.0.conv1d.0.weight"
+    assert not torch.equal(ema.state_dict()[k], model.state_dict()[k])
+    again = sdp.MainModel.from_pretrained(paths["save_model"])
+    assert again.config == cfg_a and all(torch.equal(again.state_dict()[k], sd_a[k]) for k in sd_a)
+    # and the oracle reproduces the reference's forward of those weights (the fixture the GPU test checks against)
+    z = np.load(os.path.join(GOLDEN, "ckpt_expected.npz"))
+    with torch.no_grad():
+        lo, xr, rg = O.forward(sd_a, cfg_a, torch.from_numpy(z["x"]), 3, True)
+    assert float((lo - torch.from_numpy(z["logits"])).abs().max()) < 2e-5
+    assert float((xr - torch.from_numpy(z["x_raw"])).abs().max()) < 2e-4
+
+
 def test_ema_file_and_save_model_roundtrip(sdp, tmp_path):
     sd = O.synth_state_dict(CFG, seed=4)
     ema = {"module." + k: v * 0.5 if v.is_floating_point() else v for k, v in sd.items()}   # training_tools.py:300-302

@@ -34,7 +34,7 @@ def _worker(rank, world, port, n_total, out_dir):
     lo, hi = shard.shard_range(n_total, rank, world)
     local = O.forward(sd, cfg, x[lo:hi], 3)
     full = shard.gather_logits(local, n_total)
-    # EvalMeter's cross-rank reduction is a SUM all_reduce of its 4 accumulators (CPU tensor here)
+    # EvalMeter's cross-rank reduction is a SUM all_reduce of (a clone of) its accumulators (CPU tensor here)
     acc4 = torch.tensor([float(rank + 1), 2.0, 3.0, float(hi - lo)], dtype=torch.float64)
     dist.all_reduce(acc4, op=dist.ReduceOp.SUM)
     assert acc4.tolist() == [3.0, 4.0, 6.0, float(n_total)]

@@ -1,4 +1,4 @@
-"""Attention kernel check + timing on the GPU box: python tools/attn_probe.py  (SDP_ATTN_TC=0 -> mma.sync path)."""
+"""Attention kernel check + timing on the GPU box: python tools/attn_probe.py."""
 import math
 import os
 import sys
@@ -19,7 +19,6 @@ def ref(qkv, h):
 
 
 def main():
-    print("SDP_ATTN_TC =", os.environ.get("SDP_ATTN_TC"))
     g = torch.Generator(device="cuda").manual_seed(1)
     for (B, S, h, d) in [(2, 128, 2, 64), (2, 16, 1, 64), (2, 5, 2, 64), (3, 201, 8, 96), (3, 261, 8, 96), (2, 256, 2, 128),
                          (2, 257, 2, 96), (2, 288, 2, 64), (2, 272, 1, 128), (5, 261, 8, 96)]:

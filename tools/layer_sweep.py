@@ -1,8 +1,17 @@
-"""BASELINE.json configs[4]: isolated layer sweep at embed 768 -- one ConvMixer (DW 7x7 + pointwise + MLP)
-and one EncoderLayer with 5 register tokens on a 14x14 grid, batch 1..2048, bf16.  Times the engine's
-kernel sequence for the layer (token-major buffers, CUDA events around ~25 ms bursts of back-to-back calls after a warm-up burst, median of 5) and prints a
-markdown table."""
-import math
+"""BASELINE.json configs[4]: isolated layer sweep at embed 768 -- one ConvMixer (LN + DW 7x7 + pointwise + MLP) and one
+EncoderLayer with 5 register tokens, batch 1..2048, bf16, on the 14x14 grid (S / M) and the 16x16 grid (XL), through
+the product path's kernel sequence (split residual stream, LayerNorms folded into the consumer GEMMs).
+
+  python tools/layer_sweep.py [--grids 14,16] [--batches 1,2,...]     timing: CUDA events around ~25 ms bursts of
+                                                                       back-to-back calls after a warm-up burst, median of 5
+  ncu --metrics <m> --csv --log-file L python tools/layer_sweep.py --once
+                                                                       one call per (grid, batch, layer) after a warm-up
+                                                                       call; writes gpurun_out/sweep_manifest.json (labels
+                                                                       and launch counts in launch order) for
+                                                                       tools/sweep_ncu_summary.py
+"""
+import argparse
+import json
 import os
 import sys
 
@@ -14,16 +23,7 @@ import sdpnet_b200 as sdp  # noqa: E402
 import sdpnet_oracle as O  # noqa: E402
 from sdpnet_b200.engine import Buffers, Packer, run_encoder, run_mixer  # noqa: E402
 
-C, h, G, R, k = 768, 8, 14, 5, 7
-T, S = G * G, G * G + R
-cfg = dict(embedding_dim=C, n_head=h, num_blocks=1, conv_kernel_size=k, patch_size=16, conv_block_num=1,
-           max_image_size=[16, 16], head_output_from_register=True)
-sd = O.synth_state_dict(cfg, seed=0, stress=True)
-pk = Packer("cuda", "bf16", C, h, "gelu")
-wm = pk._pack_mixer(sd, "blocks.0.conv_blocks.0.")
-we = pk._pack_encoder(sd, "blocks.0.t_block.")
-mix_flops = 2 * T * C * k * k + 2 * S * C * C + 16 * S * C * C
-enc_flops = 6 * S * C * C + 4 * S * S * C + 2 * S * C * C + 16 * S * C * C
+C, h, R, k = 768, 8, 5, 7
 
 
 def med_ms(fn, reps=5, target_ms=25.0):
@@ -45,19 +45,54 @@ def med_ms(fn, reps=5, target_ms=25.0):
     return ts[len(ts) // 2]
 
 
-print("| batch | ConvMixer ms | img/s | TFLOP/s | EncoderLayer ms | img/s | TFLOP/s |")
-print("|---:|---:|---:|---:|---:|---:|---:|")
-only = [int(v) for v in os.environ.get("SWEEP_BATCHES", "").split(",") if v]     # e.g. SWEEP_BATCHES=512,1024
-B = 1
-while B <= 2048:
-    if only and B not in only:
-        B *= 2
-        continue
-    bufs = Buffers(pk, B, T, R)
-    bufs.act.copy_(torch.randn(B, S, C, device="cuda"))
-    tm = med_ms(lambda: run_mixer(pk, wm, bufs, G, G))
-    te = med_ms(lambda: run_encoder(pk, we, bufs))
-    print(f"| {B} | {tm:.3f} | {B / tm * 1e3:.0f} | {B * mix_flops / tm / 1e9:.1f} | {te:.3f} | {B / te * 1e3:.0f} | "
-          f"{B * enc_flops / te / 1e9:.1f} |", flush=True)
-    del bufs
-    B *= 2
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grids", default="14,16")
+    ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256,512,1024,2048")
+    ap.add_argument("--once", action="store_true")
+    a = ap.parse_args()
+    cfg = dict(embedding_dim=C, n_head=h, num_blocks=1, conv_kernel_size=k, patch_size=16, conv_block_num=1,
+               max_image_size=[16, 16], head_output_from_register=True)
+    sd = O.synth_state_dict(cfg, seed=0, stress=True)
+    pk = Packer("cuda", "bf16", C, h, "gelu", ln_fold=True)
+    wm = pk._pack_mixer(sd, "blocks.0.conv_blocks.0.")
+    we = pk._pack_encoder(sd, "blocks.0.t_block.")
+    manifest = []
+    for G in [int(v) for v in a.grids.split(",")]:
+        T, S = G * G, G * G + R
+        mix_flops = 2 * T * C * k * k + 2 * S * C * C + 16 * S * C * C
+        enc_flops = 6 * S * C * C + 4 * S * S * C + 2 * S * C * C + 16 * S * C * C
+        if not a.once:
+            print(f"\n### {G} x {G} grid (S = {S})\n")
+            print("| batch | ConvMixer ms | img/s | TFLOP/s | EncoderLayer ms | img/s | TFLOP/s |")
+            print("|---:|---:|---:|---:|---:|---:|---:|")
+        for B in [int(v) for v in a.batches.split(",")]:
+            bufs = Buffers(pk, B, T, R, split=True)
+            x = torch.randn(B, S, C, device="cuda")
+            bufs.act.copy_(x)
+            bufs.act_lo.copy_(x - bufs.act.float())
+            sdp.ops.row_stats(bufs.act, bufs.stats)
+            bufs.stats_fresh = True
+            mixer = lambda: run_mixer(pk, wm, bufs, G, G)
+            encoder = lambda: run_encoder(pk, we, bufs)
+            if a.once:
+                for name, fn in (("mixer", mixer), ("encoder", encoder)):
+                    for tag in ("warm", "meas"):
+                        sdp.ops.launch_count(reset=True)
+                        fn()
+                        torch.cuda.synchronize()
+                        manifest.append({"grid": G, "batch": B, "layer": name, "pass": tag, "launches": sdp.ops.launch_count()})
+            else:
+                tm, te = med_ms(mixer), med_ms(encoder)
+                print(f"| {B} | {tm:.3f} | {B / tm * 1e3:.0f} | {B * mix_flops / tm / 1e9:.1f} | {te:.3f} | {B / te * 1e3:.0f} | "
+                      f"{B * enc_flops / te / 1e9:.1f} |", flush=True)
+            del bufs
+    if a.once:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "sweep_manifest.json"), "w") as f:
+            json.dump(manifest, f)
+        print("sections", len(manifest), "launches", sum(m["launches"] for m in manifest))
+
+
+if __name__ == "__main__":
+    main()
