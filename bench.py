@@ -48,7 +48,7 @@ def gemm_traffic(config, batch):
     """DRAM bytes per GEMM launch (dram__bytes_read + dram__bytes_write, averaged over the step's GEMM launches) from
     the committed `ncu --set full` capture; None when the capture was taken on another workload."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")) as f:
             t = json.load(f)
         if t.get("config") != config or int(t.get("batch", 0)) != int(batch):
             return None
@@ -58,10 +58,11 @@ def gemm_traffic(config, batch):
 
 
 def gemm_bytes_per_step(cfg, M):
-    """Algorithmic bytes of the step's big GEMMs: A + W + out (+ the residual read), bf16."""
+    """Algorithmic bytes of the step's big GEMMs: A + W + out in bf16; the GEMMs that write the residual stream read and
+    write both of its planes (hi + lo, 2 bytes each)."""
     C, F = int(cfg["embedding_dim"]), int(cfg.get("ff_multiplication_factor", 4)) * int(cfg["embedding_dim"])
     def g(K, N, res):
-        return 2 * (M * K + N * K + M * N * (2 if res else 1))
+        return 2 * (M * K + N * K + M * N * (4 if res else 1))
     nb, cb = int(cfg["num_blocks"]), int(cfg["conv_block_num"])
     enc = g(C, 3 * C, False) + g(C, C, True) + g(C, F, False) + g(F, C, True)
     mix = g(C, C, True) + g(C, 4 * C, False) + g(4 * C, C, True)
@@ -513,9 +514,9 @@ def main():
             "kernel": "gemm_bf16_tc_kernel (tcgen05/TMEM/TMA)", "bound": "tensor", "achieved": achieved,
             "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["sustained"],
             "traffic": gemm_traffic(args.config, B),
-            "traffic_how": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the step's GEMM launches "
-                           "by shape, from the committed ncu --set full capture (profiles/r01_gemm_traffic.json); "
-                           "compare algorithmic_bytes_per_launch",
+            "traffic_how": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 177 GEMM launches of one "
+                           "whole forward captured with ncu --set full (profiles/r02_gemm_traffic.json, keyed by kernel "
+                           "name; tools/step_ncu_probe.py + tools/step_ncu_summary.py); compare algorithmic_bytes_per_launch",
             "algorithmic_bytes_per_launch": gemm_bytes_per_step(cfg, B * (T + R)) / nl,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
             "launches_per_step": nl, "avg_launch_ms": gms / nl, "avg_launch_gflop": gf / nl / 1e9,

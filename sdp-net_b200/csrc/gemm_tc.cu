@@ -525,7 +525,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               float v[32];
               tmem_ld32(taddr + c + i, v);
               tmem_ld_wait();
-              if (lnf) ln_fold(v, col0 + i);
+              if (lnf) {                           // folded once: the normalise pass reads the folded values back
+                ln_fold(v, col0 + i);
+                tmem_st32(taddr + c + i, v);
+              }
               if (i == 0) shift = v[0];
               const uint64_t nshift = pack_f32x2(-shift, -shift);
 #pragma unroll
@@ -540,6 +543,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             unpack_f32x2(s1p[1], s1[2], s1[3]);
             unpack_f32x2(s2p[0], s2[0], s2[1]);
             unpack_f32x2(s2p[1], s2[2], s2[3]);
+            if (lnf) tmem_st_wait();
             const float dm = ((s1[0] + s1[1]) + (s1[2] + s1[3])) * (1.0f / HN);
             mean = shift + dm;
             const float q = fmaxf(((s2[0] + s2[1]) + (s2[2] + s2[3])) * (1.0f / HN) - dm * dm, 0.0f) * HN;
@@ -554,7 +558,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[32];
           tmem_ld32(taddr + c + i, v);
           tmem_ld_wait();
-          if (lnf && col0 + i + 32 <= epi.N) ln_fold(v, col0 + i);
+          if (lnf && hw == nullptr && col0 + i + 32 <= epi.N) ln_fold(v, col0 + i);   // (head-norm columns: folded above)
           if constexpr (HN > 0) {
             if (hw != nullptr) {
               const uint64_t nmean = pack_f32x2(-mean, -mean), rstd2 = pack_f32x2(rstd, rstd);
