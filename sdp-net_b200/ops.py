@@ -336,5 +336,6 @@ def _register_torch_ops() -> None:
 
 try:
     _register_torch_ops()
-except Exception:  # pragma: no cover - registration is a convenience, never a dependency
-    pass
+except RuntimeError as _e:  # pragma: no cover - a second import of the package in one process: the namespace already exists
+    if "already" not in str(_e).lower():
+        raise
