@@ -380,7 +380,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")     # NCCL logs to stderr; stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # a caller's NCCL_DEBUG (e.g. INFO, to count ranks) is respected
         dist.init_process_group("nccl", device_id=dev)
     cfg, default_batch = CONFIGS[args.config]
     B = args.batch or default_batch
@@ -406,6 +406,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    ranks_seen = 1
+    if world > 1:                                        # one SUM all_reduce of ones: every rank of the job took part
+        ones = torch.ones(1, device=dev)
+        dist.all_reduce(ones)
+        ranks_seen = int(ones.item())
 
     def max_over_ranks(ms):
         if world == 1:
@@ -498,6 +504,8 @@ def main():
         "clocks": clk.summary(),
         "e2e": e2e,
         "gpu_launches": int(launches),
+        "comm": {"backend": "nccl" if world > 1 else None, "world_size": world, "ranks_in_all_reduce": ranks_seen,
+                 "collectives_on_timed_path": 0},
         "model_tflops": value / world * flops_img / 1e12,
         "model_frac_of_sustained_peak": value / world * flops_img / 1e12 / peaks["sustained"],
         "algorithmic_gflop_per_image": flops_img / 1e9,

@@ -226,6 +226,34 @@ def test_gemm_bf16_layernorm_fold(sdp, C, N, act, hn, M):
 
 
 
+def test_gemm_bf16_layernorm_fold_large_mean_rows(sdp):
+    """Rows whose channel mean is far from zero (|mean| = 8 std): the one-pass fp32 (sum, sumsq) statistics of the bf16
+    values and the `acc - mean * s` cancellation in the consumer epilogue stay at bf16 level.  (The producer sums
+    bf16 values in fp32: mean^2 / var can reach 2^16 before the data itself stops resolving the variance, which leaves
+    the fp32 one-pass form ~1e-3 relative in the variance -- the reason no shifted sums are emitted.)"""
+    M, C, N, eps = 2610, 768, 3072, 1e-5
+    base = rnd(M, 1, seed=83) * 3.0 + 8.0
+    x = (rnd(M, C, seed=84) + base).to(torch.bfloat16)                    # per-row mean ~ 8 +- 3, std 1
+    W = rnd(N, C, seed=85, scale=1 / math.sqrt(C))
+    gamma, beta, bias = rnd(C, seed=86) * 0.3 + 1, rnd(C, seed=87) * 0.3, rnd(N, seed=88) * 0.2
+    Wf = (W * gamma[None, :]).to(torch.bfloat16)
+    s_vec, t_vec = Wf.float().sum(1).contiguous(), (W @ beta + bias).contiguous()
+    # statistics as the producer GEMM emits them: in-place residual epilogue over the split stream
+    parts = sdp.ops.gemm_stats_parts(C, torch.bfloat16)
+    stats = torch.empty(M, parts, 2, device="cuda")
+    hi, lo = _split(x.float())
+    A0 = torch.zeros(M, 64, device="cuda", dtype=torch.bfloat16)
+    sdp.ops.gemm(A0, torch.zeros(C, 64, device="cuda", dtype=torch.bfloat16), hi, residual=hi, residual_lo=lo, out_lo=lo, stats_out=stats)
+    assert torch.equal(hi, x)                                              # adding zero changes nothing
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    sdp.ops.gemm(hi, Wf, out, act="gelu", ln_fold=(stats, eps, s_vec, t_vec))
+    ref = torch.nn.functional.gelu(F.layer_norm(x.float(), (C,), gamma, beta, eps) @ W.t() + bias)
+    assert relerr(out, ref) < 2e-2
+    mean = stats[:, :, 0].sum(1) / C
+    var = stats[:, :, 1].sum(1) / C - mean * mean
+    assert float(((var - x.float().var(1, unbiased=False)).abs() / x.float().var(1, unbiased=False)).max()) < 2e-3
+
+
 def _split(x):
     """fp32 -> (hi, lo) bf16 planes of the split residual stream."""
     hi = x.to(torch.bfloat16)
