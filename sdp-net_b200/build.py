@@ -11,6 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(HERE, "lib", "libsdpnet_b200.so")
+TORCH_LIB = os.path.join(HERE, "lib", "libsdpnet_b200_torch.so")     # TORCH_LIBRARY wrappers over the C-ABI (csrc/torch_ops.cpp)
 SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "norm.cu", "dwconv.cu", "dwconv_slab.cu", "attention.cu", "attention_tc.cu", "preprocess.cu", "forward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -58,7 +59,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
         if verbose:
             print(f"linked {LIB}")
+    build_torch_ops(force, verbose)
     return LIB
+
+
+def build_torch_ops(force: bool = False, verbose: bool = False) -> str:
+    """g++ build of the thin `torch.ops.sdpnet_b200.*` wrappers against the installed torch headers; links the C-ABI
+    library next to it (rpath $ORIGIN)."""
+    src = os.path.join(CSRC, "torch_ops.cpp")
+    if not (force or _stale(TORCH_LIB, [src, LIB, os.path.join(ROOT, "include", "sdpnet_b200.h")])):
+        return TORCH_LIB
+    import torch
+    from torch.utils import cpp_extension as ce
+    inc = [f"-I{p}" for p in ce.include_paths()] + ["-I/usr/local/cuda/include"]
+    tlib = ce.library_paths()[0]
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"] + inc + \
+          [src, "-o", TORCH_LIB, f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda", "-ltorch_cuda",
+           f"-L{os.path.dirname(LIB)}", "-lsdpnet_b200", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed on torch_ops.cpp:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print(f"linked {TORCH_LIB}")
+    return TORCH_LIB
 
 
 if __name__ == "__main__":

@@ -305,37 +305,24 @@ def device_ok() -> bool:
     return bool(L.lib().sdp_device_ok())
 
 
-# ---- torch.ops registration (thin: the op bodies are the ctypes calls above) ------------------
-def _register_torch_ops() -> None:
-    lib = torch.library.Library("sdpnet_b200", "DEF")
-    lib.define("gemm(Tensor A, Tensor W, Tensor(a!) out, Tensor? bias, Tensor? residual, int act) -> ()")
-    lib.define("layernorm_rows(Tensor x, Tensor? w, Tensor? b, Tensor(a!) out, float eps) -> ()")
-    lib.define("ln_dwconv(Tensor act, Tensor gamma, Tensor beta, Tensor wdw, Tensor? bdw, Tensor(a!) out, "
-               "int Gh, int Gw, int R, float eps) -> ()")
-    lib.define("attention(Tensor qkv, Tensor(a!) out, int n_head, Tensor? qn_w, Tensor? qn_b, Tensor? kn_w, "
-               "Tensor? kn_b, float eps) -> ()")
-
-    def _gemm(A, W, out, bias, residual, act):
-        gemm(A, W, out, bias=bias, residual=residual, act=act)
-
-    def _ln(x, w, b, out, eps):
-        layernorm_rows(x, w, b, out, eps)
-
-    def _dw(act, g, be, wdw, bdw, out, Gh, Gw, R, eps):
-        ln_dwconv(act, g, be, wdw, bdw, out, Gh, Gw, R, eps)
-
-    def _attn(qkv, out, nh, a, b, c, d, eps):
-        attention(qkv, out, nh, a, b, c, d, eps)
-
-    lib.impl("gemm", _gemm, "CUDA")
-    lib.impl("layernorm_rows", _ln, "CUDA")
-    lib.impl("ln_dwconv", _dw, "CUDA")
-    lib.impl("attention", _attn, "CUDA")
-    globals()["_torch_lib"] = lib   # keep alive
+# ---- torch.ops registration: C++ TORCH_LIBRARY wrappers over the C-ABI (csrc/torch_ops.cpp) -------------------------
+TORCH_OPS_PATH = L.LIB_PATH.replace("libsdpnet_b200.so", "libsdpnet_b200_torch.so")
 
 
-try:
-    _register_torch_ops()
-except RuntimeError as _e:  # pragma: no cover - a second import of the package in one process: the namespace already exists
-    if "already" not in str(_e).lower():
-        raise
+def load_torch_ops() -> None:
+    """Registers `torch.ops.sdpnet_b200.{gemm, layernorm_rows, ln_dwconv, attention}` (thin C++ wrappers that pass raw
+    device pointers and the tensors' current CUDA stream to the C-ABI).  Raises when the wrapper library is missing."""
+    import os
+    if getattr(load_torch_ops, "_done", False):
+        return
+    if not os.path.exists(TORCH_OPS_PATH):
+        raise L.SdpNetLibraryError(f"{TORCH_OPS_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    L.lib()                                  # the C-ABI library first (RTLD_GLOBAL): the wrappers link against it
+    torch.ops.load_library(TORCH_OPS_PATH)
+    load_torch_ops._done = True
+
+
+try:                                         # at import when the build is there; `load_torch_ops()` says why if it is not
+    load_torch_ops()
+except L.SdpNetLibraryError:  # pragma: no cover
+    pass

@@ -66,6 +66,19 @@ def test_ctypes_structs_follow_header_field_order(sdp):
     assert fields("sdp_image_desc") == [n for n, _ in L.ImageDesc._fields_] and ctypes.sizeof(L.ImageDesc) == 16
 
 
+def test_torch_library_ops_are_registered_from_the_cpp_wrappers(sdp):
+    """`torch.ops.sdpnet_b200.*` come from TORCH_LIBRARY in csrc/torch_ops.cpp (libsdpnet_b200_torch.so), CUDA-only:
+    a CPU tensor has no kernel to dispatch to."""
+    import torch
+    sdp.ops.load_torch_ops()
+    for name in ("gemm", "layernorm_rows", "ln_dwconv", "attention"):
+        op = getattr(torch.ops.sdpnet_b200, name)
+        assert "Tensor(a!) out" in str(op.default._schema)
+    x = torch.zeros(4, 8)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.sdpnet_b200.layernorm_rows(x, None, None, torch.empty_like(x), 1e-5)
+
+
 def test_no_cpu_fallback_and_loud_errors(sdp):
     cfg = dict(embedding_dim=32, n_head=2, num_blocks=1, patch_size=4, output_classes=10, max_image_size=[4, 4])
     model = sdp.MainModel.from_dict(**cfg).eval()

@@ -695,6 +695,37 @@ def test_ops_run_on_the_tensors_device_not_the_current_one(sdp):
             sdp.ops.gemm(A, W.to("cuda:0"), out)
 
 
+def test_torch_ops_cpp_wrappers_match_the_ctypes_path(sdp):
+    """torch.ops.sdpnet_b200.* (TORCH_LIBRARY wrappers, csrc/torch_ops.cpp) give the same bits as `sdp.ops.*`."""
+    t = torch.ops.sdpnet_b200
+    A = rnd(300, 256, seed=1, dtype=torch.bfloat16)
+    W = rnd(512, 256, seed=2, scale=1 / 16, dtype=torch.bfloat16)
+    bias, res = rnd(512, seed=3), rnd(300, 512, seed=4, dtype=torch.bfloat16)
+    o1, o2 = torch.empty(300, 512, device="cuda", dtype=torch.bfloat16), torch.empty(300, 512, device="cuda", dtype=torch.bfloat16)
+    t.gemm(A, W, o1, bias, res, sdp.ops.act_id("gelu"))
+    sdp.ops.gemm(A, W, o2, bias=bias, residual=res, act="gelu")
+    assert torch.equal(o1, o2)
+    x, w, b = rnd(77, 96, seed=5, dtype=torch.bfloat16), rnd(96, seed=6) + 1, rnd(96, seed=7)
+    y1, y2 = torch.empty_like(x), torch.empty_like(x)
+    t.layernorm_rows(x, w, b, y1, 1e-5)
+    sdp.ops.layernorm_rows(x, w, b, y2, 1e-5)
+    assert torch.equal(y1, y2)
+    B, Gh, Gw, C, k, R = 3, 8, 8, 64, 5, 2
+    act = rnd(B, R + Gh * Gw, C, seed=8, dtype=torch.bfloat16)
+    g_, be, wd = rnd(C, seed=9) + 1, rnd(C, seed=10), rnd(k * k, C, seed=11, scale=0.2)
+    d1, d2 = torch.empty_like(act), torch.empty_like(act)
+    t.ln_dwconv(act, g_, be, wd, None, d1, Gh, Gw, R, 1e-6)
+    sdp.ops.ln_dwconv(act, g_, be, wd, None, d2, Gh, Gw, R, 1e-6)
+    assert torch.equal(d1, d2)
+    qkv = rnd(2, 133, 3 * 128, seed=12, dtype=torch.bfloat16)
+    a1, a2 = torch.empty(2, 133, 128, device="cuda", dtype=torch.bfloat16), torch.empty(2, 133, 128, device="cuda", dtype=torch.bfloat16)
+    t.attention(qkv, a1, 2, None, None, None, None, 1e-5)
+    sdp.ops.attention(qkv, a2, 2)
+    assert torch.equal(a1, a2)
+    with pytest.raises(RuntimeError):
+        t.gemm(A, W[:, :100].contiguous(), o1, None, None, 0)          # K mismatch: TORCH_CHECK
+
+
 def test_launch_counter(sdp):
     sdp.ops.launch_count(reset=True)
     x = rnd(4, 64)
