@@ -33,14 +33,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.  The poll loop itself is the
+// try_wait and a counter; the clock is only looked at every 16384 polls (a fifth of the attention kernel's executed
+// instructions used to be this loop's watchdog arithmetic).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {   // ~4 s at 2 GHz
-      printf("sdp gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
+    if ((++spins & 0x3FFFu) == 0) {
+      if (t0 == 0) {
+        t0 = clock64();
+      } else if (clock64() - t0 > 8000000000LL) {   // ~4 s at 2 GHz
+        printf("sdp: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
     }
   }
 }
