@@ -265,6 +265,36 @@ def gpu_comparators(cfg, state_dict, x_host, dev, engine_logits, steps=3, warmup
     return out
 
 
+def cublas_yardstick(cfg, M, dev, reps=12):
+    """What the vendor library reaches on THIS step's GEMM shapes at this M, in the same power-capped regime (a yardstick
+    only: cuBLAS is not on the product path).  The 'sustained peak' in MEASURED_PEAKS.json is an 8192^3 number whose
+    operands live in L2; at M = B*S with K = 768 / 3072 the library itself stays well below it."""
+    import torch
+    C, F = int(cfg["embedding_dim"]), int(cfg["ff_multiplication_factor"]) * int(cfg["embedding_dim"])
+    nb, cb = int(cfg["num_blocks"]), int(cfg["conv_block_num"])
+    shapes = [(3 * C, C, nb + 1), (C, C, nb + 1 + nb * cb), (F, C, nb + 1), (C, F, nb + 1), (4 * C, C, nb * cb), (C, 4 * C, nb * cb)]
+    tot_ms, tot_fl, per = 0.0, 0.0, {}
+    for N, K, count in shapes:
+        A = torch.randn(M, K, device=dev).bfloat16()
+        W = (torch.randn(N, K, device=dev) * K ** -0.5).bfloat16()
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            torch.matmul(A, W.t(), out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(A, W.t(), out=out)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        per[f"N{N} K{K}"] = round(2.0 * M * N * K / ms / 1e9, 1)
+        tot_ms += ms * count
+        tot_fl += 2.0 * M * N * K * count
+        del A, W, out
+    return {"tflops_launch_weighted": tot_fl / tot_ms / 1e9, "ms_per_step_if_every_gemm_were_plain_cublas": tot_ms, "by_shape_tflops": per,
+            "how": f"torch.matmul (cuBLAS) bf16, {reps} back-to-back launches per shape after 3 warm-ups, no epilogue work at all"}
+
+
 def algorithmic_flops_per_image(cfg, T, R):
     """2 * MAC of one forward, SURVEY.md §8(d): patcher + nb * (cbn * mixer + encoder) + final encoder + head; the
     mixers are counted on the T patch tokens, LN / GELU / softmax flops are not counted."""
@@ -531,6 +561,13 @@ def main():
             "share_of_step": gms / sum(v["ms_per_step"] for v in fam.values()),
             "how": "CUDA events around every launch of an instrumented op-by-op pass of the same forward",
         }
+        if world == 1 and not args.no_comparators:
+            y = cublas_yardstick(cfg, B * (T + R), dev)
+            line["roofline"]["cublas_same_shapes"] = y
+            line["roofline"]["frac_of_cublas_same_shapes"] = achieved / y["tflops_launch_weighted"]
+            line["roofline"]["note"] = ("the GEMM family carries, in its epilogues, every token LayerNorm of the model (folded), the GELUs, the "
+                                        "per-head q/k LayerNorm and the two-plane (hi + lo) residual stream; cublas_same_shapes is the bare "
+                                        "library GEMM on the same shapes with none of that")
         line["kernel_families_ms_per_step"] = {k: round(v["ms_per_step"], 3) for k, v in fam.items()}
         line["kernel_detail"] = detail
         # bandwidth-bound families, for the record (algorithmic bytes: read + write of [B,S,C] bf16)
