@@ -265,7 +265,7 @@ def gpu_comparators(cfg, state_dict, x_host, dev, engine_logits, steps=3, warmup
     return out
 
 
-def cublas_yardstick(cfg, M, dev, reps=12):
+def cublas_yardstick(cfg, M, dev, seconds=1.0):
     """What the vendor library reaches on THIS step's GEMM shapes at this M, in the same power-capped regime (a yardstick
     only: cuBLAS is not on the product path).  The 'sustained peak' in MEASURED_PEAKS.json is an 8192^3 number whose
     operands live in L2; at M = B*S with K = 768 / 3072 the library itself stays well below it."""
@@ -278,10 +278,14 @@ def cublas_yardstick(cfg, M, dev, reps=12):
         A = torch.randn(M, K, device=dev).bfloat16()
         W = (torch.randn(N, K, device=dev) * K ** -0.5).bfloat16()
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        for _ in range(3):
-            torch.matmul(A, W.t(), out=out)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        for _ in range(3):
+            torch.matmul(A, W.t(), out=out)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        reps = max(12, int(seconds * 1e3 / max(e0.elapsed_time(e1) / 3, 1e-3)))     # ~`seconds` of back-to-back launches:
+        e0.record()                                                                  # the power-capped regime of the step
         for _ in range(reps):
             torch.matmul(A, W.t(), out=out)
         e1.record()
@@ -292,7 +296,8 @@ def cublas_yardstick(cfg, M, dev, reps=12):
         tot_fl += 2.0 * M * N * K * count
         del A, W, out
     return {"tflops_launch_weighted": tot_fl / tot_ms / 1e9, "ms_per_step_if_every_gemm_were_plain_cublas": tot_ms, "by_shape_tflops": per,
-            "how": f"torch.matmul (cuBLAS) bf16, {reps} back-to-back launches per shape after 3 warm-ups, no epilogue work at all"}
+            "how": f"torch.matmul (cuBLAS) bf16, ~{seconds:.1f} s of back-to-back launches per shape (power-capped like the step), "
+                   "no epilogue work at all"}
 
 
 def algorithmic_flops_per_image(cfg, T, R):
