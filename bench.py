@@ -415,7 +415,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")     # a caller's NCCL_DEBUG (e.g. INFO, to count ranks) is respected
+        # NCCL_DEBUG is left exactly as the caller set it (INFO to count ranks, or unset = silent): with it unset NCCL
+        # prints nothing and stdout stays the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg, default_batch = CONFIGS[args.config]
     B = args.batch or default_batch
