@@ -15,9 +15,26 @@
 // Warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2..9 = softmax / epilogue.
 // No online rescaling is needed: a full score row fits in TMEM.
 #include "tc5.cuh"
+#if AT_TRACE
+#define AT_TDECL unsigned char tcode[200]; long long tclk[200]; int tn = 0;
+#define AT_T(code) do { if (blockIdx.x == 0 && lane == 0 && tn < 200) { tcode[tn] = (unsigned char)(code); tclk[tn++] = clock64(); } } while (0)
+#define AT_DUMP(name) do { if (blockIdx.x == 0 && lane == 0) for (int i = 0; i < tn; ++i) printf("%s w%d %3d %lld\n", name, warp, (int)tcode[i], tclk[i]); } while (0)
+#else
+#define AT_TDECL
+#define AT_T(code)
+#define AT_DUMP(name)
+#endif
 
 namespace sdp {
 
+
+// The kernel's hot code has to stay inside the 32 KB instruction cache (it ran at an 87 % hit rate when every
+// wait carried its own copy of the watchdog loop and the MMA issue loops were unrolled): waits are one try_wait
+// with the bounded poll loop out of line.
+__device__ __noinline__ void at_wait_slow(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void at_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) at_wait_slow(bar, parity);
+}
 
 constexpr int AT_MT = 128;          // query rows per tile
 constexpr int AT_THREADS = 320;        // TMA warp, MMA warp, 8 softmax warps
@@ -156,6 +173,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + bar_off + 104);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  AT_TDECL
   const int C = h * D;
   // Items (image, head) are walked with a grid stride, images from the last to the first: the QKV GEMM wrote its rows
   // in ascending order (the tail of the batch is still in L2), and the output projection starts at image 0, which
@@ -167,31 +185,6 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   // sx_full, px_full; o_full / o_free alternate between the OB accumulators with G.  sy_full / py_full skip the
   // transposed tail tile (HPT completions per item).  Per item: kv_full, k1_full, v_full.
   const int HPT = tail_mode ? tiles - 1 : tiles;
-
-  // TMA issue helpers (one thread)
-  auto load_q = [&](int item, int t) {
-    const int row0 = item_image(item) * S + t * AT_MT, head = item % h;
-    mbar_expect_tx(B.q_full, NA * AT_MT * 64);
-    for (int a = 0; a < N128; ++a) tma_load_2d(sbase + q_off + a * AT_MT * 128, &tmQ, B.q_full, head * D + 64 * a, row0);
-    if (N64) tma_load_2d(sbase + q64_off, &tmQ32, B.q_full, head * D + 64 * N128, row0);
-  };
-  auto load_k = [&](int item) {            // the first box of K rows is all the X scores need
-    const int row0 = item_image(item) * S, head = item % h;
-    for (int r = 0; r < KEYS; r += kv_box_rows) {
-      const uint32_t kbar = r == 0 ? B.kv_full : B.k1_full;
-      mbar_expect_tx(kbar, NA * kv_box_rows * 64);
-      for (int a = 0; a < N128; ++a)
-        tma_load_2d(sbase + k_off + (a * KEYS + r) * 128, &tmK, kbar, C + head * D + 64 * a, row0 + r);
-      if (N64) tma_load_2d(sbase + k64_off + r * 64, &tmKV, kbar, C + head * D + 64 * N128, row0 + r);
-    }
-  };
-  auto load_v = [&](int item) {
-    const int row0 = item_image(item) * S, head = item % h;
-    mbar_expect_tx(B.v_full, NA * KEYS * 64);
-    for (int a = 0; a < NA; ++a)
-      for (int r = 0; r < KEYS; r += kv_box_rows)
-        tma_load_2d(sbase + v_off + (a * KEYS + r) * 64, &tmKV, B.v_full, 2 * C + head * D + 32 * a, row0 + r);
-  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -212,10 +205,6 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(B.o_free, 8);
     mbar_init(B.o_free + 8, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // The loads of the first item start before the rest of the CTA is set up
-    load_q(blockIdx.x, 0);
-    load_k(blockIdx.x);
-    load_v(blockIdx.x);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -231,23 +220,41 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp == 0) {
     // ================= TMA producer =================
+    // One loop body issues every load (the code of this warp is as hot as the softmax: it must stay small).  Tile 0 of
+    // an item brings K and V along: Q and K as soon as the last score MMA of the previous item has retired, V once its
+    // last P V has (its own once-per-item barrier: this thread does not follow the O-full barriers tile by tile, and a
+    // parity wait that skips completions aliases).
     if (lane == 0) {
-      int G0 = 0;                                             // global index of the item's tile 0
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, G0 += tiles) {
-        for (int t = 1; t < tiles; ++t) {
-          mbar_wait(B.q_free, (G0 + t - 1) & 1);              // the scores of tile t - 1 have been issued and retired
-          load_q(item, t);
-        }
-        const int next = item + gridDim.x;
-        if (next < n_items) {
-          // the last score MMA of this item has retired: Q and K are free for the next item ...
-          mbar_wait(B.q_free, (G0 + tiles - 1) & 1);
-          load_q(next, 0);
-          load_k(next);
-          // ... and V once the last P V has.  (Its own once-per-item barrier: this thread does not follow the O-full
-          // barriers tile by tile, and a parity wait that skips completions aliases.)
-          mbar_wait(B.v_free, (G0 / tiles) & 1);
-          load_v(next);
+      int G = 0, itn = 0;                                     // global tile index, item count of this CTA
+#pragma unroll 1
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++itn) {
+        const int img = item_image(item), head = item - (item / h) * h;
+        const int row0 = img * S, qcol = head * D, kcol = C + head * D, vcol = 2 * C + head * D;
+#pragma unroll 1
+        for (int t = 0; t < tiles; ++t, ++G) {
+          if (G > 0) at_wait(B.q_free, (G - 1) & 1);          // the scores of the previous tile have been issued and retired
+          mbar_expect_tx(B.q_full, NA * AT_MT * 64);
+#pragma unroll 1
+          for (int a = 0; a < N128; ++a)
+            tma_load_2d(sbase + q_off + a * AT_MT * 128, &tmQ, B.q_full, qcol + 64 * a, row0 + t * AT_MT);
+          if (N64) tma_load_2d(sbase + q64_off, &tmQ32, B.q_full, qcol + 64 * N128, row0 + t * AT_MT);
+          if (t > 0) continue;
+#pragma unroll 1
+          for (int r = 0; r < KEYS; r += kv_box_rows) {       // the first box of K rows is all the X scores need
+            const uint32_t kbar = r == 0 ? B.kv_full : B.k1_full;
+            mbar_expect_tx(kbar, NA * kv_box_rows * 64);
+#pragma unroll 1
+            for (int a = 0; a < N128; ++a)
+              tma_load_2d(sbase + k_off + (a * KEYS + r) * 128, &tmK, kbar, kcol + 64 * a, row0 + r);
+            if (N64) tma_load_2d(sbase + k64_off + r * 64, &tmKV, kbar, kcol + 64 * N128, row0 + r);
+          }
+          if (itn > 0) at_wait(B.v_free, (itn - 1) & 1);
+          mbar_expect_tx(B.v_full, NA * KEYS * 64);
+#pragma unroll 1
+          for (int a = 0; a < NA; ++a)
+#pragma unroll 1
+            for (int r = 0; r < KEYS; r += kv_box_rows)
+              tma_load_2d(sbase + v_off + (a * KEYS + r) * 64, &tmKV, B.v_full, vcol + 32 * a, row0 + r);
         }
       }
     }
@@ -262,69 +269,64 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t k128_lo = at_lo(sbase + k_off, 16), k64_lo = at_lo(sbase + k64_off, 16);
       const uint32_t p128_lo = at_lo(sbase + p_off, 16), p64_lo = at_lo(sbase + p64_off, 16);
       const uint32_t v_lo = at_lo(sbase + v_off, KEYS * 64);
+      // Issue loops are rolled (a dozen instructions per MMA against 48-72 tensor-core cycles each): unrolled they were
+      // a fifth of the kernel's code.
       auto issue_qk = [&](int key0, uint32_t idesc) {         // scores of keys [key0, key0 + N) -> TMEM column key0
         const uint32_t kl128 = k128_lo + key0 * (128 >> 4), kl64 = k64_lo + key0 * (64 >> 4);
-#pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          if (ks < 4 * N128)                                    // 16 columns of a 64-column atom
-            at_mma(tmem + key0, q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
-                   kl128 + (ks >> 2) * (KEYS * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc, ks != 0);
-          else                                                  // ... of the 32-column atom
-            at_mma(tmem + key0, q64_lo + (ks & 1) * 2, AT_HI_SW64, kl64 + (ks & 1) * 2, AT_HI_SW64, idesc, ks != 0);
+#pragma unroll 1
+        for (int ks = 0; ks < 4 * N128; ++ks)                   // 16 columns of a 64-column atom
+          at_mma(tmem + key0, q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
+                 kl128 + (ks >> 2) * (KEYS * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc, ks != 0);
+        if (N64) {
+#pragma unroll 1
+          for (int ks = 0; ks < 2; ++ks)                        // ... of the 32-column atom
+            at_mma(tmem + key0, q64_lo + ks * 2, AT_HI_SW64, kl64 + ks * 2, AT_HI_SW64, idesc, (4 * N128 + ks) != 0);
         }
       };
-      auto issue_pv = [&](int j0, int j1, uint32_t o_col) {   // 16-key steps [j0, j1) of O += P V
-        const int jm = j1 < 4 * NP128 ? j1 : 4 * NP128;         // steps below jm read P from 64-key atoms
-#pragma unroll 4
-        for (int j = j0; j < jm; ++j)
-          at_mma(tmem + o_col, p128_lo + ((j >> 2) << 10) + ((j & 3) << 1), AT_HI_SW128, v_lo + j * (16 * 64 >> 4),
-                 AT_HI_SW64, idesc_o, j != 0);
-        for (int j = j0 > jm ? j0 : jm; j < j1; ++j) {
+      // 16-key steps [j0, j1) of O += P V; P from the tile's atoms (64-key, then 32-key) or, for the transposed tail
+      // tile, from the compact 16-row atoms
+      const uint32_t pt128_lo = at_lo(sbase + pt_off, 16), pt64_lo = at_lo(sbase + pt_off + NP128 * 2048, 16);
+      auto issue_pv = [&](int j0, int j1, uint32_t o_col, bool tail) {
+        const uint32_t a128 = tail ? pt128_lo : p128_lo, a64 = tail ? pt64_lo : p64_lo;
+        const uint32_t s128 = tail ? (2048 >> 4) : (AT_MT * 128 >> 4), s64 = tail ? (1024 >> 4) : (AT_MT * 64 >> 4);
+#pragma unroll 1
+        for (int j = j0; j < j1; ++j) {
           const int j2 = j - 4 * NP128;
-          at_mma(tmem + o_col, p64_lo + ((j2 >> 1) << 9) + ((j2 & 1) << 1), AT_HI_SW64, v_lo + j * (16 * 64 >> 4),
-                 AT_HI_SW64, idesc_o, j != 0);
+          const bool wide = j2 < 0;
+          const uint32_t a_lo = wide ? a128 + (j >> 2) * s128 + ((j & 3) << 1) : a64 + (j2 >> 1) * s64 + ((j2 & 1) << 1);
+          at_mma(tmem + o_col, a_lo, wide ? AT_HI_SW128 : AT_HI_SW64, v_lo + j * (16 * 64 >> 4), AT_HI_SW64, idesc_o, j != 0);
         }
       };
       // Tail tile (tail_mode: the last query tile holds <= 8 rows, e.g. the 5 register tokens of S = 261): scores are
       // computed TRANSPOSED, S^T = K Q_tail^T (keys on the TMEM lanes, 16 query columns per 128-key tile), so the
       // softmax is spread over all lanes by key instead of 5 live lanes doing a 272-wide row each; the warps write
-      // P back as rows 0..15 of compact 2 KB atoms in the (now free) Q buffer and the usual P V follows.
+      // P back as rows 0..15 of compact 2 KB atoms and the usual P V follows.
       const uint32_t idesc_t = at_idesc(AT_MT, 16, 0);
       auto issue_st = [&]() {
+#pragma unroll 1
         for (int kt = 0; kt * 128 < KEYS; ++kt) {
-#pragma unroll
-          for (int ks = 0; ks < D / 16; ++ks) {
-            if (ks < 4 * N128)
-              at_mma(tmem + 16 * kt, k128_lo + (ks >> 2) * (KEYS * 128 >> 4) + kt * (128 * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
-                     q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc_t, ks != 0);
-            else
-              at_mma(tmem + 16 * kt, k64_lo + kt * (128 * 64 >> 4) + (ks & 1) * 2, AT_HI_SW64, q64_lo + (ks & 1) * 2, AT_HI_SW64,
-                     idesc_t, ks != 0);
+#pragma unroll 1
+          for (int ks = 0; ks < 4 * N128; ++ks)
+            at_mma(tmem + 16 * kt, k128_lo + (ks >> 2) * (KEYS * 128 >> 4) + kt * (128 * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
+                   q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc_t, ks != 0);
+          if (N64) {
+#pragma unroll 1
+            for (int ks = 0; ks < 2; ++ks)
+              at_mma(tmem + 16 * kt, k64_lo + kt * (128 * 64 >> 4) + ks * 2, AT_HI_SW64, q64_lo + ks * 2, AT_HI_SW64, idesc_t,
+                     (4 * N128 + ks) != 0);
           }
-        }
-      };
-      auto issue_pv_tail = [&](uint32_t o_col) {
-        const uint32_t pt128 = at_lo(sbase + pt_off, 16), pt64 = at_lo(sbase + pt_off + NP128 * 2048, 16);
-#pragma unroll 4
-        for (int j = 0; j < 4 * NP128; ++j)
-          at_mma(tmem + o_col, pt128 + (j >> 2) * (2048 >> 4) + ((j & 3) << 1), AT_HI_SW128, v_lo + j * (16 * 64 >> 4), AT_HI_SW64,
-                 idesc_o, j != 0);
-        for (int j = 4 * NP128; j < KEYS / 16; ++j) {
-          const int j2 = j - 4 * NP128;
-          at_mma(tmem + o_col, pt64 + (j2 >> 1) * (1024 >> 4) + ((j2 & 1) << 1), AT_HI_SW64, v_lo + j * (16 * 64 >> 4), AT_HI_SW64,
-                 idesc_o, j != 0);
         }
       };
       int G0 = 0, Y0 = 0, itn = 0;                            // global tile index / Y-half index of the item's tile 0
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, G0 += tiles, Y0 += HPT, ++itn) {
         const uint32_t itp = itn & 1;
-        mbar_wait(B.kv_full, itp);
-        mbar_wait(B.q_full, G0 & 1);
+        at_wait(B.kv_full, itp);
+        at_wait(B.q_full, G0 & 1);
         tc_fence_after();
         issue_qk(0, idesc_x);                                 // (the S.X columns were handed back with px_full of the previous tile)
         tc_commit(B.sx_full);
         if (KB > 0) {
-          if (kv_box_rows < KEYS) mbar_wait(B.k1_full, itp);  // the K rows past the first box
+          if (kv_box_rows < KEYS) at_wait(B.k1_full, itp);  // the K rows past the first box
           tc_fence_after();
           issue_qk(KA, idesc_y);
           tc_commit(B.sy_full);
@@ -333,23 +335,25 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int t = 0; t < tiles; ++t) {
           const int G = G0 + t, ob = G % OB;
           const uint32_t o_col = AT_O_COL + ob * D;
-          if (G >= OB) mbar_wait(B.o_free + 8 * ob, ((G / OB) - 1) & 1);    // O(G - OB) has been read out
-          if (t == 0) mbar_wait(B.v_full, itp);
-          mbar_wait(B.px_full, G & 1);                        // P.X(t) in shared memory, S.X(t) consumed
+          if (G >= OB) at_wait(B.o_free + 8 * ob, ((G / OB) - 1) & 1);    // O(G - OB) has been read out
+          if (t == 0) at_wait(B.v_full, itp);
+          AT_T(13);
+          at_wait(B.px_full, G & 1);                        // P.X(t) in shared memory, S.X(t) consumed
           tc_fence_after();
+          AT_T(14);
           if (tail_mode && t == tiles - 1) {                  // the whole transposed P arrives with one barrier
-            issue_pv_tail(o_col);
+            issue_pv(0, KEYS / 16, o_col, true);
             tc_commit(B.o_full + 8 * ob);
             break;
           }
           const bool next_tail = tail_mode && t + 2 == tiles;
-          issue_pv(0, KA / 16, o_col);
+          issue_pv(0, KA / 16, o_col, false);
           if (KB == 0) tc_commit(B.o_full + 8 * ob);
           if (t + 1 < tiles) {
-            mbar_wait(B.q_full, (G + 1) & 1);
+            at_wait(B.q_full, (G + 1) & 1);
             tc_fence_after();
             if (next_tail) {
-              if (kv_box_rows < KEYS) mbar_wait(B.k1_full, itp);
+              if (kv_box_rows < KEYS) at_wait(B.k1_full, itp);
               issue_st();
             } else {
               issue_qk(0, idesc_x);
@@ -358,20 +362,24 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (KB == 0 || next_tail) tc_commit(B.q_free);    // (the transposed tail reads its Q rows in one go)
           }
           if (KB > 0) {
-            mbar_wait(B.py_full, (Y0 + t) & 1);
+            AT_T(15);
+            at_wait(B.py_full, (Y0 + t) & 1);
             tc_fence_after();
+            AT_T(16);
             if (t + 1 < tiles && !next_tail) {                // the softmax warps wait on these scores next
               issue_qk(KA, idesc_y);
               tc_commit(B.sy_full);
               tc_commit(B.q_free);
             }
-            issue_pv(KA / 16, KEYS / 16, o_col);
+            issue_pv(KA / 16, KEYS / 16, o_col, false);
             tc_commit(B.o_full + 8 * ob);
           }
         }
+        AT_T(19);
         tc_commit(B.v_free);                                  // every MMA of this item has retired: V may be replaced
       }
     }
+    AT_DUMP("mma");
     __syncwarp();
   } else {
     // ================= softmax + epilogue =================
@@ -420,19 +428,15 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     };
     auto pass2 = [&](int key0, int nkeys, float nm) {         // p = 2^(s*scale - max*scale) -> P (bf16), row sum
       float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      for (int k = 0; k < nkeys; k += 64) {
-        const int n = nkeys - k < 64 ? nkeys - k : 64, kk = key0 + k;
-        float v0[32], v1[32];
+#pragma unroll 1
+      for (int k = 0; k < nkeys; k += 32) {
+        const int n = nkeys - k < 32 ? nkeys - k : 32, kk = key0 + k;
+        float v0[32];
         at_ld_chunk(t_lane + kk, n, v0);
-        if (n > 32) at_ld_chunk(t_lane + kk + 32, n - 32, v1);
         tmem_ld_wait();
         uint32_t prow, ch0, sw;
         p_place(kk, prow, ch0, sw);
         at_exp_chunk(v0, min(n, S - kk), scale_log2, nm, sum, prow, ch0, sw);
-        if (n > 32) {
-          p_place(kk + 32, prow, ch0, sw);
-          at_exp_chunk(v1, min(n, S - kk) - 32, scale_log2, nm, sum, prow, ch0, sw);
-        }
       }
       return (sum[0] + sum[1]) + (sum[2] + sum[3]);
     };
@@ -447,19 +451,15 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       constexpr int HALF = D / 2;
       const int G = G0 + t, ob = G % OB;
       const float *xs = xch + 512 + (G & 1) * 256;
-      float den = xs[r] + xs[128 + r];
-      if (tail) {                                             // transposed tail tile: eight per-warp partial sums per row
-        den = 0.0f;
-        if (r < 8)
-          for (int w = 0; w < 8; ++w) den += xs[w * 8 + r];
-      }
+      const float den = tail ? xs[r & 7] : xs[r] + xs[128 + r];    // (transposed tail tile: one sum per query row)
       const float inv = 1.0f / den;
       const int row = t * AT_MT + r;
       bf16 *orow = out + ((long long)b * S + row) * C + head * D + g * HALF;
       const bool warp_live = t * AT_MT + quad * 32 < S;
       if (warp_live) {
-        mbar_wait(B.o_full + 8 * ob, (G / OB) & 1);
+        at_wait(B.o_full + 8 * ob, (G / OB) & 1);
         tc_fence_after();
+        AT_T(40);
       }
       auto store8 = [&](const float *w, int c) {              // 8 columns -> 16 bytes
         const uint32_t p0 = pack_bf16x2(w[0] * inv, w[1] * inv), p1 = pack_bf16x2(w[2] * inv, w[3] * inv);
@@ -487,6 +487,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         tc_fence_before();
         if (stage_ok) fence_proxy_async_smem();
+        AT_T(41);
       }
       __syncwarp();
       if (lane == 0) {
@@ -498,78 +499,66 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     };
 
-    // ---- tail tile, transposed: this thread owns key 128 kt + 32 quad + lane of key tiles kt = g, g + 2 ----
-    auto tail_tile = [&](int t) {
-      // All 8 query columns are processed without branches (columns past the live rows only produce garbage in P
-      // rows and sums nobody reads), so the eight shuffle chains interleave.
-      float *tmax = xch + ((G0 + t) & 1) * 256;               // [8 warps][8]
-      float *psum = xch + 512 + ((G0 + t) & 1) * 256;         // [8 warps][8]: partial row sums, added up by the epilogue
-      mbar_wait(B.sx_full, (G0 + t) & 1);
+    // ---- tail tile, transposed.  Scores: this thread owns key 128 kt + 32 quad + lane of key tiles kt = g, g + 2 and
+    // drops its 8 query columns into an [8 queries][KEYS] fp32 table in shared memory (keys past the sequence as -inf);
+    // softmax: warp w then owns query row w -- two keys per lane and 64-key step, one max and one sum reduction per
+    // row -- and writes P^T (bf16 pairs) into the compact atoms.
+    float *tsc = xch + 1024;
+    auto tail_scores = [&](int t) {
+      AT_T(49);
+      at_wait(B.sx_full, (G0 + t) & 1);
       tc_fence_after();
-      float v[2][8];
-      bool valid[2];
-      uint32_t pbase[2], pch[2];                              // P row 0 address of this thread's key, its 16-byte chunk
-      bool sw128[2], store[2];
+      AT_T(50);
+#pragma unroll 1
+      for (int kt = g; kt * 128 < KEYS; kt += 2) {
+        float v[8];
+        tmem_ld8(t_lane + 16 * kt, v);
+        tmem_ld_wait();
+        const int key = 128 * kt + 32 * quad + lane;
+        if (key < KEYS) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int kt = g + 2 * i, key = 128 * kt + 32 * quad + lane;
-        valid[i] = kt * 128 < KEYS && key < S;
-        store[i] = kt * 128 < KEYS && key < KEYS;
-        if (kt * 128 < KEYS) tmem_ld8(t_lane + 16 * kt, v[i]);
-        sw128[i] = key < 64 * NP128;
-        const int k2 = key - 64 * NP128;
-        pbase[i] = sw128[i] ? sbase + pt_off + (key >> 6) * 2048 + (key & 7) * 2 : sbase + pt_off + NP128 * 2048 + (k2 >> 5) * 1024 + (k2 & 7) * 2;
-        pch[i] = sw128[i] ? (key & 63) >> 3 : (k2 & 31) >> 3;
-      }
-      tmem_ld_wait();
-      float mq[8];
-#pragma unroll
-      for (int qi = 0; qi < 8; ++qi) mq[qi] = fmaxf(valid[0] ? v[0][qi] : -INFINITY, valid[1] ? v[1][qi] : -INFINITY);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int qi = 0; qi < 8; ++qi) mq[qi] = fmaxf(mq[qi], __shfl_xor_sync(0xffffffffu, mq[qi], o));
-      if (lane < 8) {
-        float mine = mq[0];
-#pragma unroll
-        for (int qi = 1; qi < 8; ++qi) mine = lane == qi ? mq[qi] : mine;
-        tmax[(warp - 2) * 8 + lane] = mine;
-      }
-      asm volatile("bar.sync 9, 256;" ::: "memory");          // all eight softmax warps
-      epilogue(t - 1, false);
-      float mrow = -INFINITY;                                 // lane qi: maximum of query qi over all keys
-      if (lane < 8) {
-#pragma unroll
-        for (int w = 0; w < 8; ++w) mrow = fmaxf(mrow, tmax[w * 8 + lane]);
-      }
-      float ps[8];
-#pragma unroll
-      for (int qi = 0; qi < 8; ++qi) {
-        const float nm = -__shfl_sync(0xffffffffu, mrow, qi) * scale_log2;
-        ps[qi] = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const float pv = valid[i] ? fast_ex2(fmaf(v[i][qi], scale_log2, nm)) : 0.0f;
-          ps[qi] += pv;
-          if (store[i]) {                                     // P[qi][key] into the compact atoms (zeros past the sequence)
-            const uint32_t addr = sw128[i] ? pbase[i] + qi * 128 + ((pch[i] ^ (qi & 7)) << 4)
-                                           : pbase[i] + qi * 64 + ((pch[i] ^ ((qi >> 1) & 3)) << 4);
-            const uint16_t pb = __bfloat16_as_ushort(__float2bfloat16_rn(pv));
-            asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(pb) : "memory");
-          }
+          for (int qi = 0; qi < 8; ++qi) tsc[qi * KEYS + key] = key < S ? v[qi] : -INFINITY;
         }
       }
+      AT_T(51);
+    };
+    auto tail_softmax = [&](int t) {
+      const int qi = warp - 2;
+      if (qi < S - (tiles - 1) * AT_MT) {
+        const float *row = tsc + qi * KEYS;
+        float x[10];
+        float m = -INFINITY;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
+        for (int i = 0; i < 5; ++i) {                         // KEYS <= 288 < 5 * 64
+          const int k = 64 * i + 2 * lane;
+          float2 p2 = make_float2(-INFINITY, -INFINITY);
+          if (k < KEYS) p2 = *reinterpret_cast<const float2 *>(row + k);
+          x[2 * i] = p2.x;
+          x[2 * i + 1] = p2.y;
+          m = fmaxf(m, fmaxf(p2.x, p2.y));
+        }
 #pragma unroll
-        for (int qi = 0; qi < 8; ++qi) ps[qi] += __shfl_xor_sync(0xffffffffu, ps[qi], o);
-      if (lane < 8) {
-        float mine = ps[0];
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float nm = -m * scale_log2;
+        float sum = 0.0f;
 #pragma unroll
-        for (int qi = 1; qi < 8; ++qi) mine = lane == qi ? ps[qi] : mine;
-        psum[(warp - 2) * 8 + lane] = mine;
+        for (int i = 0; i < 5; ++i) {
+          const int k = 64 * i + 2 * lane;
+          const float p0 = fast_ex2(fmaf(x[2 * i], scale_log2, nm)), p1 = fast_ex2(fmaf(x[2 * i + 1], scale_log2, nm));
+          sum += p0 + p1;
+          if (k < KEYS) {                                     // P[qi][k], P[qi][k + 1] (zeros past the sequence)
+            const int k2 = k - 64 * NP128;
+            const uint32_t addr = k2 < 0 ? sbase + pt_off + (k >> 6) * 2048 + qi * 128 + (((((k & 63) >> 3)) ^ (qi & 7)) << 4) + (k & 7) * 2
+                                         : sbase + pt_off + NP128 * 2048 + (k2 >> 5) * 1024 + qi * 64 +
+                                               (((((k2 & 31) >> 3)) ^ ((qi >> 1) & 3)) << 4) + (k2 & 7) * 2;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16x2(p0, p1)) : "memory");
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) xch[512 + ((G0 + t) & 1) * 256 + qi] = sum;
       }
-      publish(B.px_full);
+      AT_T(54);
     };
 
 #pragma unroll 1
@@ -578,35 +567,43 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     head = item % h;
 #pragma unroll 1
     for (int t = 0; t <= tiles; ++t) {                        // iteration t: scores of tile t, output of tile t - 1
-      if (tail_mode && t == tiles - 1) {
-        tail_tile(t);
-        continue;
-      }
+      const bool is_tail = tail_mode && t == tiles - 1, after_tail = tail_mode && t == tiles;
       const bool live = t < tiles && t * AT_MT + quad * 32 < S;   // warps whose rows are all past the sequence idle
       float *xm = xch + ((G0 + t) & 1) * 256, *xs = xch + 512 + ((G0 + t) & 1) * 256;
       float m = -INFINITY;
-      if (t < tiles) {
+      if (is_tail) {
+        tail_scores(t);
+      } else if (t < tiles) {
 #pragma unroll 1
         for (int hf = 0; hf < (KB > 0 ? 2 : 1); ++hf) {       // X then Y: the Y scores land while X is scanned
-          mbar_wait(hf ? B.sy_full : B.sx_full, (hf ? Y0 + t : G0 + t) & 1);
+          AT_T(20 + hf);
+          at_wait(hf ? B.sy_full : B.sx_full, (hf ? Y0 + t : G0 + t) & 1);
           tc_fence_after();
+          AT_T(22 + hf);
           if (live) m = pass1(hf ? yk0 : xk0, hf ? yn : xn, m);
+          AT_T(24 + hf);
         }
         xm[g * 128 + r] = m;
       }
-      // partial maxima of tile t, partial sums of tile t - 1: shared by the two warps of a row -- except after the
-      // transposed tail tile, whose row sums are spread over all eight softmax warps
-      if (tail_mode && t == tiles) {
+      // partial maxima of tile t, partial sums of tile t - 1: shared by the two warps of a row -- except around the
+      // transposed tail tile, whose score table and row sums are shared by all eight softmax warps
+      if (is_tail || after_tail) {
         asm volatile("bar.sync 9, 256;" ::: "memory");
-        if (stage_ok) {                                       // O(t - 2) was staged inside tail_tile with no P pass since:
+        if (after_tail && stage_ok) {                         // O(t - 2) was staged in the tail iteration with no P pass since:
           if (lane == 0) bulk_wait_read<0>();                 // its TMA store must have read the staging rows
           __syncwarp();
         }
       } else {
         pair_sync();
       }
-      if (t > 0) epilogue(t - 1, tail_mode && t == tiles);
-      if (t < tiles) {
+      AT_T(26);
+      if (t > 0) epilogue(t - 1, after_tail);
+      AT_T(27);
+      if (is_tail) {
+        tail_softmax(t);
+        publish(B.px_full);
+        AT_T(55);
+      } else if (t < tiles) {
         m = fmaxf(m, xm[(g ^ 1) * 128 + r]);
         const float nm = -m * scale_log2;
         float sum = 0.0f;
@@ -617,13 +614,16 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             __syncwarp();
           }
           if (live) sum += pass2(hf ? yk0 : xk0, hf ? yn : xn, nm);
+          AT_T(28 + hf);
           publish(hf ? B.py_full : B.px_full);
+          AT_T(30 + hf);
         }
         xs[g * 128 + r] = sum;
       }
     }
     }
     if (stage_ok && lane == 0) bulk_wait_read<0>();          // shared memory outlives the last output store
+    if (warp == 2 || warp == 6) AT_DUMP("smx");
   }
 
   tc_fence_before();
@@ -642,8 +642,12 @@ static int launch_attn_tc5(const void *qkv, void *out, int B, int S, int h, cuda
   if (KEYS > 288 || KEYS % nbox != 0 || (KEYS / nbox) % 8 != 0) return -1;
   const int NA = D / 32, NKA = (KEYS + 31) / 32;
   const int NP128 = KEYS / 64, NP64 = (KEYS % 64 + 31) / 32;
+  // the last query tile is transposed when it holds at most 8 rows
+  const int tiles = (S + AT_MT - 1) / AT_MT;
+  const int tail_mode = tiles >= 2 && S - (tiles - 1) * AT_MT <= 8 ? 1 : 0;
+  // Q, K + V, P, tail P^T, barriers, row max / sum exchange, (tail) score table, alignment slack
   const size_t smem = (size_t)NA * AT_MT * 64 + 2 * (size_t)NA * KEYS * 64 + (size_t)NKA * AT_MT * 64 +
-                      (size_t)NP128 * 2048 + (size_t)NP64 * 1024 + 128 + 4096 + 1024;
+                      (size_t)NP128 * 2048 + (size_t)NP64 * 1024 + 128 + 4096 + (tail_mode ? 8 * (size_t)KEYS * 4 : 0) + 1024;
   if (smem > 227 * 1024) return -1;
   CUtensorMap tq, tq32, tk, tkv;          // 64-column boxes are 128B-swizzled, 32-column boxes 64B-swizzled
   if (int rc = make_tensor_map_bf16(qkv, (uint64_t)B * S, 3 * C, 3 * C, AT_MT, 64, &tq)) return rc;
@@ -658,9 +662,6 @@ static int launch_attn_tc5(const void *qkv, void *out, int B, int S, int h, cuda
   SDP_CUDA(cudaGetDevice(&dev));
   SDP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
-  // the last query tile is transposed when it holds at most 8 rows
-  const int tiles = (S + AT_MT - 1) / AT_MT;
-  const int tail_mode = tiles >= 2 && S - (tiles - 1) * AT_MT <= 8 ? 1 : 0;
   const int n_items = B * h;               // persistent: one CTA per SM (512 TMEM columns, ~210 KB of shared memory)
   kern<<<n_items < sms ? n_items : sms, AT_THREADS, smem, st>>>(tq, tq32, tk, tkv, to, (bf16 *)out, S, h, KEYS, KEYS / nbox,
                                                                 scale_log2, tail_mode, n_items);
