@@ -70,15 +70,31 @@ constexpr uint32_t AT_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);
 __device__ __forceinline__ uint32_t at_lo(uint32_t saddr, uint32_t lbo) {
   return ((saddr & 0x3FFFF) >> 4) | (((lbo >> 4) & 0x3FFF) << 16);
 }
+// The MMA warp runs CONVERGED: all 32 lanes follow the control flow and compute the (warp-uniform) descriptors, so
+// they live in uniform registers; only the tcgen05 instruction itself is predicated on the elected lane.  Issued from
+// inside an `if (lane == 0)` region every MMA went through an ELECT / 5 x R2UR.BROADCAST waterfall loop (~160 cycles
+// per issue against 48-72 tensor-core cycles per MMA).
+__device__ __forceinline__ uint32_t at_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void at_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                       uint32_t idesc, uint32_t accumulate) {
+                                       uint32_t idesc, uint32_t accumulate, uint32_t leader) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
       "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
       "mov.b64 da, {%1, %2};\n\t"
       "mov.b64 db, {%3, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void at_commit(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(leader)
       : "memory");
 }
 __host__ __device__ constexpr uint32_t at_idesc(int m, int n, int b_mn_major) {
@@ -260,7 +276,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    {
+      const uint32_t leader = at_elect();
       const uint32_t idesc_x = at_idesc(AT_MT, KA, 0), idesc_y = at_idesc(AT_MT, KB > 0 ? KB : 16, 0);
       const uint32_t idesc_o = at_idesc(AT_MT, D, 1);
       // The MMAs here are short (48-72 tensor-core cycles), so the issue path is kept to a couple of integer adds
@@ -276,11 +293,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll 1
         for (int ks = 0; ks < 4 * N128; ++ks)                   // 16 columns of a 64-column atom
           at_mma(tmem + key0, q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
-                 kl128 + (ks >> 2) * (KEYS * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc, ks != 0);
+                 kl128 + (ks >> 2) * (KEYS * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc, ks != 0, leader);
         if (N64) {
 #pragma unroll 1
           for (int ks = 0; ks < 2; ++ks)                        // ... of the 32-column atom
-            at_mma(tmem + key0, q64_lo + ks * 2, AT_HI_SW64, kl64 + ks * 2, AT_HI_SW64, idesc, (4 * N128 + ks) != 0);
+            at_mma(tmem + key0, q64_lo + ks * 2, AT_HI_SW64, kl64 + ks * 2, AT_HI_SW64, idesc, (4 * N128 + ks) != 0, leader);
         }
       };
       // 16-key steps [j0, j1) of O += P V; P from the tile's atoms (64-key, then 32-key) or, for the transposed tail
@@ -294,7 +311,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const int j2 = j - 4 * NP128;
           const bool wide = j2 < 0;
           const uint32_t a_lo = wide ? a128 + (j >> 2) * s128 + ((j & 3) << 1) : a64 + (j2 >> 1) * s64 + ((j2 & 1) << 1);
-          at_mma(tmem + o_col, a_lo, wide ? AT_HI_SW128 : AT_HI_SW64, v_lo + j * (16 * 64 >> 4), AT_HI_SW64, idesc_o, j != 0);
+          at_mma(tmem + o_col, a_lo, wide ? AT_HI_SW128 : AT_HI_SW64, v_lo + j * (16 * 64 >> 4), AT_HI_SW64, idesc_o, j != 0, leader);
         }
       };
       // Tail tile (tail_mode: the last query tile holds <= 8 rows, e.g. the 5 register tokens of S = 261): scores are
@@ -308,12 +325,12 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll 1
           for (int ks = 0; ks < 4 * N128; ++ks)
             at_mma(tmem + 16 * kt, k128_lo + (ks >> 2) * (KEYS * 128 >> 4) + kt * (128 * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
-                   q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc_t, ks != 0);
+                   q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc_t, ks != 0, leader);
           if (N64) {
 #pragma unroll 1
             for (int ks = 0; ks < 2; ++ks)
               at_mma(tmem + 16 * kt, k64_lo + kt * (128 * 64 >> 4) + ks * 2, AT_HI_SW64, q64_lo + ks * 2, AT_HI_SW64, idesc_t,
-                     (4 * N128 + ks) != 0);
+                     (4 * N128 + ks) != 0, leader);
           }
         }
       };
@@ -324,14 +341,14 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         at_wait(B.q_full, G0 & 1);
         tc_fence_after();
         issue_qk(0, idesc_x);                                 // (the S.X columns were handed back with px_full of the previous tile)
-        tc_commit(B.sx_full);
+        at_commit(B.sx_full, leader);
         if (KB > 0) {
           if (kv_box_rows < KEYS) at_wait(B.k1_full, itp);  // the K rows past the first box
           tc_fence_after();
           issue_qk(KA, idesc_y);
-          tc_commit(B.sy_full);
+          at_commit(B.sy_full, leader);
         }
-        tc_commit(B.q_free);
+        at_commit(B.q_free, leader);
         for (int t = 0; t < tiles; ++t) {
           const int G = G0 + t, ob = G % OB;
           const uint32_t o_col = AT_O_COL + ob * D;
@@ -343,12 +360,12 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           AT_T(14);
           if (tail_mode && t == tiles - 1) {                  // the whole transposed P arrives with one barrier
             issue_pv(0, KEYS / 16, o_col, true);
-            tc_commit(B.o_full + 8 * ob);
+            at_commit(B.o_full + 8 * ob, leader);
             break;
           }
           const bool next_tail = tail_mode && t + 2 == tiles;
           issue_pv(0, KA / 16, o_col, false);
-          if (KB == 0) tc_commit(B.o_full + 8 * ob);
+          if (KB == 0) at_commit(B.o_full + 8 * ob, leader);
           if (t + 1 < tiles) {
             at_wait(B.q_full, (G + 1) & 1);
             tc_fence_after();
@@ -358,8 +375,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             } else {
               issue_qk(0, idesc_x);
             }
-            tc_commit(B.sx_full);
-            if (KB == 0 || next_tail) tc_commit(B.q_free);    // (the transposed tail reads its Q rows in one go)
+            at_commit(B.sx_full, leader);
+            if (KB == 0 || next_tail) at_commit(B.q_free, leader);    // (the transposed tail reads its Q rows in one go)
           }
           if (KB > 0) {
             AT_T(15);
@@ -368,15 +385,15 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             AT_T(16);
             if (t + 1 < tiles && !next_tail) {                // the softmax warps wait on these scores next
               issue_qk(KA, idesc_y);
-              tc_commit(B.sy_full);
-              tc_commit(B.q_free);
+              at_commit(B.sy_full, leader);
+              at_commit(B.q_free, leader);
             }
             issue_pv(KA / 16, KEYS / 16, o_col, false);
-            tc_commit(B.o_full + 8 * ob);
+            at_commit(B.o_full + 8 * ob, leader);
           }
         }
         AT_T(19);
-        tc_commit(B.v_free);                                  // every MMA of this item has retired: V may be replaced
+        at_commit(B.v_free, leader);                                  // every MMA of this item has retired: V may be replaced
       }
     }
     AT_DUMP("mma");
