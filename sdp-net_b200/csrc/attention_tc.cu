@@ -188,7 +188,9 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   B.px_full = bar + 40; B.py_full = bar + 48; B.o_full = bar + 56; B.o_free = bar + 72; B.v_full = bar + 88; B.k1_full = bar + 96; B.v_free = bar + 112;
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + bar_off + 104);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the shuffle makes the warp index provably warp-uniform: role branches are then uniform branches and the code
+  // under them may use the uniform datapath)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   AT_TDECL
   const int C = h * D;
   // Items (image, head) are walked with a grid stride, images from the last to the first: the QKV GEMM wrote its rows
