@@ -280,40 +280,47 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ================= MMA issuer =================
     {
       const uint32_t leader = at_elect();
+      // (shuffles: the shared-memory window and TMEM base become provably uniform, so the descriptor arithmetic below
+      // runs on the uniform datapath instead of going through R2UR for every MMA)
+      const uint32_t sb = __shfl_sync(0xffffffffu, sbase, 0), tm = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc_x = at_idesc(AT_MT, KA, 0), idesc_y = at_idesc(AT_MT, KB > 0 ? KB : 16, 0);
       const uint32_t idesc_o = at_idesc(AT_MT, D, 1);
       // The MMAs here are short (48-72 tensor-core cycles), so the issue path is kept to a couple of integer adds
       // per instruction: descriptor low words (address >> 4 | LBO) are prepared once, high words are constants.
-      const uint32_t q128_lo = at_lo(sbase + q_off, 16), q64_lo = at_lo(sbase + q64_off, 16);
-      const uint32_t k128_lo = at_lo(sbase + k_off, 16), k64_lo = at_lo(sbase + k64_off, 16);
-      const uint32_t p128_lo = at_lo(sbase + p_off, 16), p64_lo = at_lo(sbase + p64_off, 16);
-      const uint32_t v_lo = at_lo(sbase + v_off, KEYS * 64);
+      const uint32_t q128_lo = at_lo(sb + q_off, 16), q64_lo = at_lo(sb + q64_off, 16);
+      const uint32_t k128_lo = at_lo(sb + k_off, 16), k64_lo = at_lo(sb + k64_off, 16);
+      const uint32_t p128_lo = at_lo(sb + p_off, 16), p64_lo = at_lo(sb + p64_off, 16);
+      const uint32_t v_lo = at_lo(sb + v_off, KEYS * 64);
       // Issue loops are rolled (a dozen instructions per MMA against 48-72 tensor-core cycles each): unrolled they were
       // a fifth of the kernel's code.
       auto issue_qk = [&](int key0, uint32_t idesc) {         // scores of keys [key0, key0 + N) -> TMEM column key0
         const uint32_t kl128 = k128_lo + key0 * (128 >> 4), kl64 = k64_lo + key0 * (64 >> 4);
-#pragma unroll 1
+#pragma unroll
         for (int ks = 0; ks < 4 * N128; ++ks)                   // 16 columns of a 64-column atom
-          at_mma(tmem + key0, q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
+          at_mma(tm + key0, q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
                  kl128 + (ks >> 2) * (KEYS * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc, ks != 0, leader);
         if (N64) {
-#pragma unroll 1
+#pragma unroll
           for (int ks = 0; ks < 2; ++ks)                        // ... of the 32-column atom
-            at_mma(tmem + key0, q64_lo + ks * 2, AT_HI_SW64, kl64 + ks * 2, AT_HI_SW64, idesc, (4 * N128 + ks) != 0, leader);
+            at_mma(tm + key0, q64_lo + ks * 2, AT_HI_SW64, kl64 + ks * 2, AT_HI_SW64, idesc, (4 * N128 + ks) != 0, leader);
         }
       };
       // 16-key steps [j0, j1) of O += P V; P from the tile's atoms (64-key, then 32-key) or, for the transposed tail
       // tile, from the compact 16-row atoms
-      const uint32_t pt128_lo = at_lo(sbase + pt_off, 16), pt64_lo = at_lo(sbase + pt_off + NP128 * 2048, 16);
+      const uint32_t pt128_lo = at_lo(sb + pt_off, 16), pt64_lo = at_lo(sb + pt_off + NP128 * 2048, 16);
       auto issue_pv = [&](int j0, int j1, uint32_t o_col, bool tail) {
         const uint32_t a128 = tail ? pt128_lo : p128_lo, a64 = tail ? pt64_lo : p64_lo;
         const uint32_t s128 = tail ? (2048 >> 4) : (AT_MT * 128 >> 4), s64 = tail ? (1024 >> 4) : (AT_MT * 64 >> 4);
+        const int jw = j1 < 4 * NP128 ? j1 : 4 * NP128;        // steps below jw read P from 64-key atoms
+#pragma unroll 4
+        for (int j = j0; j < jw; ++j)
+          at_mma(tm + o_col, a128 + (j >> 2) * s128 + ((j & 3) << 1), AT_HI_SW128, v_lo + j * (16 * 64 >> 4), AT_HI_SW64, idesc_o,
+                 j != 0, leader);
 #pragma unroll 1
-        for (int j = j0; j < j1; ++j) {
+        for (int j = j0 > jw ? j0 : jw; j < j1; ++j) {
           const int j2 = j - 4 * NP128;
-          const bool wide = j2 < 0;
-          const uint32_t a_lo = wide ? a128 + (j >> 2) * s128 + ((j & 3) << 1) : a64 + (j2 >> 1) * s64 + ((j2 & 1) << 1);
-          at_mma(tmem + o_col, a_lo, wide ? AT_HI_SW128 : AT_HI_SW64, v_lo + j * (16 * 64 >> 4), AT_HI_SW64, idesc_o, j != 0, leader);
+          at_mma(tm + o_col, a64 + (j2 >> 1) * s64 + ((j2 & 1) << 1), AT_HI_SW64, v_lo + j * (16 * 64 >> 4), AT_HI_SW64, idesc_o,
+                 j != 0, leader);
         }
       };
       // Tail tile (tail_mode: the last query tile holds <= 8 rows, e.g. the 5 register tokens of S = 261): scores are
@@ -324,14 +331,14 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       auto issue_st = [&]() {
 #pragma unroll 1
         for (int kt = 0; kt * 128 < KEYS; ++kt) {
-#pragma unroll 1
+#pragma unroll
           for (int ks = 0; ks < 4 * N128; ++ks)
-            at_mma(tmem + 16 * kt, k128_lo + (ks >> 2) * (KEYS * 128 >> 4) + kt * (128 * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
+            at_mma(tm + 16 * kt, k128_lo + (ks >> 2) * (KEYS * 128 >> 4) + kt * (128 * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
                    q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc_t, ks != 0, leader);
           if (N64) {
-#pragma unroll 1
+#pragma unroll
             for (int ks = 0; ks < 2; ++ks)
-              at_mma(tmem + 16 * kt, k64_lo + kt * (128 * 64 >> 4) + ks * 2, AT_HI_SW64, q64_lo + ks * 2, AT_HI_SW64, idesc_t,
+              at_mma(tm + 16 * kt, k64_lo + kt * (128 * 64 >> 4) + ks * 2, AT_HI_SW64, q64_lo + ks * 2, AT_HI_SW64, idesc_t,
                      (4 * N128 + ks) != 0, leader);
           }
         }
@@ -354,21 +361,22 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int t = 0; t < tiles; ++t) {
           const int G = G0 + t, ob = G % OB;
           const uint32_t o_col = AT_O_COL + ob * D;
-          if (G >= OB) at_wait(B.o_free + 8 * ob, ((G / OB) - 1) & 1);    // O(G - OB) has been read out
-          if (t == 0) at_wait(B.v_full, itp);
           AT_T(13);
           at_wait(B.px_full, G & 1);                        // P.X(t) in shared memory, S.X(t) consumed
           tc_fence_after();
           AT_T(14);
-          if (tail_mode && t == tiles - 1) {                  // the whole transposed P arrives with one barrier
+          const bool tail_tile = tail_mode && t == tiles - 1, next_tail = tail_mode && t + 2 == tiles;
+          if (G >= OB) at_wait(B.o_free + 8 * ob, ((G / OB) - 1) & 1);    // O(G - OB) has been read out
+          if (t == 0) at_wait(B.v_full, itp);
+          tc_fence_after();
+          if (tail_tile) {                                    // the whole transposed P arrives with one barrier
             issue_pv(0, KEYS / 16, o_col, true);
             at_commit(B.o_full + 8 * ob, leader);
             break;
           }
-          const bool next_tail = tail_mode && t + 2 == tiles;
           issue_pv(0, KA / 16, o_col, false);
           if (KB == 0) at_commit(B.o_full + 8 * ob, leader);
-          if (t + 1 < tiles) {
+          if (t + 1 < tiles) {                                  // the scores the softmax warps wait on next
             at_wait(B.q_full, (G + 1) & 1);
             tc_fence_after();
             if (next_tail) {
