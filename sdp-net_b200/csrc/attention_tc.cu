@@ -38,7 +38,6 @@ __device__ __forceinline__ void at_wait(uint32_t bar, uint32_t parity) {
 
 constexpr int AT_MT = 128;          // query rows per tile
 constexpr int AT_THREADS = 320;        // TMA warp, MMA warp, 8 softmax warps
-constexpr int AT_O_COL = 288;       // first TMEM column of the O accumulator(s); scores use [0, 288)
 
 // 64B-swizzled tiles: rows of 64 bytes (32 bf16), groups of 8 rows = 512 bytes.
 // K-major operand descriptor (A, and B = K): layout type 4 (SWIZZLE_64B), SBO = 512.
@@ -161,7 +160,6 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   // a slice over all banks (64B-swizzled rows collide two by two), so they use 64-column atoms wherever 64
   // columns are left and a 32-column atom for the rest (d = 96: one of each).
   constexpr int N128 = D / 64, N64 = (D % 64) / 32;
-  constexpr int OB = (AT_O_COL + 2 * D <= 512) ? 2 : 1;       // O accumulators in TMEM
   extern __shared__ uint8_t at_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -170,6 +168,15 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (KA == 0) KA = (KEYS / 2) & ~31;
   if (KA == 0) KA = KEYS;
   const int KB = KEYS - KA;                    // keys in the Y half (may be 0)
+  // TMEM columns.  When they fit, the X half has TWO score buffers (tile G uses buffer G & 1), so the tensor core
+  // computes S.X of the next tile -- across item boundaries too -- while the softmax warps are still reading this
+  // one, and a single O accumulator (the softmax warps drain O(t - 1) before they publish P.X(t), so the second one
+  // bought nothing):  [X0 | X1 | Y | O]  = 128 + 128 + 144 (-> 416) + 96 = 512 columns at S = 261, d = 96.
+  const int sw2 = (2 * KA + KB + 31) & ~31;
+  const int XB = (KB > 0 && sw2 + D <= 512) ? 2 : 1;
+  const uint32_t y_col = XB * KA;              // column of key KA
+  const uint32_t o_base = XB == 2 ? sw2 : ((KEYS + 31) & ~31);
+  const int OB = o_base + 2 * D <= 512 ? 2 : 1;          // O accumulators
   // tail tile P^T: compact atoms [NP128][16 rows][128 B] [NP64][16 rows][64 B].  First in the layout: the P V MMAs of
   // the tail tile are M = 128 wide and read 112 rows past each 16-row atom (their results land in TMEM lanes nobody
   // reads), which must still be shared memory of this CTA -- the Q / K tiles behind it.
@@ -202,7 +209,6 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   // Per-barrier completion counts.  Per tile (global tile index G = item iteration * tiles + t): q_full, q_free,
   // sx_full, px_full; o_full / o_free alternate between the OB accumulators with G.  sy_full / py_full skip the
   // transposed tail tile (HPT completions per item).  Per item: kv_full, k1_full, v_full.
-  const int HPT = tail_mode ? tiles - 1 : tiles;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -250,7 +256,9 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int row0 = img * S, qcol = head * D, kcol = C + head * D, vcol = 2 * C + head * D;
 #pragma unroll 1
         for (int t = 0; t < tiles; ++t, ++G) {
+          AT_T(1);
           if (G > 0) at_wait(B.q_free, (G - 1) & 1);          // the scores of the previous tile have been issued and retired
+          AT_T(2);
           mbar_expect_tx(B.q_full, NA * AT_MT * 64);
 #pragma unroll 1
           for (int a = 0; a < N128; ++a)
@@ -266,7 +274,9 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               tma_load_2d(sbase + k_off + (a * KEYS + r) * 128, &tmK, kbar, kcol + 64 * a, row0 + r);
             if (N64) tma_load_2d(sbase + k64_off + r * 64, &tmKV, kbar, kcol + 64 * N128, row0 + r);
           }
+          AT_T(3);
           if (itn > 0) at_wait(B.v_free, (itn - 1) & 1);
+          AT_T(4);
           mbar_expect_tx(B.v_full, NA * KEYS * 64);
 #pragma unroll 1
           for (int a = 0; a < NA; ++a)
@@ -275,6 +285,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               tma_load_2d(sbase + v_off + (a * KEYS + r) * 64, &tmKV, B.v_full, vcol + 32 * a, row0 + r);
         }
       }
+      AT_DUMP("prd");
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
@@ -293,16 +304,16 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t v_lo = at_lo(sb + v_off, KEYS * 64);
       // Issue loops are rolled (a dozen instructions per MMA against 48-72 tensor-core cycles each): unrolled they were
       // a fifth of the kernel's code.
-      auto issue_qk = [&](int key0, uint32_t idesc) {         // scores of keys [key0, key0 + N) -> TMEM column key0
+      auto issue_qk = [&](uint32_t dcol, int key0, uint32_t idesc) {   // scores of keys [key0, key0 + N) -> TMEM column dcol
         const uint32_t kl128 = k128_lo + key0 * (128 >> 4), kl64 = k64_lo + key0 * (64 >> 4);
 #pragma unroll
         for (int ks = 0; ks < 4 * N128; ++ks)                   // 16 columns of a 64-column atom
-          at_mma(tm + key0, q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
+          at_mma(tm + dcol, q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
                  kl128 + (ks >> 2) * (KEYS * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc, ks != 0, leader);
         if (N64) {
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks)                        // ... of the 32-column atom
-            at_mma(tm + key0, q64_lo + ks * 2, AT_HI_SW64, kl64 + ks * 2, AT_HI_SW64, idesc, (4 * N128 + ks) != 0, leader);
+            at_mma(tm + dcol, q64_lo + ks * 2, AT_HI_SW64, kl64 + ks * 2, AT_HI_SW64, idesc, (4 * N128 + ks) != 0, leader);
         }
       };
       // 16-key steps [j0, j1) of O += P V; P from the tile's atoms (64-key, then 32-key) or, for the transposed tail
@@ -328,82 +339,97 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // softmax is spread over all lanes by key instead of 5 live lanes doing a 272-wide row each; the warps write
       // P back as rows 0..15 of compact 2 KB atoms and the usual P V follows.
       const uint32_t idesc_t = at_idesc(AT_MT, 16, 0);
-      auto issue_st = [&]() {
+      auto issue_st = [&](uint32_t dcol) {
 #pragma unroll 1
         for (int kt = 0; kt * 128 < KEYS; ++kt) {
 #pragma unroll
           for (int ks = 0; ks < 4 * N128; ++ks)
-            at_mma(tm + 16 * kt, k128_lo + (ks >> 2) * (KEYS * 128 >> 4) + kt * (128 * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
+            at_mma(tm + dcol + 16 * kt, k128_lo + (ks >> 2) * (KEYS * 128 >> 4) + kt * (128 * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128,
                    q128_lo + (ks >> 2) * (AT_MT * 128 >> 4) + (ks & 3) * 2, AT_HI_SW128, idesc_t, ks != 0, leader);
           if (N64) {
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
-              at_mma(tm + 16 * kt, k64_lo + kt * (128 * 64 >> 4) + ks * 2, AT_HI_SW64, q64_lo + ks * 2, AT_HI_SW64, idesc_t,
+              at_mma(tm + dcol + 16 * kt, k64_lo + kt * (128 * 64 >> 4) + ks * 2, AT_HI_SW64, q64_lo + ks * 2, AT_HI_SW64, idesc_t,
                      (4 * N128 + ks) != 0, leader);
           }
         }
       };
-      int G0 = 0, Y0 = 0, itn = 0;                            // global tile index / Y-half index of the item's tile 0
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, G0 += tiles, Y0 += HPT, ++itn) {
-        const uint32_t itp = itn & 1;
-        at_wait(B.kv_full, itp);
-        at_wait(B.q_full, G0 & 1);
+      // Scores of tile Gn.  `first`: the tile opens an item (its K arrives with kv_full / k1_full of parity kpar);
+      // `tail`: transposed tail tile (reads all of K and its Q rows in one go, has no Y half).
+      auto issue_scores_x = [&](int Gn, bool first, bool tail, uint32_t kpar) {
+        AT_T(10);
+        at_wait(B.q_full, Gn & 1);
+        AT_T(11);
+        if (first) at_wait(B.kv_full, kpar);
+        if (tail && kv_box_rows < KEYS) at_wait(B.k1_full, kpar);
         tc_fence_after();
-        issue_qk(0, idesc_x);                                 // (the S.X columns were handed back with px_full of the previous tile)
+        const uint32_t xc = (XB == 2 && (Gn & 1)) ? KA : 0;
+        if (tail) issue_st(xc);
+        else issue_qk(xc, 0, idesc_x);
         at_commit(B.sx_full, leader);
-        if (KB > 0) {
-          if (kv_box_rows < KEYS) at_wait(B.k1_full, itp);  // the K rows past the first box
-          tc_fence_after();
-          issue_qk(KA, idesc_y);
-          at_commit(B.sy_full, leader);
-        }
+        if (KB == 0 || tail) at_commit(B.q_free, leader);
+      };
+      auto issue_scores_y = [&](bool first, uint32_t kpar) {
+        if (first && kv_box_rows < KEYS) at_wait(B.k1_full, kpar);  // the K rows past the first box
+        tc_fence_after();
+        issue_qk(y_col, KA, idesc_y);
+        at_commit(B.sy_full, leader);
         at_commit(B.q_free, leader);
-        for (int t = 0; t < tiles; ++t) {
-          const int G = G0 + t, ob = G % OB;
-          const uint32_t o_col = AT_O_COL + ob * D;
+      };
+      // One flat sequence of tiles over the items of this CTA.  Step G: [X scores of tile G + 1 when they have their own
+      // buffer] - P.X(G) ready -> P V over the X keys [- X scores of G + 1 into the buffer just released] - P.Y(G)
+      // ready -> Y scores of G + 1, P V over the Y keys.  The scores of an item's first tile are issued during the
+      // previous item's last step.
+      int G = 0, itn = 0, yc = 0;                             // global tile index, item count, Y halves so far
+      if (blockIdx.x < n_items) {
+        issue_scores_x(0, true, false, 0);
+        if (KB > 0) issue_scores_y(true, 0);
+      }
+#pragma unroll 1
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++itn) {
+        const uint32_t itp = itn & 1;
+        const bool more = item + (int)gridDim.x < n_items;
+#pragma unroll 1
+        for (int t = 0; t < tiles; ++t, ++G) {
+          const bool last = t == tiles - 1, cur_tail = tail_mode && last, next_tail = tail_mode && t + 2 == tiles;
+          const bool has_next = !last || more;
+          const uint32_t npar = last ? itp ^ 1 : itp;         // (the next tile opens the next item)
+          if (XB == 2 && has_next) issue_scores_x(G + 1, last, next_tail, npar);
           AT_T(13);
-          at_wait(B.px_full, G & 1);                        // P.X(t) in shared memory, S.X(t) consumed
-          tc_fence_after();
+          at_wait(B.px_full, G & 1);                          // P.X(t) in shared memory, S.X(t) consumed
           AT_T(14);
-          const bool tail_tile = tail_mode && t == tiles - 1, next_tail = tail_mode && t + 2 == tiles;
-          if (G >= OB) at_wait(B.o_free + 8 * ob, ((G / OB) - 1) & 1);    // O(G - OB) has been read out
+          const int ob = OB == 2 ? (G & 1) : 0;
+          const uint32_t o_col = o_base + ob * D;
+          if (G >= OB) at_wait(B.o_free + 8 * ob, ((OB == 2 ? (G >> 1) : G) - 1) & 1);    // O(G - OB) has been read out
           if (t == 0) at_wait(B.v_full, itp);
           tc_fence_after();
-          if (tail_tile) {                                    // the whole transposed P arrives with one barrier
+          if (cur_tail) {                                     // the whole transposed P arrives with one barrier
             issue_pv(0, KEYS / 16, o_col, true);
             at_commit(B.o_full + 8 * ob, leader);
-            break;
+          } else {
+            issue_pv(0, KA / 16, o_col, false);
+            if (KB == 0) at_commit(B.o_full + 8 * ob, leader);
           }
-          issue_pv(0, KA / 16, o_col, false);
-          if (KB == 0) at_commit(B.o_full + 8 * ob, leader);
-          if (t + 1 < tiles) {                                  // the scores the softmax warps wait on next
-            at_wait(B.q_full, (G + 1) & 1);
-            tc_fence_after();
-            if (next_tail) {
-              if (kv_box_rows < KEYS) at_wait(B.k1_full, itp);
-              issue_st();
-            } else {
-              issue_qk(0, idesc_x);
-            }
-            at_commit(B.sx_full, leader);
-            if (KB == 0 || next_tail) at_commit(B.q_free, leader);    // (the transposed tail reads its Q rows in one go)
-          }
-          if (KB > 0) {
+          if (XB == 1 && has_next) issue_scores_x(G + 1, last, next_tail, npar);
+          const bool cur_y = KB > 0 && !cur_tail;
+          if (cur_y) {
             AT_T(15);
-            at_wait(B.py_full, (Y0 + t) & 1);
-            tc_fence_after();
+            at_wait(B.py_full, yc & 1);
+            ++yc;
             AT_T(16);
-            if (t + 1 < tiles && !next_tail) {                // the softmax warps wait on these scores next
-              issue_qk(KA, idesc_y);
-              at_commit(B.sy_full, leader);
-              at_commit(B.q_free, leader);
-            }
+          }
+          // (the Y columns are free: the P.Y barrier of the last tile that had a Y half has been seen)
+          if (KB > 0 && has_next && !next_tail) issue_scores_y(last, npar);
+          if (cur_y) {
+            tc_fence_after();
             issue_pv(KA / 16, KEYS / 16, o_col, false);
             at_commit(B.o_full + 8 * ob, leader);
           }
+          if (last) {
+            AT_T(19);
+            at_commit(B.v_free, leader);                      // every MMA of this item has been issued: V may be replaced once they retire
+          }
         }
-        AT_T(19);
-        at_commit(B.v_free, leader);                                  // every MMA of this item has retired: V may be replaced
       }
     }
     AT_DUMP("mma");
@@ -413,7 +439,6 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // Eight warps: TMEM lane quadrant = warp % 4 (a warp only reaches its own 32 lanes), so two warps share every
     // query row; warp group g = 0/1 takes the first / second part of each key half and of the O columns.  The
     // two partial maxima and sums of a row meet in shared memory across a 64-thread named barrier.
-    int b = 0, head = 0, G0 = 0, Y0 = 0;                      // current item: image, head, global index of its tile 0 / Y half 0
     const int quad = warp & 3;
     const int g = (warp - 2) >> 2;
     const int r = quad * 32 + lane;                           // row inside the tile = TMEM lane
@@ -441,25 +466,27 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const bool stage_ok = (KA & 63) == 0 && ya == 64 && KB >= 128 && KA / 64 + 2 <= NP128;
     const uint32_t stage = sbase + p_off + (KA / 64 + g) * AT_MT * 128 + quad * 32 * 128 + lane * (D / 2) * 2;
 
-    auto pass1 = [&](int key0, int nkeys, float m) {          // row maximum of this group's keys
+    // (key kk of the X half sits in TMEM column xc + kk, xc = this tile's X buffer; key kk of the Y half in column
+    // kk + (XB - 1) KA)
+    auto pass1 = [&](int key0, int nkeys, float m, uint32_t coff) {          // row maximum of this group's keys
       float mx[4] = {m, m, m, m};
 #pragma unroll 1
       for (int k = 0; k < nkeys; k += 32) {                   // one chunk per TMEM round trip: two in flight were measured
         const int n = nkeys - k < 32 ? nkeys - k : 32, kk = key0 + k;   // at 1.09 vs 0.79 ms (spills at the 168-register cap)
         float v0[32];
-        at_ld_chunk(t_lane + kk, n, v0);
+        at_ld_chunk(t_lane + coff + kk, n, v0);
         tmem_ld_wait();
         at_max_chunk(v0, min(n, S - kk), mx);
       }
       return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
     };
-    auto pass2 = [&](int key0, int nkeys, float nm) {         // p = 2^(s*scale - max*scale) -> P (bf16), row sum
+    auto pass2 = [&](int key0, int nkeys, float nm, uint32_t coff) {         // p = 2^(s*scale - max*scale) -> P (bf16), row sum
       float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 1
       for (int k = 0; k < nkeys; k += 32) {
         const int n = nkeys - k < 32 ? nkeys - k : 32, kk = key0 + k;
         float v0[32];
-        at_ld_chunk(t_lane + kk, n, v0);
+        at_ld_chunk(t_lane + coff + kk, n, v0);
         tmem_ld_wait();
         uint32_t prow, ch0, sw;
         p_place(kk, prow, ch0, sw);
@@ -474,9 +501,10 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (lane == 0) mbar_arrive(barrier);
     };
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
-    auto epilogue = [&](int t, bool tail) {                   // this group's half of O(t) / row sum -> bf16 -> global
+    // this group's half of O / row sum -> bf16 -> global, for tile G = tile t of image b, head `head`
+    auto epilogue = [&](int G, int b, int head, int t, bool tail) {
       constexpr int HALF = D / 2;
-      const int G = G0 + t, ob = G % OB;
+      const int ob = OB == 2 ? (G & 1) : 0;
       const float *xs = xch + 512 + (G & 1) * 256;
       const float den = tail ? xs[r & 7] : xs[r] + xs[128 + r];    // (transposed tail tile: one sum per query row)
       const float inv = 1.0f / den;
@@ -484,7 +512,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       bf16 *orow = out + ((long long)b * S + row) * C + head * D + g * HALF;
       const bool warp_live = t * AT_MT + quad * 32 < S;
       if (warp_live) {
-        at_wait(B.o_full + 8 * ob, (G / OB) & 1);
+        at_wait(B.o_full + 8 * ob, (OB == 2 ? (G >> 1) : G) & 1);
         tc_fence_after();
         AT_T(40);
       }
@@ -501,13 +529,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       constexpr int REST = HALF - 32;                         // 0, 16 or 32 columns after the first 32
       if (warp_live) {
         float v[32];
-        tmem_ld32(t_lane + AT_O_COL + ob * D + g * HALF, v);
+        tmem_ld32(t_lane + o_base + ob * D + g * HALF, v);
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 4; ++c) store8(&v[8 * c], 8 * c);
         if constexpr (REST > 0) {
-          if constexpr (REST == 32) tmem_ld32(t_lane + AT_O_COL + ob * D + g * HALF + 32, v);
-          else tmem_ld16(t_lane + AT_O_COL + ob * D + g * HALF + 32, v);
+          if constexpr (REST == 32) tmem_ld32(t_lane + o_base + ob * D + g * HALF + 32, v);
+          else tmem_ld16(t_lane + o_base + ob * D + g * HALF + 32, v);
           tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < REST / 8; ++c) store8(&v[8 * c], 32 + 8 * c);
@@ -531,15 +559,15 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // softmax: warp w then owns query row w -- two keys per lane and 64-key step, one max and one sum reduction per
     // row -- and writes P^T (bf16 pairs) into the compact atoms.
     float *tsc = xch + 1024;
-    auto tail_scores = [&](int t) {
+    auto tail_scores = [&](int G, uint32_t xc) {
       AT_T(49);
-      at_wait(B.sx_full, (G0 + t) & 1);
+      at_wait(B.sx_full, G & 1);
       tc_fence_after();
       AT_T(50);
 #pragma unroll 1
       for (int kt = g; kt * 128 < KEYS; kt += 2) {
         float v[8];
-        tmem_ld8(t_lane + 16 * kt, v);
+        tmem_ld8(t_lane + xc + 16 * kt, v);
         tmem_ld_wait();
         const int key = 128 * kt + 32 * quad + lane;
         if (key < KEYS) {
@@ -549,7 +577,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       AT_T(51);
     };
-    auto tail_softmax = [&](int t) {
+    auto tail_softmax = [&](int G) {
       const int qi = warp - 2;
       if (qi < S - (tiles - 1) * AT_MT) {
         const float *row = tsc + qi * KEYS;
@@ -583,40 +611,49 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) xch[512 + ((G0 + t) & 1) * 256 + qi] = sum;
+        if (lane == 0) xch[512 + (G & 1) * 256 + qi] = sum;
       }
       AT_T(54);
     };
 
+    // One flat sequence of tiles over the items of this CTA; iteration G: scores of tile G (row maxima), output of tile
+    // G - 1 -- across item boundaries too, so that nobody waits for the P V of an item's last tile (the transposed tail,
+    // whose few live rows belong to the two warps of one lane quadrant) -- then the probabilities of tile G.
+    int item = blockIdx.x, t = 0, b = 0, head = 0, yc = 0;    // current tile; Y halves so far
+    int pb = 0, phead = 0, pt = 0;                            // previous tile
+    bool ptail = false;
 #pragma unroll 1
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, G0 += tiles, Y0 += HPT) {
-    b = item_image(item);
-    head = item % h;
-#pragma unroll 1
-    for (int t = 0; t <= tiles; ++t) {                        // iteration t: scores of tile t, output of tile t - 1
-      const bool is_tail = tail_mode && t == tiles - 1, after_tail = tail_mode && t == tiles;
-      const bool live = t < tiles && t * AT_MT + quad * 32 < S;   // warps whose rows are all past the sequence idle
-      float *xm = xch + ((G0 + t) & 1) * 256, *xs = xch + 512 + ((G0 + t) & 1) * 256;
+    for (int G = 0;; ++G) {
+      const bool cur = item < n_items;
+      if (!cur && G == 0) break;
+      if (cur && t == 0) {
+        b = item_image(item);
+        head = item - (item / h) * h;
+      }
+      const bool is_tail = cur && tail_mode && t == tiles - 1;
+      const bool live = t * AT_MT + quad * 32 < S;            // warps whose rows are all past the sequence idle
+      float *xm = xch + (G & 1) * 256, *xs = xch + 512 + (G & 1) * 256;
       float m = -INFINITY;
+      const uint32_t xc = (XB == 2 && (G & 1)) ? KA : 0;      // this tile's X score buffer
       if (is_tail) {
-        tail_scores(t);
-      } else if (t < tiles) {
+        tail_scores(G, xc);
+      } else if (cur) {
 #pragma unroll 1
         for (int hf = 0; hf < (KB > 0 ? 2 : 1); ++hf) {       // X then Y: the Y scores land while X is scanned
           AT_T(20 + hf);
-          at_wait(hf ? B.sy_full : B.sx_full, (hf ? Y0 + t : G0 + t) & 1);
+          at_wait(hf ? B.sy_full : B.sx_full, (hf ? yc : G) & 1);
           tc_fence_after();
           AT_T(22 + hf);
-          if (live) m = pass1(hf ? yk0 : xk0, hf ? yn : xn, m);
+          if (live) m = pass1(hf ? yk0 : xk0, hf ? yn : xn, m, hf ? y_col - KA : xc);
           AT_T(24 + hf);
         }
         xm[g * 128 + r] = m;
       }
-      // partial maxima of tile t, partial sums of tile t - 1: shared by the two warps of a row -- except around the
+      // partial maxima of tile G, partial sums of tile G - 1: shared by the two warps of a row -- except around a
       // transposed tail tile, whose score table and row sums are shared by all eight softmax warps
-      if (is_tail || after_tail) {
+      if (is_tail || ptail) {
         asm volatile("bar.sync 9, 256;" ::: "memory");
-        if (after_tail && stage_ok) {                         // O(t - 2) was staged in the tail iteration with no P pass since:
+        if (ptail && stage_ok) {                              // O(G - 2) was staged in the tail iteration with no P pass since:
           if (lane == 0) bulk_wait_read<0>();                 // its TMA store must have read the staging rows
           __syncwarp();
         }
@@ -624,33 +661,42 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         pair_sync();
       }
       AT_T(26);
-      if (t > 0) epilogue(t - 1, after_tail);
+      if (G > 0) epilogue(G - 1, pb, phead, pt, ptail);
       AT_T(27);
+      if (!cur) break;
       if (is_tail) {
-        tail_softmax(t);
+        tail_softmax(G);
         publish(B.px_full);
         AT_T(55);
-      } else if (t < tiles) {
+      } else {
         m = fmaxf(m, xm[(g ^ 1) * 128 + r]);
         const float nm = -m * scale_log2;
         float sum = 0.0f;
 #pragma unroll 1
         for (int hf = 0; hf < (KB > 0 ? 2 : 1); ++hf) {
-          if (hf && stage_ok) {                               // the staged O(t - 1) must have left shared memory
+          if (hf && stage_ok) {                               // the staged O(G - 1) must have left shared memory
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
           }
-          if (live) sum += pass2(hf ? yk0 : xk0, hf ? yn : xn, nm);
+          if (live) sum += pass2(hf ? yk0 : xk0, hf ? yn : xn, nm, hf ? y_col - KA : xc);
           AT_T(28 + hf);
           publish(hf ? B.py_full : B.px_full);
           AT_T(30 + hf);
         }
         xs[g * 128 + r] = sum;
+        if (KB > 0) ++yc;
+      }
+      pb = b;
+      phead = head;
+      pt = t;
+      ptail = is_tail;
+      if (++t == tiles) {
+        t = 0;
+        item += gridDim.x;
       }
     }
-    }
     if (stage_ok && lane == 0) bulk_wait_read<0>();          // shared memory outlives the last output store
-    if (warp == 2 || warp == 6) AT_DUMP("smx");
+    AT_DUMP("smx");
   }
 
   tc_fence_before();
