@@ -48,7 +48,10 @@ def main():
         ("pw +gelu +res(hi+lo) +pass +stats", C, C, lambda: sdp.ops.gemm(qkv[:, :C], W["o"], hi, act="gelu", residual=hi, stats_out=stats,
                                                                        residual_lo=lo, out_lo=lo, pass_rows=(S, R))),
     ]
+    only = os.environ.get("GEMM_FLAVORS_ONLY")               # e.g. "ff1": the flavours whose name starts with it
     for name, N, K, fn in flavours:
+        if only and not name.startswith(only):
+            continue
         # keep the stream finite over thousands of in-place accumulations
         hi.copy_(x.bfloat16())
         ms, clk = sustained(fn, secs)
