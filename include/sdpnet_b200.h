@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SDPNET_B200_ABI_VERSION 6
+#define SDPNET_B200_ABI_VERSION 7
 
 typedef enum { SDP_F32 = 0, SDP_BF16 = 1 } sdp_dtype;
 
@@ -188,6 +188,16 @@ int sdp_attention(const void *qkv, const float *qn_w, const float *qn_b, const f
                   const float *kn_b, void *out, int B, int S, int h, int d, float eps, int dtype,
                   void *stream);
 
+/* The same attention (layers.py:289-291) for q / k whose per-head LayerNorm (layers.py:286) has already been applied
+ * (the QKV GEMM's head-norm epilogue), with a caller-supplied bound: |q_i . k_j| / sqrt(d) <= score_bound (nats) for
+ * every pair.  LayerNorm outputs have a known norm -- |LN(x)|_2 <= max|gamma| sqrt(d) + |beta|_2 -- so the bound follows
+ * from the four parameter vectors alone.  With it the softmax needs no row maximum (it is invariant to the exponent
+ * reference; exp(s) cannot overflow) and the tcgen05 kernel reads every score from TMEM once instead of twice.
+ * score_bound == 0 (unknown) or above 60 nats, or a shape the tcgen05 kernel does not cover: behaves exactly like
+ * sdp_attention with qn_w == NULL.  A bound that does not hold makes the result undefined (inf / NaN), never out of bounds. */
+int sdp_attention_bounded(const void *qkv, void *out, int B, int S, int h, int d, float score_bound, int dtype,
+                          void *stream);
+
 /* Head front (layers.py:464 `registers.mean(-2)` + LN at :445/:449, or AdaptiveAvgPool at
  * :457): out[b, :] = LN(mean over rows [row0, row0+nrows) of image b), LN skipped when
  * ln_w == NULL.  act [B, S, C] (+ act_lo, the lo plane of a split bf16 stream, or NULL) -> out [B, ldo]. */
@@ -259,6 +269,7 @@ typedef struct {          /* one EncoderLayer, layers.py:216-257 */
   const void *w_ff1; const float *b_ff1;           /* [mC, C], [mC] */
   const void *w_ff2; const float *b_ff2;           /* [C, mC], [C] */
   const float *s_qkv, *t_qkv, *s_ff1, *t_ff1;      /* LN-fold vectors ([3C], [3C], [mC], [mC]) or NULL */
+  float qk_score_bound;                            /* bound on |q.k|/sqrt(d) after q_norm / k_norm (see sdp_attention_bounded); 0 = unknown */
 } sdp_encoder_weights;
 
 typedef struct {          /* one ConvMixer, layers.py:63-99 */

@@ -47,7 +47,7 @@ class GemmArgs(C.Structure):
 class EncoderWeights(C.Structure):
     _fields_ = [(n, c_void_p) for n in (
         "norm1_w", "norm1_b", "norm2_w", "norm2_b", "qn_w", "qn_b", "kn_w", "kn_b",
-        "w_qkv", "w_o", "w_ff1", "b_ff1", "w_ff2", "b_ff2", "s_qkv", "t_qkv", "s_ff1", "t_ff1")]
+        "w_qkv", "w_o", "w_ff1", "b_ff1", "w_ff2", "b_ff2", "s_qkv", "t_qkv", "s_ff1", "t_ff1")] + [("qk_score_bound", c_float)]
 
 
 class MixerWeights(C.Structure):
@@ -97,6 +97,7 @@ SYMBOLS = {
     "sdp_ln_dwconv_slab": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "sdp_ln_dwconv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "sdp_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "sdp_attention_bounded": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "sdp_pool_ln": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_i64, c_void_p]),
     "sdp_tokens_from_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sdp_tokens_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -129,7 +130,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)   # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if handle.sdp_abi_version() != 6:
+        if handle.sdp_abi_version() != 7:
             raise SdpNetLibraryError("libsdpnet_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

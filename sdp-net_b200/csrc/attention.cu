@@ -675,15 +675,15 @@ static int launch_attn_simt(const void *qkv, const float *qn_w, const float *qn_
   return 0;
 }
 
-int attention_tc5(const void *qkv, void *out, int B, int S, int h, int d, cudaStream_t st);   // attention_tc.cu
+int attention_tc5(const void *qkv, void *out, int B, int S, int h, int d, float score_bound, cudaStream_t st);   // attention_tc.cu
 
 }  // namespace sdp
 
 using namespace sdp;
 
-extern "C" int sdp_attention(const void *qkv, const float *qn_w, const float *qn_b, const float *kn_w,
-                             const float *kn_b, void *out, int B, int S, int h, int d, float eps, int dtype,
-                             void *stream) {
+static int attention_dispatch(const void *qkv, const float *qn_w, const float *qn_b, const float *kn_w,
+                              const float *kn_b, void *out, int B, int S, int h, int d, float eps, int dtype,
+                              float score_bound, void *stream) {
   SDP_CHECK(qkv && out && B > 0 && S > 0 && h > 0 && d > 0, "sdp_attention: bad arguments");
   SDP_CHECK((qn_w == nullptr) == (kn_w == nullptr) && (qn_w == nullptr) == (qn_b == nullptr) &&
                 (kn_w == nullptr) == (kn_b == nullptr),
@@ -693,7 +693,7 @@ extern "C" int sdp_attention(const void *qkv, const float *qn_w, const float *qn
     const bool aligned = (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && ((long long)h * d) % 8 == 0;
     int rc = -1;
     if (aligned && qn_w == nullptr) {
-      rc = attention_tc5(qkv, out, B, S, h, d, st);      // tcgen05 path: d in {64, 96, 128}, S <= 288
+      rc = attention_tc5(qkv, out, B, S, h, d, score_bound, st);      // tcgen05 path: d in {64, 96, 128}, S <= 288
       if (rc >= 0) return rc;
     }
     if (aligned && qn_w == nullptr) {
@@ -723,3 +723,16 @@ extern "C" int sdp_attention(const void *qkv, const float *qn_w, const float *qn
   SDP_CHECK(dtype == SDP_F32, "sdp_attention: unknown dtype %d", dtype);
   return launch_attn_simt<float>(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, d, eps, st);
 }
+
+extern "C" int sdp_attention(const void *qkv, const float *qn_w, const float *qn_b, const float *kn_w,
+                             const float *kn_b, void *out, int B, int S, int h, int d, float eps, int dtype,
+                             void *stream) {
+  return attention_dispatch(qkv, qn_w, qn_b, kn_w, kn_b, out, B, S, h, d, eps, dtype, 0.0f, stream);
+}
+
+extern "C" int sdp_attention_bounded(const void *qkv, void *out, int B, int S, int h, int d, float score_bound,
+                                     int dtype, void *stream) {
+  SDP_CHECK(score_bound >= 0.0f && score_bound == score_bound, "sdp_attention_bounded: score_bound must be >= 0 (0 = unknown)");
+  return attention_dispatch(qkv, nullptr, nullptr, nullptr, nullptr, out, B, S, h, d, 0.0f, dtype, score_bound, stream);
+}
+

@@ -38,6 +38,7 @@ __device__ __forceinline__ void at_wait(uint32_t bar, uint32_t parity) {
 
 constexpr int AT_MT = 128;          // query rows per tile
 constexpr int AT_THREADS = 320;        // TMA warp, MMA warp, 8 softmax warps
+constexpr float AT_ONE_PASS_BOUND = 60.0f;   // largest |score| (nats) the one-pass softmax accepts
 
 // 64B-swizzled tiles: rows of 64 bytes (32 bf16), groups of 8 rows = 512 bytes.
 // K-major operand descriptor (A, and B = K): layout type 4 (SWIZZLE_64B), SBO = 512.
@@ -121,20 +122,33 @@ __device__ __forceinline__ void at_max_chunk(float (&v)[32], int lim, float (&mx
 #pragma unroll
   for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], v[j]);
 }
+// RS: the row sum is taken over the bf16-ROUNDED probabilities, the values the P V MMA multiplies: numerator and
+// denominator then carry the same rounding (a row dominated by one key comes out exact whatever the exponent
+// reference; with the row maximum as reference the dominant p is 1.0 and exact anyway).
+template <bool RS>
 __device__ __forceinline__ void at_exp_chunk(float (&v)[32], int lim, float scale_log2, float nm, float (&sum)[4],
                                              uint32_t prow, uint32_t ch0, uint32_t sw) {
   at_mask_chunk(v, lim);
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     v[j] = fast_ex2(fmaf(v[j], scale_log2, nm));
-    sum[j & 3] += v[j];
+    if constexpr (!RS) sum[j & 3] += v[j];
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {                               // 64 B of the row's P atom at swizzled 16-byte chunks
-    const uint32_t p0 = pack_bf16x2(v[8 * c], v[8 * c + 1]), p1 = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
-    const uint32_t p2 = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), p3 = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (((ch0 + c) ^ sw) << 4)), "r"(p0), "r"(p1), "r"(p2),
-                 "r"(p3)
+    const uint32_t pw[4] = {pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                            pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7])};
+    if constexpr (RS) {                                       // one packed add per rounded pair
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint64_t pr = pack_f32x2(__uint_as_float(pw[q] << 16), __uint_as_float(pw[q] & 0xffff0000u));
+        uint64_t acc = pack_f32x2(sum[2 * (q & 1)], sum[2 * (q & 1) + 1]);
+        acc = add_f32x2(acc, pr);
+        unpack_f32x2(acc, sum[2 * (q & 1)], sum[2 * (q & 1) + 1]);
+      }
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (((ch0 + c) ^ sw) << 4)), "r"(pw[0]), "r"(pw[1]), "r"(pw[2]),
+                 "r"(pw[3])
                  : "memory");
   }
 }
@@ -145,10 +159,10 @@ __device__ __forceinline__ void at_exp_chunk(float (&v)[32], int lim, float scal
 //            same two instalments, so the tensor core works underneath the exponentials
 //   softmax: max over X, [O(t-1) -> global], max over Y, exp/sum/P over X, exp/sum/P over Y
 struct AtBars {
-  uint32_t kv_full, q_full, q_free, sx_full, sy_full, px_full, py_full, o_full, o_free, v_full, k1_full, v_free, sx_full1;   // o_*: two barriers each; sx_full1: second X buffer
+  uint32_t kv_full, q_full, q_free, sx_full, sy_full, px_full, py_full, o_full, o_free, v_full, k1_full, v_free, sx_full1, px_free;   // o_*: two barriers each; sx_full1: second X buffer; px_free: one-pass kernels only
 };
 
-template <int D, int SQ>
+template <int D, int SQ, bool OP>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ32,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmKV,
@@ -203,6 +217,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   AtBars B;
   B.kv_full = bar; B.q_full = bar + 8; B.q_free = bar + 16; B.sx_full = bar + 24; B.sy_full = bar + 32;
   B.px_full = bar + 40; B.py_full = bar + 48; B.o_full = bar + 56; B.o_free = bar + 72; B.v_full = bar + 88; B.k1_full = bar + 96; B.v_free = bar + 112; B.sx_full1 = bar + 120;
+  B.px_free = bar + 128;                       // (one-pass kernels: in the unused row-maximum exchange area)
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + bar_off + 104);
 
   // (the shuffle makes the warp index provably warp-uniform: role branches are then uniform branches and the code
@@ -232,6 +247,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(B.q_free, 1);
     mbar_init(B.sx_full, 1);
     mbar_init(B.sx_full1, 1);
+    if constexpr (OP) mbar_init(B.px_free, 1);
     mbar_init(B.sy_full, 1);
     mbar_init(B.px_full, 8);
     mbar_init(B.py_full, 8);
@@ -421,6 +437,9 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             issue_pv(0, KA / 16, o_col, false);
             if (KB == 0) at_commit(B.o_full + 8 * ob, leader);
           }
+          // (one-pass softmax: P.X(G + 1) is written before O(G) has been waited for -- its own signal that these MMAs
+          // have read P.X(G))
+          if constexpr (OP) at_commit(B.px_free, leader);
           if (XB == 1 && has_next) issue_scores_x(G + 1, last, next_tail, npar);
           const bool cur_y = KB > 0 && !cur_tail;
           if (cur_y) {
@@ -501,7 +520,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld_wait();
         uint32_t prow, ch0, sw;
         p_place(kk, prow, ch0, sw);
-        at_exp_chunk(v0, min(n, S - kk), scale_log2, nm, sum, prow, ch0, sw);
+        at_exp_chunk<OP>(v0, min(n, S - kk), scale_log2, nm, sum, prow, ch0, sw);
       }
       return (sum[0] + sum[1]) + (sum[2] + sum[3]);
     };
@@ -603,15 +622,22 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           x[2 * i + 1] = p2.y;
           m = fmaxf(m, fmaxf(p2.x, p2.y));
         }
+        if constexpr (!OP) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const float nm = -m * scale_log2;
+          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        }
+        const float nm = OP ? 0.0f : -m * scale_log2;
         float sum = 0.0f;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
           const int k = 64 * i + 2 * lane;
           const float p0 = fast_ex2(fmaf(x[2 * i], scale_log2, nm)), p1 = fast_ex2(fmaf(x[2 * i + 1], scale_log2, nm));
-          sum += p0 + p1;
+          if constexpr (OP) {                                 // (sum of the rounded values, as in at_exp_chunk)
+            const uint32_t pw = pack_bf16x2(p0, p1);
+            sum += __uint_as_float(pw << 16) + __uint_as_float(pw & 0xffff0000u);
+          } else {
+            sum += p0 + p1;
+          }
           if (k < KEYS) {                                     // P[qi][k], P[qi][k + 1] (zeros past the sequence)
             const int k2 = k - 64 * NP128;
             const uint32_t addr = k2 < 0 ? sbase + pt_off + (k >> 6) * 2048 + qi * 128 + (((((k & 63) >> 3)) ^ (qi & 7)) << 4) + (k & 7) * 2
@@ -649,56 +675,116 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // (one barrier per X buffer: the tensor core may commit the scores of tile G + 1 before these warps have looked
       // at the barrier of tile G -- on a single barrier that parity wait aliases and the CTA hangs)
       const uint32_t sx_bar = (XB == 2 && (G & 1)) ? B.sx_full1 : B.sx_full, sx_par = (XB == 2 ? G >> 1 : G) & 1;
-      if (is_tail) {
-        tail_scores(sx_bar, sx_par, xc);
-      } else if (cur) {
-#pragma unroll 1
-        for (int hf = 0; hf < (KB > 0 ? 2 : 1); ++hf) {       // X then Y: the Y scores land while X is scanned
-          AT_T(20 + hf);
-          at_wait(hf ? B.sy_full : sx_bar, hf ? yc & 1 : sx_par);
-          tc_fence_after();
-          AT_T(22 + hf);
-          if (live) m = pass1(hf ? yk0 : xk0, hf ? yn : xn, m, hf ? y_col - KA : xc);
-          AT_T(24 + hf);
-        }
-        xm[g * 128 + r] = m;
-      }
-      // partial maxima of tile G, partial sums of tile G - 1: shared by the two warps of a row -- except around a
-      // transposed tail tile, whose score table and row sums are shared by all eight softmax warps
-      if (is_tail || ptail) {
-        asm volatile("bar.sync 9, 256;" ::: "memory");
-        if (ptail && stage_ok) {                              // O(G - 2) was staged in the tail iteration with no P pass since:
-          if (lane == 0) bulk_wait_read<0>();                 // its TMA store must have read the staging rows
-          __syncwarp();
-        }
-      } else {
-        pair_sync();
-      }
-      AT_T(26);
-      if (G > 0) epilogue(G - 1, pb, phead, pt, ptail);
-      AT_T(27);
-      if (!cur) break;
-      if (is_tail) {
-        tail_softmax(G);
-        publish(B.px_full);
-        AT_T(55);
-      } else {
-        m = fmaxf(m, xm[(g ^ 1) * 128 + r]);
-        const float nm = -m * scale_log2;
+      if constexpr (OP) {
+        // ONE pass over the scores: the caller bounds |q k^T| / sqrt(d) (q and k come out of a LayerNorm whose scale
+        // and shift are known), so p = exp(s) cannot overflow and needs no row maximum; softmax is invariant to the
+        // reference.  Every score is read from TMEM once instead of twice, and nothing waits for the Y scores before
+        // the X exponentials start.  Order per tile: P.X(G) - output of tile G - 1 - P.Y(G).
+        const bool full = cur && !is_tail;
         float sum = 0.0f;
+        bool done = false;
 #pragma unroll 1
-        for (int hf = 0; hf < (KB > 0 ? 2 : 1); ++hf) {
-          if (hf && stage_ok) {                               // the staged O(G - 1) must have left shared memory
-            if (lane == 0) bulk_wait_read<0>();
+        for (int hf = 0; hf < 2; ++hf) {
+          if (full && (hf == 0 || KB > 0)) {
+            AT_T(20 + hf);
+            at_wait(hf ? B.sy_full : sx_bar, hf ? yc & 1 : sx_par);
+            tc_fence_after();
+            if (hf && stage_ok) {                             // the staged O(G - 1) must have left shared memory
+              if (lane == 0) bulk_wait_read<0>();
+              __syncwarp();
+            }
+            // the P V MMAs of tile G - 1 have read P.X (a transposed tail reads its own P^T region, and the tile in
+            // front of it was waited for through its O).  After an item's first tile this wait is exposed (~800 cycles
+            // per item: those MMAs have themselves waited for the item's V, which loads once the previous item's last
+            // P V has retired); waiting behind the first chunk's exponentials instead measured slower.
+            if (hf == 0 && G > 0 && !ptail) at_wait(B.px_free, (G - 1) & 1);
+            AT_T(22 + hf);
+            if (live) sum += pass2(hf ? yk0 : xk0, hf ? yn : xn, 0.0f, hf ? y_col - KA : xc);
+            AT_T(28 + hf);
+            publish(hf ? B.py_full : B.px_full);
+          }
+          if (hf == 0) {
+            if (is_tail) tail_scores(sx_bar, sx_par, xc);
+            // partial row sums of tile G - 1: shared by the two warps of a row -- except around a transposed tail tile,
+            // whose score table and row sums are shared by all eight softmax warps
+            if (is_tail || ptail) {
+              asm volatile("bar.sync 9, 256;" ::: "memory");
+              if (ptail && stage_ok) {                        // O(G - 2) was staged in the tail iteration with no P.Y pass since
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+              }
+            } else {
+              pair_sync();
+            }
+            AT_T(26);
+            if (G > 0) epilogue(G - 1, pb, phead, pt, ptail);
+            AT_T(27);
+            if (!full) {
+              done = !cur;
+              break;
+            }
+          }
+        }
+        if (done) break;
+        if (is_tail) {
+          tail_softmax(G);
+          publish(B.px_full);
+        } else {
+          xs[g * 128 + r] = sum;
+          if (KB > 0) ++yc;
+        }
+      } else {
+        if (is_tail) {
+          tail_scores(sx_bar, sx_par, xc);
+        } else if (cur) {
+  #pragma unroll 1
+          for (int hf = 0; hf < (KB > 0 ? 2 : 1); ++hf) {       // X then Y: the Y scores land while X is scanned
+            AT_T(20 + hf);
+            at_wait(hf ? B.sy_full : sx_bar, hf ? yc & 1 : sx_par);
+            tc_fence_after();
+            AT_T(22 + hf);
+            if (live) m = pass1(hf ? yk0 : xk0, hf ? yn : xn, m, hf ? y_col - KA : xc);
+            AT_T(24 + hf);
+          }
+          xm[g * 128 + r] = m;
+        }
+        // partial maxima of tile G, partial sums of tile G - 1: shared by the two warps of a row -- except around a
+        // transposed tail tile, whose score table and row sums are shared by all eight softmax warps
+        if (is_tail || ptail) {
+          asm volatile("bar.sync 9, 256;" ::: "memory");
+          if (ptail && stage_ok) {                              // O(G - 2) was staged in the tail iteration with no P pass since:
+            if (lane == 0) bulk_wait_read<0>();                 // its TMA store must have read the staging rows
             __syncwarp();
           }
-          if (live) sum += pass2(hf ? yk0 : xk0, hf ? yn : xn, nm, hf ? y_col - KA : xc);
-          AT_T(28 + hf);
-          publish(hf ? B.py_full : B.px_full);
-          AT_T(30 + hf);
+        } else {
+          pair_sync();
         }
-        xs[g * 128 + r] = sum;
-        if (KB > 0) ++yc;
+        AT_T(26);
+        if (G > 0) epilogue(G - 1, pb, phead, pt, ptail);
+        AT_T(27);
+        if (!cur) break;
+        if (is_tail) {
+          tail_softmax(G);
+          publish(B.px_full);
+          AT_T(55);
+        } else {
+          m = fmaxf(m, xm[(g ^ 1) * 128 + r]);
+          const float nm = -m * scale_log2;
+          float sum = 0.0f;
+  #pragma unroll 1
+          for (int hf = 0; hf < (KB > 0 ? 2 : 1); ++hf) {
+            if (hf && stage_ok) {                               // the staged O(G - 1) must have left shared memory
+              if (lane == 0) bulk_wait_read<0>();
+              __syncwarp();
+            }
+            if (live) sum += pass2(hf ? yk0 : xk0, hf ? yn : xn, nm, hf ? y_col - KA : xc);
+            AT_T(28 + hf);
+            publish(hf ? B.py_full : B.px_full);
+            AT_T(30 + hf);
+          }
+          xs[g * 128 + r] = sum;
+          if (KB > 0) ++yc;
+        }
       }
       pb = b;
       phead = head;
@@ -721,7 +807,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
-template <int D, int SQ>
+template <int D, int SQ, bool OP>
 static int launch_attn_tc5(const void *qkv, void *out, int B, int S, int h, cudaStream_t st) {
   const int C = h * D;
   const int KEYS = (S + 15) & ~15;
@@ -743,7 +829,7 @@ static int launch_attn_tc5(const void *qkv, void *out, int B, int S, int h, cuda
   if (int rc = make_tensor_map_bf16(qkv, (uint64_t)B * S, 3 * C, 3 * C, KEYS / nbox, 32, &tkv)) return rc;
   CUtensorMap to;                          // [B][S][C] output, 32-row x D/2-column boxes
   if (int rc = make_tensor_map_bf16_3d(out, B, S, C, 32, D / 2, &to)) return rc;
-  auto kern = attention_tc5_kernel<D, SQ>;
+  auto kern = attention_tc5_kernel<D, SQ, OP>;
   SDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device, cheap
   int dev = 0, sms = 0;
   SDP_CUDA(cudaGetDevice(&dev));
@@ -756,16 +842,24 @@ static int launch_attn_tc5(const void *qkv, void *out, int B, int S, int h, cuda
   return 0;
 }
 
-// -1: shape not covered (the caller falls back to the mma.sync kernel)
-int attention_tc5(const void *qkv, void *out, int B, int S, int h, int d, cudaStream_t st) {
+template <int D, int SQ>
+static int launch_attn_tc5_sq(const void *qkv, void *out, int B, int S, int h, bool one_pass, cudaStream_t st) {
+  return one_pass ? launch_attn_tc5<D, SQ, true>(qkv, out, B, S, h, st) : launch_attn_tc5<D, SQ, false>(qkv, out, B, S, h, st);
+}
+
+// -1: shape not covered (the caller falls back to the mma.sync kernel).  score_bound > 0: the caller guarantees
+// |q k^T| / sqrt(d) <= score_bound (nats) for every query / key pair; up to AT_ONE_PASS_BOUND the one-pass kernel runs
+// (p = exp(s) stays inside [e^-60, e^60], its row sums and P V inside fp32 with 38 decades to spare).
+int attention_tc5(const void *qkv, void *out, int B, int S, int h, int d, float score_bound, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (h * d) % 8) return -1;
+  const bool op = score_bound > 0.0f && score_bound <= AT_ONE_PASS_BOUND;
   switch (d) {
-    case 64: return S == 201 ? launch_attn_tc5<64, 201>(qkv, out, B, S, h, st) : launch_attn_tc5<64, 0>(qkv, out, B, S, h, st);
+    case 64: return S == 201 ? launch_attn_tc5_sq<64, 201>(qkv, out, B, S, h, op, st) : launch_attn_tc5_sq<64, 0>(qkv, out, B, S, h, op, st);
     case 96:
-      return S == 261   ? launch_attn_tc5<96, 261>(qkv, out, B, S, h, st)
-             : S == 201 ? launch_attn_tc5<96, 201>(qkv, out, B, S, h, st)
-                        : launch_attn_tc5<96, 0>(qkv, out, B, S, h, st);
-    case 128: return launch_attn_tc5<128, 0>(qkv, out, B, S, h, st);
+      return S == 261   ? launch_attn_tc5_sq<96, 261>(qkv, out, B, S, h, op, st)
+             : S == 201 ? launch_attn_tc5_sq<96, 201>(qkv, out, B, S, h, op, st)
+                        : launch_attn_tc5_sq<96, 0>(qkv, out, B, S, h, op, st);
+    case 128: return launch_attn_tc5_sq<128, 0>(qkv, out, B, S, h, op, st);
     default: return -1;
   }
 }

@@ -97,9 +97,13 @@ int encoder(const Ctx &c, const sdp_encoder_weights &w) {
   Fold f1; f1.s = w.s_qkv; f1.t = w.t_qkv; f1.eps = 1e-5f;
   if (int rc = gemm(c, xin, C, w.w_qkv, C, nullptr, M, 3 * C, C, SDP_ACT_NONE, nullptr, c.ws->qkv, 3 * C, dt, false,
                     fold ? &f1 : nullptr, false, fuse_qk ? &w : nullptr)) return rc;
-  if (int rc = sdp_attention(c.ws->qkv, fuse_qk ? nullptr : w.qn_w, fuse_qk ? nullptr : w.qn_b,
-                             fuse_qk ? nullptr : w.kn_w, fuse_qk ? nullptr : w.kn_b, c.ws->attn, c.B, c.S, m.n_head, d,
-                             1e-5f, dt, c.st)) return rc;
+  if (fuse_qk && w.qk_score_bound > 0.0f) {     // q, k normalised by the epilogue above, their scores bounded by its parameters
+    if (int rc = sdp_attention_bounded(c.ws->qkv, c.ws->attn, c.B, c.S, m.n_head, d, w.qk_score_bound, dt, c.st)) return rc;
+  } else if (int rc = sdp_attention(c.ws->qkv, fuse_qk ? nullptr : w.qn_w, fuse_qk ? nullptr : w.qn_b,
+                                    fuse_qk ? nullptr : w.kn_w, fuse_qk ? nullptr : w.kn_b, c.ws->attn, c.B, c.S, m.n_head, d,
+                                    1e-5f, dt, c.st)) {
+    return rc;
+  }
   if (int rc = gemm(c, c.ws->attn, C, w.w_o, C, nullptr, M, C, C, SDP_ACT_NONE, c.ws->act, c.ws->act, C, dt, false,
                     nullptr, fold)) return rc;
   if (!fold) {

@@ -76,11 +76,17 @@ void ln_dwconv(const at::Tensor &act, const at::Tensor &gamma, const at::Tensor 
 // layers.py:286-300: per-head q/k LayerNorm (optional) + softmax(q k^T / sqrt(d)) v on qkv [B, S, 3C]
 void attention(const at::Tensor &qkv, at::Tensor out, int64_t n_head, const c10::optional<at::Tensor> &qn_w,
                const c10::optional<at::Tensor> &qn_b, const c10::optional<at::Tensor> &kn_w, const c10::optional<at::Tensor> &kn_b,
-               double eps) {
+               double eps, double score_bound) {
   TORCH_CHECK(qkv.is_cuda() && out.is_cuda() && qkv.dim() == 3 && qkv.is_contiguous() && out.is_contiguous() &&
                   qkv.size(2) == 3 * out.size(2) && qkv.size(0) == out.size(0) && qkv.size(1) == out.size(1) && out.size(2) % n_head == 0,
               "sdpnet_b200::attention: qkv [B,S,3C] and out [B,S,C] must be contiguous");
   c10::cuda::CUDAGuard guard(qkv.device());
+  if (score_bound > 0.0 && !qn_w.has_value()) {   // q, k already normalised and their scores bounded: one-pass softmax
+    check(sdp_attention_bounded(qkv.data_ptr(), out.data_ptr(), (int)qkv.size(0), (int)qkv.size(1), (int)n_head,
+                                (int)(out.size(2) / n_head), (float)score_bound, dt(qkv), stream_of(qkv)),
+          "sdp_attention_bounded");
+    return;
+  }
   check(sdp_attention(qkv.data_ptr(), f32(qn_w, "qn_w"), f32(qn_b, "qn_b"), f32(kn_w, "kn_w"), f32(kn_b, "kn_b"), out.data_ptr(),
                       (int)qkv.size(0), (int)qkv.size(1), (int)n_head, (int)(out.size(2) / n_head), (float)eps, dt(qkv), stream_of(qkv)),
         "sdp_attention");
@@ -92,7 +98,7 @@ TORCH_LIBRARY(sdpnet_b200, m) {
   m.def("gemm(Tensor A, Tensor W, Tensor(a!) out, Tensor? bias, Tensor? residual, int act) -> ()");
   m.def("layernorm_rows(Tensor x, Tensor? w, Tensor? b, Tensor(a!) out, float eps) -> ()");
   m.def("ln_dwconv(Tensor act, Tensor gamma, Tensor beta, Tensor wdw, Tensor? bdw, Tensor(a!) out, int Gh, int Gw, int R, float eps) -> ()");
-  m.def("attention(Tensor qkv, Tensor(a!) out, int n_head, Tensor? qn_w, Tensor? qn_b, Tensor? kn_w, Tensor? kn_b, float eps) -> ()");
+  m.def("attention(Tensor qkv, Tensor(a!) out, int n_head, Tensor? qn_w, Tensor? qn_b, Tensor? kn_w, Tensor? kn_b, float eps, float score_bound=0.0) -> ()");
 }
 
 TORCH_LIBRARY_IMPL(sdpnet_b200, CUDA, m) {

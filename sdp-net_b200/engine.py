@@ -134,7 +134,10 @@ class Packer:
             w_ff1=self._w(g("ff_linear1.weight")), b_ff1=self._f(g("ff_linear1.bias")),
             w_ff2=self._w(g("ff_linear2.weight")), b_ff2=self._f(g("ff_linear2.bias")),
             s_qkv=None, t_qkv=None, s_ff1=None, t_ff1=None,
+            qk_score_bound=0.0,
         )
+        if w["qn_w"] is not None:    # what the per-head LayerNorm lets q . k / sqrt(d) reach: attention needs no row maximum
+            w["qk_score_bound"] = ops.qk_score_bound(w["qn_w"], w["qn_b"], w["kn_w"], w["kn_b"])
         if self.ln_fold:    # norm1 -> QKV and norm2 -> ff_linear1 folded (layers.py:280-284, 307-308)
             wqkv = torch.cat([g("q_proj.weight"), g("k_proj.weight"), g("v_proj.weight")], 0)
             w["w_qkv"], w["s_qkv"], w["t_qkv"] = self._fold(wqkv, g("norm1.weight"), g("norm1.bias"), None)
@@ -295,7 +298,7 @@ def run_encoder(pw: Packer, w: dict, bufs: Buffers, act_name: Optional[str] = No
     ops.gemm(xin, w["w_qkv"], bufs.qkv.view(M, 3 * C_), headnorm=hn,
              ln_fold=(st, 1e-5, w["s_qkv"], w["t_qkv"]) if fold else None)
     if hn is not None:
-        ops.attention(bufs.qkv, bufs.attn, pw.n_head, None, None, None, None, 1e-5)
+        ops.attention(bufs.qkv, bufs.attn, pw.n_head, None, None, None, None, 1e-5, score_bound=w["qk_score_bound"])
     else:
         ops.attention(bufs.qkv, bufs.attn, pw.n_head, w["qn_w"], w["qn_b"], w["kn_w"], w["kn_b"], 1e-5)
     lo = None if bufs.act_lo is None else bufs.act_lo.view(M, C_)       # split residual stream: both planes in place
@@ -377,8 +380,8 @@ class Engine:
         p = lambda t: None if t is None else t.data_ptr()
         enc = (L.EncoderWeights * len(pw.enc))()
         for i, w in enumerate(pw.enc):
-            for name, _ in L.EncoderWeights._fields_:
-                setattr(enc[i], name, p(w[name]))
+            for name, ctype in L.EncoderWeights._fields_:
+                setattr(enc[i], name, float(w[name]) if ctype is L.c_float else p(w[name]))
         mix = (L.MixerWeights * max(len(pw.mix), 1))()
         for i, w in enumerate(pw.mix):
             for name, _ in L.MixerWeights._fields_:

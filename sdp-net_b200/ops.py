@@ -210,15 +210,29 @@ def ln_dwconv_wants_stats(Gh: int, Gw: int, Cc: int, k: int, R: int, dtype: torc
 
 
 def attention(qkv: torch.Tensor, out: torch.Tensor, n_head: int, qn_w=None, qn_b=None, kn_w=None, kn_b=None,
-              eps: float = 1e-5) -> torch.Tensor:
+              eps: float = 1e-5, score_bound: float = 0.0) -> torch.Tensor:
     B, S, C3 = qkv.shape
     Cc = C3 // 3
     if not qkv.is_contiguous() or not out.is_contiguous() or out.shape != (B, S, Cc):
         raise ValueError("attention: qkv [B,S,3C] and out [B,S,C] must be contiguous")
+    if score_bound and qn_w is None:       # q, k already normalised, |q.k|/sqrt(d) <= score_bound: one-pass softmax
+        _call("sdp_attention_bounded", qkv, _p(qkv), _p(out), B, S, n_head, Cc // n_head, float(score_bound), _dt(qkv))
+        return out
     _call("sdp_attention", qkv, _p(qkv), _p(_f32(qn_w, "qn_w")), _p(_f32(qn_b, "qn_b")), _p(_f32(kn_w, "kn_w")),
                                   _p(_f32(kn_b, "kn_b")), _p(out), B, S, n_head, Cc // n_head, float(eps),
                                   _dt(qkv))
     return out
+
+
+def qk_score_bound(qn_w, qn_b, kn_w, kn_b) -> float:
+    """Upper bound of |q . k| / sqrt(d) (nats) for q = LayerNorm(.; qn_w, qn_b), k = LayerNorm(.; kn_w, kn_b) over d
+    (layers.py:286): a normalised vector has norm <= sqrt(d), so |LN(x)| <= max|w| sqrt(d) + |b|.  2 % on top for
+    the bf16 rounding of q and k."""
+    d = qn_w.numel()
+    rd = float(d) ** 0.5
+    nq = float(qn_w.detach().abs().max()) * rd + float(qn_b.detach().float().norm())
+    nk = float(kn_w.detach().abs().max()) * rd + float(kn_b.detach().float().norm())
+    return 1.02 * nq * nk / rd
 
 
 def pool_ln(act: torch.Tensor, row0: int, nrows: int, ln_w, ln_b, out: torch.Tensor, eps: float = 1e-5,

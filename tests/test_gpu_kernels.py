@@ -635,6 +635,99 @@ def test_attention_many_ctas_repeatable(sdp, S, h, d):
         assert (o[-24:].float() - attn_ref(qkv[-24:], h, None, None, None, None)).abs().max() < 2e-2
 
 
+def _score_bound(qkv, h):
+    """max |q| max |k| / sqrt(d): a valid bound of every score of the batch (nats)."""
+    B, S, C3 = qkv.shape
+    C = C3 // 3
+    d = C // h
+    q, k = qkv[..., :C].float().view(B, S, h, d), qkv[..., C:2 * C].float().view(B, S, h, d)
+    return float(q.norm(dim=-1).max() * k.norm(dim=-1).max() / math.sqrt(d)) * 1.001
+
+
+@pytest.mark.parametrize("S,h,d", [(261, 8, 96), (201, 8, 96), (201, 8, 64), (257, 2, 96), (133, 2, 128), (128, 2, 64), (5, 2, 64),
+                                   (16, 1, 64), (288, 2, 64), (272, 1, 128), (144, 3, 96), (208, 2, 128)])
+def test_attention_bounded_one_pass(sdp, S, h, d):
+    """sdp_attention_bounded: with a bound on |q k^T| / sqrt(d) the tcgen05 kernel takes exp(s) without a row maximum
+    (softmax is invariant to the exponent reference) -- same result as the two-pass kernel and the fp32 reference."""
+    B, C = 3, h * d
+    qkv = (rnd(B, S, 3 * C, seed=61) * 0.6).to(torch.bfloat16)
+    sb = _score_bound(qkv, h)
+    assert 0 < sb < 60
+    two = torch.full((B, S, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    one = torch.full_like(two, float("nan"))
+    sdp.ops.attention(qkv, two, h)
+    sdp.ops.attention(qkv, one, h, score_bound=sb)
+    ref = attn_ref(qkv, h, None, None, None, None)
+    assert torch.isfinite(one.float()).all()
+    assert (one.float() - ref).abs().max() < 2e-2
+    assert (one.float() - two.float()).abs().max() < 2e-2
+    # a bound past the one-pass limit (or none) is the two-pass kernel, bit for bit
+    far = torch.full_like(two, float("nan"))
+    sdp.ops.attention(qkv, far, h, score_bound=75.0)
+    assert torch.equal(far, two)
+
+
+def test_attention_bounded_extreme_rows(sdp):
+    """Rows whose scores sit at the ends of the bound: every score of a row at +bound or at -bound (exp(s) at e^+-40),
+    and a row with one dominant key.  Finite, and equal to the reference."""
+    S, h, d = 261, 8, 96
+    B, C = 2, h * d
+    g = _g(62)
+    k = torch.randn(B, S, h, d, generator=g, device="cuda")
+    k = k / k.norm(dim=-1, keepdim=True)
+    q = torch.randn(B, S, h, d, generator=g, device="cuda")
+    q = q / q.norm(dim=-1, keepdim=True)
+    amp = 40.0 * math.sqrt(d)                               # |q| |k| / sqrt(d) = 40 nats
+    q[:, 0] = k[:, 7]                                       # one dominant key: score +40 against ~0
+    q[:, 1] = -k[:, 9]                                      # one key at -40
+    k[:, 100:] = k[:, 100:101]                              # many identical keys ...
+    q[:, 2] = k[:, 100]                                     # ... all at +40 for this row
+    q[:, 3] = -k[:, 100]                                    # ... and at -40 for this one
+    v = torch.randn(B, S, h, d, generator=g, device="cuda")
+    qkv = torch.cat([(q * amp).reshape(B, S, C), k.reshape(B, S, C), v.reshape(B, S, C)], -1).to(torch.bfloat16).contiguous()
+    sb = _score_bound(qkv, h)
+    assert 39 < sb < 42
+    out = torch.full((B, S, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    sdp.ops.attention(qkv, out, h, score_bound=sb)
+    ref = attn_ref(qkv, h, None, None, None, None)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max() < 3e-2
+
+
+@pytest.mark.parametrize("S,h,d", [(261, 8, 96), (201, 8, 64), (133, 2, 128)])
+def test_attention_bounded_many_ctas_repeatable(sdp, S, h, d):
+    B, C = 1200 // h * 2, h * d
+    qkv = (rnd(B, S, 3 * C, seed=63) * 0.6).to(torch.bfloat16)
+    sb = _score_bound(qkv, h)
+    outs = []
+    for _ in range(3):
+        o = torch.full((B, S, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+        sdp.ops.attention(qkv, o, h, score_bound=sb)
+        outs.append(o)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    for sl in (slice(0, 24), slice(B - 24, B)):
+        assert (outs[0][sl].float() - attn_ref(qkv[sl], h, None, None, None, None)).abs().max() < 2e-2
+
+
+def test_qk_score_bound_holds_for_layernormed_heads(sdp):
+    """ops.qk_score_bound (what the engine hands to sdp_attention_bounded): no score of LayerNorm-ed, bf16-rounded
+    q and k exceeds it (layers.py:286,289-291)."""
+    d, n = 96, 4096
+    g = _g(64)
+    for scale, shift in ((1.0, 0.0), (1.7, 0.4), (0.3, 2.0)):
+        qw = 1 + 0.3 * torch.randn(d, generator=g, device="cuda") * scale
+        kw = 1 + 0.3 * torch.randn(d, generator=g, device="cuda") * scale
+        qb, kb = shift * torch.randn(d, generator=g, device="cuda"), shift * torch.randn(d, generator=g, device="cuda")
+        x, y = torch.randn(n, d, generator=g, device="cuda") * 5 + 3, torch.randn(n, d, generator=g, device="cuda")
+        y[: n // 2] = x[: n // 2]                           # aligned pairs: where the bound is approached
+        q = F.layer_norm(x, (d,), qw, qb, 1e-5).bfloat16().float()
+        k = F.layer_norm(y, (d,), kw, kb, 1e-5).bfloat16().float()
+        smax = float((q @ k.t()).abs().max()) / math.sqrt(d)
+        assert smax <= sdp.ops.qk_score_bound(qw, qb, kw, kb)
+
+
 @pytest.mark.parametrize("B,K,ls", [(37, 100, 0.0), (512, 1000, 0.1), (3, 7, 0.0)])
 def test_eval_metrics_kernel(sdp, B, K, ls):
     """On-device CE / BCE / top-1 accumulation (model_test.py:76-85) against the oracle's definition."""
