@@ -215,7 +215,7 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, n_head: int, qn_w=None, qn_b
     Cc = C3 // 3
     if not qkv.is_contiguous() or not out.is_contiguous() or out.shape != (B, S, Cc):
         raise ValueError("attention: qkv [B,S,3C] and out [B,S,C] must be contiguous")
-    if score_bound and qn_w is None:       # q, k already normalised, |q.k|/sqrt(d) <= score_bound: one-pass softmax
+    if score_bound > 0 and qn_w is None:   # q, k already normalised, |q.k|/sqrt(d) <= score_bound: one-pass softmax
         _call("sdp_attention_bounded", qkv, _p(qkv), _p(out), B, S, n_head, Cc // n_head, float(score_bound), _dt(qkv))
         return out
     _call("sdp_attention", qkv, _p(qkv), _p(_f32(qn_w, "qn_w")), _p(_f32(qn_b, "qn_b")), _p(_f32(kn_w, "kn_w")),

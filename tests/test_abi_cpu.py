@@ -120,3 +120,27 @@ def test_constructor_defaults_and_init_match_reference_contract(sdp):
         sdp.MainModel(activation="fast_gelu")
     with pytest.raises(AssertionError):
         sdp.StochasticDepth(0.0)
+
+
+def test_qk_score_bound_is_an_upper_bound(sdp):
+    """`ops.qk_score_bound` (handed to sdp_attention_bounded as the exponent range of the one-pass softmax): pure host
+    arithmetic on the q_norm / k_norm parameters (layers.py:236-237,286); no score of LayerNorm-ed, bf16-rounded q and k
+    may exceed it, aligned pairs come close."""
+    import math
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    for d in (32, 64, 96):
+        for scale, shift in ((0.0, 0.0), (1.0, 0.2), (2.0, 1.5)):
+            qw, kw = 1 + 0.3 * scale * torch.randn(d, generator=g), 1 + 0.3 * scale * torch.randn(d, generator=g)
+            qb, kb = shift * torch.randn(d, generator=g), shift * torch.randn(d, generator=g)
+            x = torch.randn(2048, d, generator=g) * 4 + 1
+            y = torch.randn(2048, d, generator=g)
+            y[:1024] = x[:1024]
+            q = F.layer_norm(x, (d,), qw, qb, 1e-5).bfloat16().float()
+            k = F.layer_norm(y, (d,), kw, kb, 1e-5).bfloat16().float()
+            smax = float((q @ k.t()).abs().max()) / math.sqrt(d)
+            bound = sdp.ops.qk_score_bound(qw, qb, kw, kb)
+            assert smax <= bound
+            if scale == 0.0:
+                assert bound == pytest.approx(1.02 * math.sqrt(d)) and smax > 0.9 * math.sqrt(d)
