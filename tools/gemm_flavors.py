@@ -48,9 +48,9 @@ def main():
         ("pw +gelu +res(hi+lo) +pass +stats", C, C, lambda: sdp.ops.gemm(qkv[:, :C], W["o"], hi, act="gelu", residual=hi, stats_out=stats,
                                                                        residual_lo=lo, out_lo=lo, pass_rows=(S, R))),
     ]
-    only = os.environ.get("GEMM_FLAVORS_ONLY")               # e.g. "ff1": the flavours whose name starts with it
+    only = os.environ.get("GEMM_FLAVORS_ONLY")               # e.g. "ff1,o ": the flavours whose names start with one of these
     for name, N, K, fn in flavours:
-        if only and not name.startswith(only):
+        if only and not any(name.startswith(o) for o in only.split(",")):
             continue
         # keep the stream finite over thousands of in-place accumulations
         hi.copy_(x.bfloat16())
