@@ -268,11 +268,16 @@ ln_dwconv_slab_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_con
       for (int hh = 0; hh < 2; ++hh) {
         const int y = g + 8 * hh, x = 8 * n + 2 * q;
         if (y < Gh) {
+          // the bank of a store depends on the token's parity, q and the warp only -- not on y -- so lanes of odd g take
+          // the two tokens of their pair in the other order: eight bank positions per instruction instead of four
+          const uint32_t lo_e[2] = {pack_bf16x2(acc[0][n][2 * hh], acc[1][n][2 * hh]), pack_bf16x2(acc[0][n][2 * hh + 1], acc[1][n][2 * hh + 1])};
+          const uint32_t hi_e[2] = {pack_bf16x2(acc[2][n][2 * hh], acc[3][n][2 * hh]), pack_bf16x2(acc[2][n][2 * hh + 1], acc[3][n][2 * hh + 1])};
+          const bool odd = g & 1;
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const uint32_t lo2 = pack_bf16x2(acc[0][n][2 * hh + e], acc[1][n][2 * hh + e]);
-            const uint32_t hi2 = pack_bf16x2(acc[2][n][2 * hh + e], acc[3][n][2 * hh + e]);
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(otile_addr + (y * 16 + x + e) * DS_RAWP +
+            const int ee = e ^ (int)odd;
+            const uint32_t lo2 = odd ? lo_e[e ^ 1] : lo_e[e], hi2 = odd ? hi_e[e ^ 1] : hi_e[e];
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(otile_addr + (y * 16 + x + ee) * DS_RAWP +
                                                                   ((((warp >> 1) ^ q) << 4) | ((warp & 1) << 3))),
                          "r"(lo2), "r"(hi2)
                          : "memory");
