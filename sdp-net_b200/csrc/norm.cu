@@ -374,6 +374,53 @@ im2col_pairs_kernel(const TI *__restrict__ x, TO *__restrict__ A, int ldA, int B
   }
 }
 
+// One CTA per row of patches (b, ii): the 3 x p image rows of that patch row arrive in shared memory with coalesced
+// loads (converted to the output type), then every patch's im2col row [3 p p | zero padding up to ldA] leaves as one
+// contiguous run of pairs.  The pair kernel above writes each patch row in p-element pieces (28 bytes at p = 14:
+// partial, misaligned sectors); this one moves the same bytes in full lines.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+im2col_rows_kernel(const TI *__restrict__ x, TO *__restrict__ A, int ldA, int H, int W, int p, int Gh, int Gw) {
+  extern __shared__ __align__(16) uint8_t i2c_raw[];
+  TO *tile = reinterpret_cast<TO *>(i2c_raw);                // [3][p][Wc], Wc = Gw * p
+  const int b = blockIdx.x / Gh, ii = blockIdx.x - b * Gh;
+  const int Wc = Gw * p, wp = Wc >> 1, rows = 3 * p;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < rows * wp; i += blockDim.x) {
+    const int r = i / wp, w2 = (i - r * wp) * 2;             // r = c * p + dy
+    const int c = r / p, dy = r - c * p;
+    const TI *src = x + ((long long)(b * 3 + c) * H + ii * p + dy) * W + w2;
+    float v0, v1;
+    if constexpr (sizeof(TI) == 4) {
+      const float2 t = *reinterpret_cast<const float2 *>(src);
+      v0 = t.x; v1 = t.y;
+    } else {
+      const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(src));
+      v0 = t.x; v1 = t.y;
+    }
+    if constexpr (sizeof(TO) == 4) *reinterpret_cast<float2 *>(tile + r * Wc + w2) = make_float2(v0, v1);
+    else *reinterpret_cast<uint32_t *>(tile + r * Wc + w2) = pack_bf16x2(v0, v1);
+  }
+  __syncthreads();
+  const int Kc = 3 * p * p, lp = ldA >> 1, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < Gw; j += blockDim.x >> 5) {         // one warp per patch: consecutive lanes, consecutive pairs
+    TO *row = A + ((long long)(b * Gh + ii) * Gw + j) * ldA;
+#pragma unroll 4
+    for (int k2 = lane; k2 < lp; k2 += 32) {
+      const int k = 2 * k2;
+      if (k < Kc) {
+        const int r = k / p, dx = k - r * p;                 // r = c * p + dy (p even: a pair never leaves its tap row)
+        const TO *src = tile + r * Wc + j * p + dx;
+        if constexpr (sizeof(TO) == 4) *reinterpret_cast<float2 *>(row + k) = *reinterpret_cast<const float2 *>(src);
+        else *reinterpret_cast<uint32_t *>(row + k) = *reinterpret_cast<const uint32_t *>(src);
+      } else {
+        if constexpr (sizeof(TO) == 4) *reinterpret_cast<float2 *>(row + k) = make_float2(0.0f, 0.0f);
+        else *reinterpret_cast<uint32_t *>(row + k) = 0u;
+      }
+    }
+  }
+}
+
 // one warp per row: log-sum-exp cross-entropy, smoothed-target BCE-with-logits, first-max argmax
 __global__ void __launch_bounds__(256)
 eval_metrics_kernel(const float *__restrict__ logits, long long ldl, const long long *__restrict__ labels, int B, int K,
@@ -555,6 +602,18 @@ extern "C" int sdp_im2col_patches(const void *x, int x_dtype, void *A, int a_dty
   const size_t xs = dtype_size(x_dtype), as = dtype_size(a_dtype);
   const bool pairs = p % 2 == 0 && W % 2 == 0 && ldA % 2 == 0 && ldA < (1 << 24) && (long long)B * Gh * Gw < (1ll << 31) &&
                      (reinterpret_cast<uintptr_t>(x) % (2 * xs)) == 0 && (reinterpret_cast<uintptr_t>(A) % (2 * as)) == 0;
+  // whole patch rows staged in shared memory when they fit (every reference geometry does: 3 * 14 * 224 values)
+  const size_t tile_bytes = (size_t)3 * p * (Gw * p) * as;
+  if (pairs && tile_bytes <= 48 * 1024 && (long long)B * Gh < (1ll << 31)) {
+#define I2R(TI, TO) im2col_rows_kernel<TI, TO><<<B * Gh, 256, tile_bytes, st>>>((const TI *)x, (TO *)A, (int)ldA, H, W, p, Gh, Gw)
+    if (x_dtype == SDP_F32 && a_dtype == SDP_BF16) I2R(float, bf16);
+    else if (x_dtype == SDP_F32) I2R(float, float);
+    else if (a_dtype == SDP_BF16) I2R(bf16, bf16);
+    else I2R(bf16, float);
+#undef I2R
+    SDP_LAUNCH_OK();
+    return 0;
+  }
   if (pairs) {
     const int gp = grid_for((long long)B * 3 * H * (W / 2));
 #define I2P(TI, TO) im2col_pairs_kernel<TI, TO><<<gp, 256, 0, st>>>((const TI *)x, (TO *)A, (int)ldA, B, H, W, p, Gh, Gw)
